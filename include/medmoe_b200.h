@@ -1,0 +1,154 @@
+/* medmoe_b200 — C ABI of the B200-native (sm_100a) MoE + contrastive-loss hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (shivangchopra11/MedMoE) is pure Python and has no FFI of its own; each entry point
+ * below names the reference code it replaces (paths relative to the reference root).
+ * A Python host binds these with ctypes (medmoe_b200/_lib.py); INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it is documented as "host"; the caller owns
+ *     all memory (incl. workspaces) — the library allocates nothing and keeps no pointers;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises;
+ *   - return value: 0 = ok, negative = mm_status below; mm_last_error() gives the text
+ *     (thread-local: autograd's backward runs on a worker thread);
+ *   - bf16 buffers are passed as void*; "rows" buffers use the expert-sorted, 128-row
+ *     padded layout produced by mm_dispatch_build.
+ */
+#ifndef MEDMOE_B200_H
+#define MEDMOE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum mm_status {
+    MM_OK = 0,
+    MM_ERR_BAD_SHAPE = -1,
+    MM_ERR_MISALIGNED = -2,
+    MM_ERR_UNSUPPORTED = -3,
+    MM_ERR_CUDA = -4,
+    MM_ERR_NO_DEVICE = -5,
+    MM_ERR_WORKSPACE = -6
+};
+
+enum mm_epilogue_flags { MM_EPI_RELU = 1, MM_EPI_ZERO_PAD = 2 };
+
+const char* mm_last_error(void);
+int mm_abi_version(void);
+int mm_device_sm_count(void);
+
+/* ---- (1) router gate: softmax + top-k -------------------------------------------------
+ * replaces src/models/components/swin.py:98-100 (router MLP, softmax, argmax).
+ * x [B, D] fp32; W1 [128, D], b1 [128], W2 [K, 128], b2 [K] fp32.
+ * out: hidden [B, 128] (post-ReLU, saved for backward), probs [B, K], topk_idx [B, topk] int32
+ * (first maximum wins, as torch.argmax), topk_w [B, topk] (1.0 when topk == 1, else the
+ * selected probs renormalised to sum 1). */
+int mm_router_topk(const float* x, int B, int D, const float* W1, const float* b1, const float* W2, const float* b2,
+                   int K, int topk, float* hidden, float* probs, int32_t* topk_idx, float* topk_w, void* stream);
+
+/* gradient of the returned probabilities (the only gradient path into the router:
+ * src/models/medmoe_module.py:235-237 applies cross-entropy to them).
+ * out: dlogit [B, K], dhidden [B, 128] scratch; dx [B, D] (may be NULL); dW1, db1, dW2, db2. */
+int mm_router_bwd(const float* dprobs, const float* probs, const float* hidden, const float* x, const float* W1,
+                  const float* W2, int B, int D, int K, float* dlogit, float* dhidden, float* dx, float* dW1,
+                  float* db1, float* dW2, float* db2, void* stream);
+
+/* ---- (2) dispatch ---------------------------------------------------------------------
+ * replaces the dense "run all experts, stack, gather" of swin.py:105-108 with a counting
+ * sort of the (image, choice) items by expert.  All arrays int32.
+ *   P[S], region_base[S], region_tiles[S], chunk_base[S], chunk_cap[S], chunk_tiles[S] : HOST arrays
+ *   out: counts [K], offsets [K+1], perm [n] slot->item, inv_perm [n] item->slot, slot_expert [n],
+ *        seg_start [S, K] first global row of expert e in region s, slot_row [S, n],
+ *        tile_info [sum region_tiles][2] = {expert | -1, valid rows}, chunks [sum chunk_cap][4] =
+ *        {expert, first tile, tiles, scale}. */
+int mm_dispatch_build(const int32_t* item_expert, int n_items, int K, int S, const int32_t* P,
+                      const int32_t* region_base, const int32_t* region_tiles, const int32_t* chunk_base,
+                      const int32_t* chunk_cap, const int32_t* chunk_tiles, int32_t* counts, int32_t* offsets,
+                      int32_t* perm, int32_t* inv_perm, int32_t* slot_expert, int32_t* seg_start, int32_t* slot_row,
+                      int32_t* tile_info, int32_t* chunks, void* stream);
+
+/* permute the S stage-feature tensors (swin.py:139 `stage_feats`, [B, P_s, D_s], fp32 or bf16)
+ * into expert-sorted bf16 row segments, zeroing segment padding.  src/dst: HOST arrays of S device pointers. */
+int mm_dispatch_rows(const void* const* src, int src_is_f32, void* const* dst, int n_items, int topk, int K, int S,
+                     const int32_t* P, const int32_t* D, const int32_t* region_base, const int32_t* perm,
+                     const int32_t* slot_row, const int32_t* counts, const int32_t* seg_start, void* stream);
+/* transpose of mm_dispatch_rows for the stage-feature gradients (sums the top-k slots of an image). */
+int mm_undispatch_rows(const void* const* src, void* const* dst, int dst_is_f32, int n_images, int topk, int S,
+                       const int32_t* P, const int32_t* D, const int32_t* region_base, const int32_t* inv_perm,
+                       const int32_t* slot_row, void* stream);
+
+int mm_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+int mm_transpose_cast_f32_bf16(const float* src, void* dst, int batch, int R, int C, void* stream);
+
+/* ---- (3) grouped expert GEMMs on tcgen05 / TMEM / TMA ----------------------------------
+ * replaces Expert.proj_convs (Conv1d k=1 + ReLU, swin.py:18-23,41) and Expert.attn_proj[0]
+ * (Linear(768,384), swin.py:26-27,63) and their autograd.
+ *   out[rows, N] = epi(out_scale * A[rows, K] W_e[N, K]^T + bias_e + aux) masked by gate > 0
+ * A, W, aux, gate bf16; out bf16 (or fp32 when out_f32); bias, colsum fp32 [E, N].
+ * tile_info == NULL: one dense problem of M rows with expert 0. */
+int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                         long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
+                         const float* bias, const void* aux, long long ld_aux, const void* gate, long long ld_gate,
+                         void* out, long long ld_out, int out_f32, float* colsum, float out_scale, int flags,
+                         void* stream);
+/* dW[e][N1, N2] += sum_{rows of expert e} A[row, N1]^T B[row, N2]  (fp32 red.add; caller zeroes dW). */
+int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
+                          int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,
+                          int tile_base, float* out, void* stream);
+
+/* ---- (4) interpolate + scale-softmax + weighted combine / scatter-back ------------------
+ * replaces swin.py:42-80 (F.interpolate, stack/permute, attn_proj[1:], softmax over scales,
+ * weighted sum) and swin.py:108-113 (gather, mean, local_feat layout).
+ * Y [rows, D], Z [rows, D/2] bf16; w2 [E, D/2], b2 [E] fp32; Ps HOST [4].
+ * out [B, P, D] (bf16 or fp32), beta [n_items, P, 4], gpart [B, nblk, D] scratch, global_feat [B, D] fp32. */
+int mm_combine_num_token_blocks(int P);
+int mm_combine_num_row_blocks(const int32_t* Ps);
+int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk, int P,
+                                  const int32_t* Ps, int D, const int32_t* inv_perm, const int32_t* slot_expert,
+                                  const int32_t* slot_row, const float* gate, float* beta, void* out, int out_f32,
+                                  float* gpart, float* global_feat, void* stream);
+/* backward: dlocal [B, P, D] (bf16/fp32, may be NULL), dglobal [B, D] fp32 (may be NULL) ->
+ * dlogit [n_items, P, 4], dgate [n_items] (+=, may be NULL), dUT [rows, D] bf16, dZ [rows, D/2] bf16,
+ * part [n_items, nrb, D + 1] scratch, dw2_db1_db2 [K, D + 1] = per expert {dw2 (D/2) | db1 (D/2) | db2}. */
+int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
+                                  const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,
+                                  const int32_t* slot_expert, const int32_t* slot_row, const int32_t* counts,
+                                  const int32_t* seg_start, const int32_t* offsets, const float* gate,
+                                  const float* beta, const void* dlocal, int dlocal_f32, const float* dglobal,
+                                  float* dlogit, float* dgate, void* dUT, void* dZ, float* part, float* dw2_db1_db2,
+                                  void* stream);
+
+/* ---- (5) global contrastive loss -------------------------------------------------------
+ * GLORIA semantics: replaces GLORIAGlobalContrastiveLoss.forward, src/losses.py:766-794.
+ * img, txt [B, D] fp32; ws = mm_gloria_workspace_floats(B) floats kept from fwd to bwd. */
+long long mm_gloria_workspace_floats(int B);
+int mm_gloria_global_fwd(const float* img, const float* txt, int B, int D, float temp, float eps, float* ws,
+                         float* loss, void* stream);
+int mm_gloria_global_bwd(const float* img, const float* txt, int B, int D, float temp, float eps, float* ws,
+                         const float* gout, float* dimg, float* dtxt, void* stream);
+/* FLAVA / CLIP semantics, one direction: replaces contrastive_loss_with_temperature,
+ * src/losses.py:527-592 (the all-gather of :503-524 stays in torch.distributed).
+ * logits [R, N] = *logit_scale_exp * a b_all^T; labels = label0 + row; loss = sum_r w_r (lse_r - logits[r, label]),
+ * w == NULL means 1/R. */
+int mm_infonce_fwd(const float* a, const float* b_all, int R, int N, int D, const float* logit_scale_exp, int label0,
+                   const float* row_w, float* logits, float* lse, float* picked, float* loss, void* stream);
+int mm_infonce_bwd(const float* a, const float* b_all, int R, int N, int D, const float* logit_scale_exp, int label0,
+                   const float* row_w, const float* logits, const float* lse, const float* gout, float gmul,
+                   float* dlogits, float* row_tmp, float* da, float* db_all, float* dscale, int accumulate_dscale,
+                   void* stream);
+int mm_l2_normalize_fwd(const float* x, int R, int D, float eps, float* y, float* norms, void* stream);
+int mm_l2_normalize_bwd(const float* dy, const float* y, const float* norms, int R, int D, float eps, float* dx,
+                        void* stream);
+
+/* ---- zero-shot classification (BASELINE config 5; src/eval_zs.py is empty in the reference,
+ * semantics from SURVEY §8a row Z): pred[m] = argmax_c cos(img_m, txt_c), first maximum wins. */
+int mm_zeroshot_argmax(const float* img, const float* txt, int M, int C, int D, float eps, long long* pred, float* sim,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDMOE_B200_H */

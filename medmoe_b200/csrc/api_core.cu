@@ -1,0 +1,256 @@
+// medmoe_b200 — C-ABI core: error state, device queries, TMA descriptor encoding and the
+// grouped-GEMM entry points.  See include/medmoe_b200.h for the contract.
+#include "api_internal.h"
+#include "gemm.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace mm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA error %d (%s)", what, static_cast<int>(e), cudaGetErrorString(e));
+        return MM_ERR_CUDA;
+    }
+    return MM_OK;
+}
+
+int sm_count() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time through the runtime API so that the library still loads
+// (and exports its symbols) on a box without a driver; compute calls then fail loudly.
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_rows, const char* what) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver)", what);
+        return MM_ERR_NO_DEVICE;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride * 2) % 16 != 0) {
+        set_error("%s: TMA operand must be 16-byte aligned with a 16-byte multiple row pitch", what);
+        return MM_ERR_MISALIGNED;
+    }
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_stride * 2};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu pitch=%llu box=%ux%u)", what,
+                  static_cast<int>(r), (unsigned long long)inner, (unsigned long long)rows,
+                  (unsigned long long)row_stride, box_inner, box_rows);
+        return MM_ERR_CUDA;
+    }
+    return MM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+template <int BN, bool OUT_F32>
+static int launch_rows(const CUtensorMap& tA, const CUtensorMap& tB, const RowsGemmArgs& args, cudaStream_t st) {
+    constexpr int STAGES = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
+    using S = GemmSmem<BN, STAGES>;
+    auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32>;
+    static bool configured = false;   // benign race: attribute set is idempotent
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("gemm_rows: cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            return MM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int work = args.tile_count * args.n_tiles;
+    const int grid = work < sm_count() ? work : sm_count();
+    if (grid <= 0) return MM_OK;
+    kern<<<grid, 256, S::TOTAL, st>>>(tA, tB, args);
+    return check_launch("gemm_rows");
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const WgradArgs& args, cudaStream_t st) {
+    constexpr int STAGES = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
+    using S = GemmSmem<BN, STAGES>;
+    auto kern = gemm_wgrad_kernel<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("gemm_wgrad: cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            return MM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int work = args.chunk_count * args.n_i * args.n_j;
+    const int grid = work < sm_count() ? work : sm_count();
+    if (grid <= 0) return MM_OK;
+    kern<<<grid, 256, S::TOTAL, st>>>(tA, tB, args);
+    return check_launch("gemm_wgrad");
+}
+
+static int pick_bn_rows(int N) {
+    const int cands[] = {256, 192, 128, 96, 64, 32};
+    for (int c : cands)
+        if (N % c == 0) return c;
+    return 0;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" const char* mm_last_error(void) { return g_err; }
+
+extern "C" int mm_abi_version(void) { return 1; }
+
+extern "C" int mm_device_sm_count(void) { return sm_count(); }
+
+// C[rows, N] = epi(A[rows, K] * W[e][N, K]^T) over 128-row tiles; see include/medmoe_b200.h.
+extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                                    long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
+                                    const float* bias, const void* aux, long long ld_aux, const void* gate,
+                                    long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
+                                    float out_scale, int flags, void* stream) {
+    MM_REQUIRE(A && W && out, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: null operand");
+    MM_REQUIRE(K > 0 && K % 8 == 0 && N > 0 && E > 0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: K must be a positive multiple of 8");
+    const int BN = pick_bn_rows(N);
+    MM_REQUIRE(BN != 0, MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: N must be a multiple of 32");
+    if (!tile_info) {
+        MM_REQUIRE(M >= 0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: M < 0");
+        tile_count = (M + TILE_M - 1) / TILE_M;
+        tile_begin = 0;
+    }
+    if (tile_count <= 0) return MM_OK;
+    MM_REQUIRE((ld_out * (out_f32 ? 4 : 2)) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, MM_ERR_MISALIGNED,
+               "mm_grouped_gemm_rows: out must be 16-byte aligned");
+    MM_REQUIRE(!aux || ((ld_aux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0), MM_ERR_MISALIGNED,
+               "mm_grouped_gemm_rows: aux must be 16-byte aligned");
+    MM_REQUIRE(!gate || ((ld_gate * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0), MM_ERR_MISALIGNED,
+               "mm_grouped_gemm_rows: gate must be 16-byte aligned");
+    CUtensorMap tA, tB;
+    int rc = encode_tmap_bf16(&tA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(a_rows), static_cast<uint64_t>(lda), 64,
+                              TILE_M, "mm_grouped_gemm_rows(A)");
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64, BN,
+                          "mm_grouped_gemm_rows(W)");
+    if (rc) return rc;
+    RowsGemmArgs g;
+    g.tile_info = reinterpret_cast<const int2*>(tile_info);
+    g.tile_begin = tile_begin;
+    g.tile_count = tile_count;
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.n_tiles = N / BN;
+    g.bias = bias;
+    g.aux = static_cast<const __nv_bfloat16*>(aux);
+    g.ld_aux = ld_aux;
+    g.gate = static_cast<const __nv_bfloat16*>(gate);
+    g.ld_gate = ld_gate;
+    g.out = out;
+    g.ld_out = ld_out;
+    g.colsum = colsum;
+    g.out_scale = out_scale;
+    g.flags = flags;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MM_ROWS_CASE(bn)                                                   \
+    case bn:                                                               \
+        return out_f32 ? launch_rows<bn, true>(tA, tB, g, st) : launch_rows<bn, false>(tA, tB, g, st);
+    switch (BN) {
+        MM_ROWS_CASE(256)
+        MM_ROWS_CASE(192)
+        MM_ROWS_CASE(128)
+        MM_ROWS_CASE(96)
+        MM_ROWS_CASE(64)
+        MM_ROWS_CASE(32)
+    }
+#undef MM_ROWS_CASE
+    set_error("mm_grouped_gemm_rows: unreachable tile width %d", BN);
+    return MM_ERR_UNSUPPORTED;
+}
+
+// dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e.
+extern "C" int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B,
+                                     long long b_rows, int N2, long long ldb, const int32_t* chunks, int chunk_begin,
+                                     int chunk_count, int tile_base, float* out, void* stream) {
+    MM_REQUIRE(A && B && out && chunks, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_wgrad: null operand");
+    MM_REQUIRE(N1 > 0 && N1 % 8 == 0 && N2 > 0 && N2 % 8 == 0, MM_ERR_BAD_SHAPE,
+               "mm_grouped_gemm_wgrad: N1, N2 must be positive multiples of 8");
+    if (chunk_count <= 0) return MM_OK;
+    int BN;
+    if (N2 % 256 == 0) BN = 256;
+    else if (N2 % 192 == 0) BN = 192;
+    else if (N2 <= 64) BN = 64;
+    else if (N2 <= 128) BN = 128;
+    else if (N2 <= 192) BN = 192;
+    else BN = 256;
+    CUtensorMap tA, tB;
+    int rc = encode_tmap_bf16(&tA, A, static_cast<uint64_t>(N1), static_cast<uint64_t>(a_rows), static_cast<uint64_t>(lda), 64, 64,
+                              "mm_grouped_gemm_wgrad(A)");
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tB, B, static_cast<uint64_t>(N2), static_cast<uint64_t>(b_rows), static_cast<uint64_t>(ldb), 64, 64,
+                          "mm_grouped_gemm_wgrad(B)");
+    if (rc) return rc;
+    WgradArgs g;
+    g.chunks = reinterpret_cast<const int4*>(chunks);
+    g.chunk_begin = chunk_begin;
+    g.chunk_count = chunk_count;
+    g.tile_base = tile_base;
+    g.N1 = N1;
+    g.N2 = N2;
+    g.n_i = (N1 + TILE_M - 1) / TILE_M;
+    g.n_j = (N2 + BN - 1) / BN;
+    g.out = out;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (BN) {
+        case 256: return launch_wgrad<256>(tA, tB, g, st);
+        case 192: return launch_wgrad<192>(tA, tB, g, st);
+        case 128: return launch_wgrad<128>(tA, tB, g, st);
+        case 64: return launch_wgrad<64>(tA, tB, g, st);
+    }
+    set_error("mm_grouped_gemm_wgrad: unreachable tile width %d", BN);
+    return MM_ERR_UNSUPPORTED;
+}

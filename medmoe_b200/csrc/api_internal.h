@@ -1,0 +1,28 @@
+// medmoe_b200 — internals shared by the C-ABI translation units (error state, launch checks,
+// TMA descriptor encoding).  The public contract is include/medmoe_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace mm {
+// thread-local last-error text (backward runs on the autograd engine's worker thread)
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+// 2-D bf16 tensor map, 128-byte swizzle.  inner = contiguous extent (elements), rows = outer extent,
+// row_stride = elements between rows, box = {box_inner (<= 64), box_rows (<= 256)}.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_rows, const char* what);
+int sm_count();
+}  // namespace mm
+
+#define MM_REQUIRE(cond, code, msg)        \
+    do {                                   \
+        if (!(cond)) {                     \
+            mm::set_error("%s", msg);      \
+            return code;                   \
+        }                                  \
+    } while (0)
+
+static inline int mm_check_launch(const char* what) { return mm::check_launch(what); }

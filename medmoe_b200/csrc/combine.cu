@@ -1,0 +1,543 @@
+// medmoe_b200 — interpolate + scale-softmax + weighted combine / scatter-back
+// (north-star kernel 4; SURVEY §2.2 rows E2,E3,E5,E6,E7,M2,M3 fused into one pass).
+//
+// Reference arithmetic being restated (swin.py:38-80, 105-113), per image and selected expert:
+//     U_s   = interp_linear(Y_s -> P tokens)                      Y_s = ReLU(conv1x1(f_s)), native resolution
+//     logit = w2 . ReLU(W1 U_s + b1) + b2  = w2 . ReLU(interp(Z_s)) + b2   with Z_s = Y_s W1^T + b1
+//             (the first Linear commutes with the lerp because lerp weights sum to 1 — SURVEY §8a a6)
+//     beta  = softmax_s(logit)
+//     fused = sum_s beta_s U_s           -> local_feat (token-major [B, P, D]; the reference's
+//                                           [B, D, sqrt(P), sqrt(P)] result is a stride-view of it)
+//     global_feat = mean_p fused
+// The store goes to the image's ORIGINAL batch slot (scatter-back folded into the store).
+//
+// Backward (no reference code — it is autograd of the above):
+//   pass A (token-centric)   dbeta_s = <dF, U_s>, dlogit = softmax backward           -> dlogit[slot, p, 4]
+//   pass B (native-row-centric, the transpose of the lerp as a gather, no atomics)
+//        dUT_s[i] = sum_p w_i(p) beta_s(p) dF(p)                                      -> bf16 [rows, D]
+//        dZ_s[i]  = sum_p w_i(p) dlogit_s(p) w2 * [interp(Z_s)(p) > 0]                -> bf16 [rows, D/2]
+//        dw2, db2, db1 partial sums per CTA (reduced per expert by mm_expert_reduce)
+#include "mm_common.cuh"
+#include "api_internal.h"
+
+namespace mm {
+
+constexpr int CB_TOKENS_PER_WARP = 8;
+constexpr int CB_TOKENS_PER_BLOCK = 64;   // 8 warps x 8 tokens
+constexpr int CB_ROWS_PER_WARP = 8;
+constexpr int CB_ROWS_PER_BLOCK = 64;
+
+struct CombineArgs {
+    int B, topk, P, n_items;
+    int Ps[4];
+    float scale[4];                 // Ps[s] / P as float (ATen's area_pixel_compute_scale)
+    const int* inv_perm;            // [n_items] item -> slot
+    const int* perm;                // [n_items] slot -> item
+    const int* slot_expert;         // [n_items]
+    const int* slot_row;            // [4, n_items] global row of the slot's first native row
+    const int* counts;              // [K]
+    const int* seg_start;           // [4, K]
+    int K;
+    const float* gate;              // [n_items] gate weight of item, nullptr => 1
+    const __nv_bfloat16* Y;         // [rows, D]
+    const __nv_bfloat16* Z;         // [rows, D/2]
+    const float* w2;                // [E, D/2]
+    const float* b2;                // [E]
+    float* beta;                    // [n_items, P, 4]
+    void* out;                      // [B, P, D]
+    float* gpart;                   // [B, nblk, D]
+    int nblk;
+    // backward
+    const void* dlocal;             // [B, P, D] (same dtype as out) or nullptr
+    const float* dglobal;           // [B, D] fp32 or nullptr
+    float* dlogit;                  // [n_items, P, 4]
+    float* dgate;                   // [n_items] (zeroed by caller) or nullptr
+    __nv_bfloat16* dUT;             // [rows, D]
+    __nv_bfloat16* dZ;              // [rows, D/2]
+    float* part;                    // [n_items, nrb, 2*(D/2) + 1] per-CTA partials: dw2 | db1 | db2
+    int nrb;
+};
+
+template <int N>
+MM_DEVINL void load_row_bf16x8(const __nv_bfloat16* row, int lane, float (&f)[N * 8]) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const uint4 u = *reinterpret_cast<const uint4*>(row + 8 * (lane + 32 * t));
+        f[8 * t + 0] = bf16lo(u.x); f[8 * t + 1] = bf16hi(u.x); f[8 * t + 2] = bf16lo(u.y); f[8 * t + 3] = bf16hi(u.y);
+        f[8 * t + 4] = bf16lo(u.z); f[8 * t + 5] = bf16hi(u.z); f[8 * t + 6] = bf16lo(u.w); f[8 * t + 7] = bf16hi(u.w);
+    }
+}
+template <int N>
+MM_DEVINL void load_row_bf16x4(const __nv_bfloat16* row, int lane, float (&f)[N * 4]) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const uint2 u = *reinterpret_cast<const uint2*>(row + 4 * (lane + 32 * t));
+        f[4 * t + 0] = bf16lo(u.x); f[4 * t + 1] = bf16hi(u.x); f[4 * t + 2] = bf16lo(u.y); f[4 * t + 3] = bf16hi(u.y);
+    }
+}
+template <int N>
+MM_DEVINL void load_row_f32x4(const float* row, int lane, float (&f)[N * 4]) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const float4 u = *reinterpret_cast<const float4*>(row + 4 * (lane + 32 * t));
+        f[4 * t + 0] = u.x; f[4 * t + 1] = u.y; f[4 * t + 2] = u.z; f[4 * t + 3] = u.w;
+    }
+}
+// One [D] row of the output-typed tensors, in the x8 lane layout.
+template <int N, typename T>
+MM_DEVINL void load_row_x8(const T* row, int lane, float (&f)[N * 8]) {
+    if constexpr (sizeof(T) == 2) {
+        load_row_bf16x8<N>(reinterpret_cast<const __nv_bfloat16*>(row), lane, f);
+    } else {
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const float4 a = *reinterpret_cast<const float4*>(row + 8 * (lane + 32 * t));
+            const float4 b = *reinterpret_cast<const float4*>(row + 8 * (lane + 32 * t) + 4);
+            f[8 * t + 0] = a.x; f[8 * t + 1] = a.y; f[8 * t + 2] = a.z; f[8 * t + 3] = a.w;
+            f[8 * t + 4] = b.x; f[8 * t + 5] = b.y; f[8 * t + 6] = b.z; f[8 * t + 7] = b.w;
+        }
+    }
+}
+template <int N, typename T>
+MM_DEVINL void store_row_x8(T* row, int lane, const float (&f)[N * 8]) {
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int t = 0; t < N; ++t)
+            stg_v4(row + 8 * (lane + 32 * t), make_uint4(pack_bf16x2(f[8 * t], f[8 * t + 1]), pack_bf16x2(f[8 * t + 2], f[8 * t + 3]),
+                                                         pack_bf16x2(f[8 * t + 4], f[8 * t + 5]), pack_bf16x2(f[8 * t + 6], f[8 * t + 7])));
+    } else {
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            *reinterpret_cast<float4*>(row + 8 * (lane + 32 * t)) = make_float4(f[8 * t], f[8 * t + 1], f[8 * t + 2], f[8 * t + 3]);
+            *reinterpret_cast<float4*>(row + 8 * (lane + 32 * t) + 4) = make_float4(f[8 * t + 4], f[8 * t + 5], f[8 * t + 6], f[8 * t + 7]);
+        }
+    }
+}
+
+// logit of one (token, scale): w2 . ReLU(lerp(Z rows)) (without b2), full warp reduction.
+template <int N>
+MM_DEVINL float scale_logit(const __nv_bfloat16* Z, int H, long long r0, long long r1, float lam, const float (&w2)[N * 4], int lane) {
+    float z0[N * 4], z1[N * 4];
+    load_row_bf16x4<N>(Z + r0 * H, lane, z0);
+    if (r1 != r0) load_row_bf16x4<N>(Z + r1 * H, lane, z1);
+    float acc = 0.f;
+    const float l0 = 1.0f - lam;
+#pragma unroll
+    for (int i = 0; i < N * 4; ++i) {
+        const float h = (r1 != r0) ? (l0 * z0[i] + lam * z1[i]) : z0[i];
+        acc = fmaf(fmaxf(h, 0.f), w2[i], acc);
+    }
+    return warp_sum(acc);
+}
+
+// ------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256)
+combine_fwd_kernel(const CombineArgs a) {
+    constexpr int N = D / 256;      // 16-byte chunks per lane for a [D] bf16 row; 8-byte chunks for a [D/2] row
+    constexpr int H = D / 2;
+    __shared__ float s_g[8][D];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p_begin = blockIdx.x * CB_TOKENS_PER_BLOCK + warp * CB_TOKENS_PER_WARP;
+    float gsum[N * 8];
+#pragma unroll
+    for (int i = 0; i < N * 8; ++i) gsum[i] = 0.f;
+
+    for (int tp = 0; tp < CB_TOKENS_PER_WARP; ++tp) {
+        const int p = p_begin + tp;
+        if (p >= a.P) break;
+        float o[N * 8];
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) o[i] = 0.f;
+        for (int j = 0; j < a.topk; ++j) {
+            const int item = b * a.topk + j;
+            const int slot = a.inv_perm[item];
+            const int e = a.slot_expert[slot];
+            const float g = a.gate ? a.gate[item] : 1.0f;
+            float w2[N * 4];
+            load_row_f32x4<N>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+            const float b2 = a.b2[e];
+            float logit[4];
+            long long r0[4], r1[4];
+            float lam[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                const long long base = a.slot_row[s * a.n_items + slot];
+                r0[s] = base + L.i0; r1[s] = base + L.i1; lam[s] = L.lam;
+                if (L.lam == 0.f) r1[s] = r0[s];
+                logit[s] = scale_logit<N>(a.Z, H, r0[s], r1[s], lam[s], w2, lane) + b2;
+            }
+            const float mx = fmaxf(fmaxf(logit[0], logit[1]), fmaxf(logit[2], logit[3]));
+            float ex[4], sum = 0.f;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { ex[s] = expf(logit[s] - mx); sum += ex[s]; }
+            const float inv = 1.0f / sum;
+            float beta[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) beta[s] = ex[s] * inv;
+            if (lane == 0)
+                *reinterpret_cast<float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4) = make_float4(beta[0], beta[1], beta[2], beta[3]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                float y0[N * 8];
+                load_row_bf16x8<N>(a.Y + r0[s] * D, lane, y0);
+                const float c0 = g * beta[s] * (1.0f - lam[s]);
+                if (r1[s] != r0[s]) {
+                    float y1[N * 8];
+                    load_row_bf16x8<N>(a.Y + r1[s] * D, lane, y1);
+                    const float c1 = g * beta[s] * lam[s];
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) o[i] = fmaf(c0, y0[i], fmaf(c1, y1[i], o[i]));
+                } else {
+                    const float c = g * beta[s];
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) o[i] = fmaf(c, y0[i], o[i]);
+                }
+            }
+        }
+        store_row_x8<N, OutT>(static_cast<OutT*>(a.out) + (static_cast<size_t>(b) * a.P + p) * D, lane, o);
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) gsum[i] += o[i];
+    }
+    // deterministic per-block partial of the global mean
+#pragma unroll
+    for (int t = 0; t < N; ++t)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_g[warp][8 * (lane + 32 * t) + i] = gsum[8 * t + i];
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_g[w][d];
+        a.gpart[(static_cast<size_t>(b) * a.nblk + blockIdx.x) * D + d] = acc;
+    }
+}
+
+// global_feat[b, d] = (sum over blocks of gpart) / P
+__global__ void __launch_bounds__(256) global_mean_kernel(const float* __restrict__ gpart, int nblk, int D, float inv_p, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float acc = 0.f;
+    for (int k = 0; k < nblk; ++k) acc += gpart[(static_cast<size_t>(b) * nblk + k) * D + d];
+    out[static_cast<size_t>(b) * D + d] = acc * inv_p;
+}
+
+// dF(p) of image b in the x8 lane layout: dlocal[b, p, :] + dglobal[b, :] / P
+template <int N, int D, typename OutT>
+MM_DEVINL void load_dfused(const CombineArgs& a, int b, int p, const float (&dg)[N * 8], int lane, float (&df)[N * 8]) {
+    if (a.dlocal) {
+        load_row_x8<N, OutT>(static_cast<const OutT*>(a.dlocal) + (static_cast<size_t>(b) * a.P + p) * D, lane, df);
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) df[i] += dg[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) df[i] = dg[i];
+    }
+}
+template <int N, int D>
+MM_DEVINL void load_dglobal(const CombineArgs& a, int b, int lane, float (&dg)[N * 8]) {
+    if (a.dglobal) {
+        const float inv_p = 1.0f / static_cast<float>(a.P);
+        load_row_x8<N, float>(a.dglobal + static_cast<size_t>(b) * D, lane, dg);
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) dg[i] *= inv_p;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) dg[i] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// backward pass A: dlogit (and the gate gradient for the top-k extension)
+// ------------------------------------------------------------------------------------
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256)
+combine_bwd_logit_kernel(const CombineArgs a) {
+    constexpr int N = D / 256;
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p_begin = blockIdx.x * CB_TOKENS_PER_BLOCK + warp * CB_TOKENS_PER_WARP;
+    float dg[N * 8];
+    load_dglobal<N, D>(a, b, lane, dg);
+    for (int j = 0; j < a.topk; ++j) {
+        const int item = b * a.topk + j;
+        const int slot = a.inv_perm[item];
+        const float g = a.gate ? a.gate[item] : 1.0f;
+        float dgate_acc = 0.f;
+        for (int tp = 0; tp < CB_TOKENS_PER_WARP; ++tp) {
+            const int p = p_begin + tp;
+            if (p >= a.P) break;
+            float df[N * 8];
+            load_dfused<N, D, OutT>(a, b, p, dg, lane, df);
+            float dbeta[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                const long long base = a.slot_row[s * a.n_items + slot];
+                float y0[N * 8];
+                load_row_bf16x8<N>(a.Y + (base + L.i0) * D, lane, y0);
+                float acc = 0.f;
+                if (L.lam != 0.f && L.i1 != L.i0) {
+                    float y1[N * 8];
+                    load_row_bf16x8<N>(a.Y + (base + L.i1) * D, lane, y1);
+                    const float l0 = 1.0f - L.lam;
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) acc = fmaf(df[i], l0 * y0[i] + L.lam * y1[i], acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) acc = fmaf(df[i], y0[i], acc);
+                }
+                dbeta[s] = warp_sum(acc);
+            }
+            const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+            const float dot = bt.x * dbeta[0] + bt.y * dbeta[1] + bt.z * dbeta[2] + bt.w * dbeta[3];
+            dgate_acc += dot;
+            if (lane == 0) {
+                float4 dl;
+                dl.x = g * bt.x * (dbeta[0] - dot); dl.y = g * bt.y * (dbeta[1] - dot);
+                dl.z = g * bt.z * (dbeta[2] - dot); dl.w = g * bt.w * (dbeta[3] - dot);
+                *reinterpret_cast<float4*>(a.dlogit + (static_cast<size_t>(slot) * a.P + p) * 4) = dl;
+            }
+        }
+        if (a.dgate && lane == 0) atomicAdd(a.dgate + item, dgate_acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// backward pass B: transposed lerp as a gather over each native row's token window
+// ------------------------------------------------------------------------------------
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256)
+combine_bwd_rows_kernel(const CombineArgs a) {
+    constexpr int N = D / 256;
+    constexpr int H = D / 2;
+    constexpr int PART = 2 * H + 1;
+    __shared__ float s_part[8][PART];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (blockIdx.y >= a.n_items) {
+        // zero the 128-row padding behind every expert segment of dZ (wgrad reduces over whole tiles)
+        const int e = blockIdx.y - a.n_items;
+        for (int s = 0; s < 4; ++s) {
+            const long long rows = static_cast<long long>(a.counts[e]) * a.Ps[s];
+            const long long pad = (rows + TILE_M - 1) / TILE_M * TILE_M - rows;
+            __nv_bfloat16* dz = a.dZ + (static_cast<long long>(a.seg_start[s * a.K + e]) + rows) * H;
+            for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4; i < pad * H;
+                 i += static_cast<long long>(gridDim.x) * 256 * 4)
+                *reinterpret_cast<uint2*>(dz + i) = make_uint2(0, 0);
+        }
+        return;
+    }
+
+    const int slot = blockIdx.y;
+    const int item = a.perm[slot];
+    const int b = item / a.topk;
+    const int e = a.slot_expert[slot];
+    const float g = a.gate ? a.gate[item] : 1.0f;
+    float w2[N * 4];
+    load_row_f32x4<N>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+    float dg[N * 8];
+    load_dglobal<N, D>(a, b, lane, dg);
+
+    float dw2_acc[N * 4], db1_acc[N * 4], db2_acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < N * 4; ++i) { dw2_acc[i] = 0.f; db1_acc[i] = 0.f; }
+
+    const int total_rows = a.Ps[0] + a.Ps[1] + a.Ps[2] + a.Ps[3];
+    const int u_begin = blockIdx.x * CB_ROWS_PER_BLOCK + warp * CB_ROWS_PER_WARP;
+    for (int tr = 0; tr < CB_ROWS_PER_WARP; ++tr) {
+        int u = u_begin + tr;
+        if (u >= total_rows) break;
+        int s = 0;
+        while (u >= a.Ps[s]) { u -= a.Ps[s]; ++s; }
+        const int i = u;
+        const int Ps = a.Ps[s];
+        const float scale = a.scale[s];
+        const long long base = a.slot_row[s * a.n_items + slot];
+        // token window of native row i: tokens whose i0 is i-1 or i (plus a one-token safety margin)
+        const float inv_scale = static_cast<float>(a.P) / static_cast<float>(Ps);
+        int p_lo = static_cast<int>(floorf((static_cast<float>(i) - 0.5f) * inv_scale - 0.5f)) - 1;
+        int p_hi = static_cast<int>(ceilf((static_cast<float>(i) + 1.5f) * inv_scale - 0.5f)) + 1;
+        if (i == 0) p_lo = 0;
+        if (i == Ps - 1) p_hi = a.P;
+        p_lo = max(p_lo, 0);
+        p_hi = min(p_hi, a.P);
+
+        float zc[N * 4], zm[N * 4], zp[N * 4];
+        load_row_bf16x4<N>(a.Z + (base + i) * H, lane, zc);
+        load_row_bf16x4<N>(a.Z + (base + max(i - 1, 0)) * H, lane, zm);
+        load_row_bf16x4<N>(a.Z + (base + min(i + 1, Ps - 1)) * H, lane, zp);
+
+        float acc_u[N * 8], acc_z[N * 4];
+#pragma unroll
+        for (int k = 0; k < N * 8; ++k) acc_u[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < N * 4; ++k) acc_z[k] = 0.f;
+
+        for (int p = p_lo; p < p_hi; ++p) {
+            const LerpSrc L = lerp_src(p, scale, Ps);
+            const float l0 = 1.0f - L.lam;
+            float w = 0.f;
+            if (L.i0 == i) w += l0;
+            if (L.i1 == i) w += L.lam;
+            if (L.i0 != i && L.i1 != i) continue;
+            const size_t tok = static_cast<size_t>(slot) * a.P + p;
+            const float bt = a.beta[tok * 4 + s];
+            const float dl = a.dlogit[tok * 4 + s];
+            if (w != 0.f) {
+                float df[N * 8];
+                load_dfused<N, D, OutT>(a, b, p, dg, lane, df);
+                const float c = w * bt * g;
+#pragma unroll
+                for (int k = 0; k < N * 8; ++k) acc_u[k] = fmaf(c, df[k], acc_u[k]);
+            }
+            // interp(Z)(p) from the three cached native rows
+            const bool lo_is_i = (L.i0 == i);
+            const float cz = w * dl;
+#pragma unroll
+            for (int k = 0; k < N * 4; ++k) {
+                const float za = lo_is_i ? zc[k] : zm[k];
+                const float zb = lo_is_i ? (L.i1 == i ? zc[k] : zp[k]) : zc[k];
+                const float h = (L.i1 != L.i0 && L.lam != 0.f) ? (l0 * za + L.lam * zb) : za;
+                if (h > 0.f) {
+                    acc_z[k] = fmaf(cz, w2[k], acc_z[k]);
+                    if (lo_is_i) dw2_acc[k] = fmaf(dl, h, dw2_acc[k]);   // each (token, scale) counted once
+                }
+            }
+            if (lo_is_i) db2_acc += dl;
+        }
+        // write dUT (bf16) and dZ (bf16); db1 = column sums of dZ
+        store_row_x8<N, __nv_bfloat16>(a.dUT + (base + i) * D, lane, acc_u);
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            *reinterpret_cast<uint2*>(a.dZ + (base + i) * H + 4 * (lane + 32 * t)) =
+                make_uint2(pack_bf16x2(acc_z[4 * t], acc_z[4 * t + 1]), pack_bf16x2(acc_z[4 * t + 2], acc_z[4 * t + 3]));
+        }
+#pragma unroll
+        for (int k = 0; k < N * 4; ++k) db1_acc[k] += acc_z[k];
+    }
+
+    // per-CTA partials: [dw2 (H) | db1 (H) | db2 (1)]
+#pragma unroll
+    for (int t = 0; t < N; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s_part[warp][4 * (lane + 32 * t) + k] = dw2_acc[4 * t + k];
+            s_part[warp][H + 4 * (lane + 32 * t) + k] = db1_acc[4 * t + k];
+        }
+    if (lane == 0) s_part[warp][2 * H] = db2_acc;
+    __syncthreads();
+    float* dst = a.part + (static_cast<size_t>(slot) * a.nrb + blockIdx.x) * PART;
+    for (int c = threadIdx.x; c < PART; c += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += s_part[w][c];
+        dst[c] = acc;
+    }
+}
+
+// out[e, c] = sum over the slots of expert e and their nrb blocks of part[slot, blk, c]; grid = (ceil(C/256), K)
+__global__ void __launch_bounds__(256)
+expert_reduce_kernel(const float* __restrict__ part, const int* __restrict__ offsets, int nrb, int C, float* __restrict__ out) {
+    const int e = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long long lo = static_cast<long long>(offsets[e]) * nrb, hi = static_cast<long long>(offsets[e + 1]) * nrb;
+    float acc = 0.f;
+    for (long long r = lo; r < hi; ++r) acc += part[r * C + c];
+    out[static_cast<size_t>(e) * C + c] = acc;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+static int fill_common(CombineArgs& a, int B, int topk, int P, const int32_t* Ps, int D, const char* who) {
+    if (!(B > 0 && topk >= 1 && P > 0)) { mm::set_error("%s: bad shape", who); return MM_ERR_BAD_SHAPE; }
+    if (!(D == 256 || D == 512 || D == 768 || D == 1024)) {
+        mm::set_error("%s: output_dim must be one of 256/512/768/1024 (got %d)", who, D);
+        return MM_ERR_UNSUPPORTED;
+    }
+    a.B = B; a.topk = topk; a.P = P; a.n_items = B * topk;
+    for (int s = 0; s < 4; ++s) {
+        a.Ps[s] = Ps[s];
+        a.scale[s] = static_cast<float>(Ps[s]) / static_cast<float>(P);
+    }
+    return MM_OK;
+}
+
+#define MM_DISPATCH_D(D, OUT_F32, KERNEL, GRID, ST, ARGS)                                             \
+    switch (D) {                                                                                      \
+        case 256: if (OUT_F32) KERNEL<256, float><<<GRID, 256, 0, ST>>>(ARGS); else KERNEL<256, __nv_bfloat16><<<GRID, 256, 0, ST>>>(ARGS); break;   \
+        case 512: if (OUT_F32) KERNEL<512, float><<<GRID, 256, 0, ST>>>(ARGS); else KERNEL<512, __nv_bfloat16><<<GRID, 256, 0, ST>>>(ARGS); break;   \
+        case 768: if (OUT_F32) KERNEL<768, float><<<GRID, 256, 0, ST>>>(ARGS); else KERNEL<768, __nv_bfloat16><<<GRID, 256, 0, ST>>>(ARGS); break;   \
+        case 1024: if (OUT_F32) KERNEL<1024, float><<<GRID, 256, 0, ST>>>(ARGS); else KERNEL<1024, __nv_bfloat16><<<GRID, 256, 0, ST>>>(ARGS); break; \
+    }
+
+extern "C" int mm_combine_num_token_blocks(int P) { return (P + CB_TOKENS_PER_BLOCK - 1) / CB_TOKENS_PER_BLOCK; }
+extern "C" int mm_combine_num_row_blocks(const int32_t* Ps) {
+    return (Ps[0] + Ps[1] + Ps[2] + Ps[3] + CB_ROWS_PER_BLOCK - 1) / CB_ROWS_PER_BLOCK;
+}
+
+extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk,
+                                             int P, const int32_t* Ps, int D, const int32_t* inv_perm,
+                                             const int32_t* slot_expert, const int32_t* slot_row, const float* gate,
+                                             float* beta, void* out, int out_f32, float* gpart, float* global_feat,
+                                             void* stream) {
+    CombineArgs a{};
+    int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_fwd");
+    if (rc) return rc;
+    a.inv_perm = inv_perm; a.slot_expert = slot_expert; a.slot_row = slot_row; a.gate = gate;
+    a.Y = static_cast<const __nv_bfloat16*>(Y); a.Z = static_cast<const __nv_bfloat16*>(Z);
+    a.w2 = w2; a.b2 = b2; a.beta = beta; a.out = out; a.gpart = gpart;
+    a.nblk = mm_combine_num_token_blocks(P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(a.nblk, B);
+    MM_DISPATCH_D(D, out_f32, combine_fwd_kernel, grid, st, a)
+    rc = mm_check_launch("mm_interp_softmax_combine_fwd");
+    if (rc) return rc;
+    global_mean_kernel<<<dim3((D + 255) / 256, B), 256, 0, st>>>(gpart, a.nblk, D, 1.0f / static_cast<float>(P), global_feat);
+    return mm_check_launch("mm_interp_softmax_combine_fwd(global mean)");
+}
+
+extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
+                                             const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,
+                                             const int32_t* slot_expert, const int32_t* slot_row, const int32_t* counts,
+                                             const int32_t* seg_start, const int32_t* offsets, const float* gate,
+                                             const float* beta, const void* dlocal, int dlocal_f32, const float* dglobal,
+                                             float* dlogit, float* dgate, void* dUT, void* dZ, float* part,
+                                             float* dw2_db1_db2, void* stream) {
+    CombineArgs a{};
+    int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_bwd");
+    if (rc) return rc;
+    a.perm = perm; a.inv_perm = inv_perm; a.slot_expert = slot_expert; a.slot_row = slot_row; a.gate = gate;
+    a.counts = counts; a.seg_start = seg_start; a.K = K;
+    a.Y = static_cast<const __nv_bfloat16*>(Y); a.Z = static_cast<const __nv_bfloat16*>(Z);
+    a.w2 = w2; a.beta = const_cast<float*>(beta);
+    a.dlocal = dlocal; a.dglobal = dglobal; a.dlogit = dlogit; a.dgate = dgate;
+    a.dUT = static_cast<__nv_bfloat16*>(dUT); a.dZ = static_cast<__nv_bfloat16*>(dZ);
+    a.part = part;
+    a.nblk = mm_combine_num_token_blocks(P);
+    a.nrb = mm_combine_num_row_blocks(Ps);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        dim3 grid(a.nblk, B);
+        MM_DISPATCH_D(D, dlocal_f32, combine_bwd_logit_kernel, grid, st, a)
+        rc = mm_check_launch("mm_interp_softmax_combine_bwd(logit)");
+        if (rc) return rc;
+    }
+    {
+        dim3 grid(a.nrb, a.n_items + K);
+        MM_DISPATCH_D(D, dlocal_f32, combine_bwd_rows_kernel, grid, st, a)
+        rc = mm_check_launch("mm_interp_softmax_combine_bwd(rows)");
+        if (rc) return rc;
+    }
+    const int C = 2 * (D / 2) + 1;
+    expert_reduce_kernel<<<dim3((C + 255) / 256, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
+    return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");
+}

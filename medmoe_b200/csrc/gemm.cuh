@@ -1,0 +1,421 @@
+// medmoe_b200 — tcgen05 / TMEM / TMA grouped GEMM kernels (sm_100a).
+//
+// Two persistent, warp-specialised kernels cover every matrix product on the hot path
+// (SURVEY §2.2 rows E1, E4 and their backward; north-star item 3):
+//
+//   gemm_rows_kernel   C[m, n] = epi( sum_k A[m, k] * W_e[n, k] )       "TN": both operands K-major
+//       rows m are expert-sorted, 128-row tiles never straddle experts (tile_info says
+//       which expert's weight slab a tile multiplies).  Used for
+//         E1  Y_s = ReLU(f_s W_s^T + b_s)      (reference swin.py:41, Conv1d k=1 + ReLU)
+//         E4  Z   = Y W1^T + b1                (reference swin.py:63, first Linear of attn_proj,
+//                                               evaluated at native resolution — lerp commutes)
+//         dY  = (dUT + dZ W1) * [Y > 0]        (backward of E4 + ReLU of E1)
+//         df_s = dPre_s W_s                    (backward of E1 w.r.t. the Swin stage features)
+//
+//   gemm_wgrad_kernel  dW_e[i, j] = sum_m A[m, i] * B[m, j]             both operands MN-major
+//       reduction over the rows of expert e (split into chunks, fp32 red.add into dW).
+//
+// Roles per CTA (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
+// (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "mm_common.cuh"
+
+namespace mm {
+
+enum : int {
+    EPI_RELU = 1,       // out = max(out, 0)
+    EPI_ZERO_PAD = 2,   // rows >= valid_rows of a tile are written as zeros
+};
+
+struct RowsGemmArgs {
+    const int2* tile_info;   // [tile] {expert or -1, valid_rows}; nullptr => single problem of M rows
+    int tile_begin;          // first entry of tile_info used by this launch
+    int tile_count;          // number of 128-row tiles this launch covers (local tile 0 == row 0 of A/out)
+    int M;                   // rows (only when tile_info == nullptr)
+    int N, K;
+    int n_tiles;             // N / BN
+    const float* bias;       // [E, N] fp32 or nullptr
+    const __nv_bfloat16* aux;   // [rows, ld_aux] added to the accumulator, or nullptr
+    long long ld_aux;
+    const __nv_bfloat16* gate;  // [rows, ld_gate]; out = gate > 0 ? out : 0, or nullptr
+    long long ld_gate;
+    void* out;               // bf16 (or fp32 when OUT_F32) [rows, ld_out]
+    long long ld_out;
+    float* colsum;           // [E, N] fp32, += column sums of the written tile (bias gradients) or nullptr
+    float out_scale;         // multiplies the accumulator before bias (1.0 for the MoE path)
+    int flags;
+};
+
+struct WgradArgs {
+    const int4* chunks;      // [chunk] {expert, first_tile (global), num_tiles, 0}
+    int chunk_begin, chunk_count;
+    int tile_base;           // global tile index of row 0 of A/B in this launch
+    int N1, N2;              // dW is [E, N1, N2]; A is [rows, N1], B is [rows, N2]
+    int n_i, n_j;            // tiles along N1 (128 each) and N2 (BN each)
+    float* out;              // [E, N1, N2] fp32, accumulated with red.add
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = TILE_M * 64 * 2;                 // 16 KB: 128 rows x 64 bf16 (K-major) or 2 x (64 k-rows x 64 mn)
+    static constexpr int B_BYTES = ((BN + 63) / 64) * 64 * 64 * 2;   // BN rounded up to 64-wide chunks
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+};
+
+// ------------------------------------------------------------------------------------
+// Column sums of a 32x32 register tile: lane r holds row r (f[0..31]); on return lane c
+// holds sum over rows of column c in f[0].  31 shuffles.
+// ------------------------------------------------------------------------------------
+MM_DEVINL float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            float send = up ? f[i] : f[i + o];
+            float keep = up ? f[i + o] : f[i];
+            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return f[0];
+}
+
+// ------------------------------------------------------------------------------------
+// gemm_rows_kernel
+// ------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool OUT_F32>
+__global__ void __launch_bounds__(256, 1)
+gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const RowsGemmArgs a) {
+    using S = GemmSmem<BN, STAGES>;
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
+    static_assert(BN % 16 == 0, "UMMA N constraint for M = 128");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * S::A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_kb = (a.K + 63) / 64;
+    const int total_work = a.tile_count * a.n_tiles;
+
+    if (threadIdx.x == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
+            int e = 0;
+            if (a.tile_info) { e = a.tile_info[a.tile_begin + lt].x; if (e < 0) continue; }
+            const int row_a = lt * TILE_M;
+            const int row_b = e * a.N + nt * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], S::A_BYTES + BN * 128);
+                tma_load_2d(sA + stage * S::A_BYTES, &tmA, &full[stage], kb * 64, row_a);
+                tma_load_2d(sB + stage * S::B_BYTES, &tmB, &full[stage], kb * 64, row_b);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int lt = w / a.n_tiles;
+            if (a.tile_info && a.tile_info[a.tile_begin + lt].x < 0) continue;
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + stage * S::B_BYTES);
+                const int ksteps = min(4, (a.K - kb * 64 + 15) / 16);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+                    const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+                    umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
+            int e = 0, valid = TILE_M;
+            if (a.tile_info) {
+                const int2 ti = a.tile_info[a.tile_begin + lt];
+                e = ti.x; valid = ti.y;
+                if (e < 0) continue;
+            } else {
+                valid = min(TILE_M, a.M - lt * TILE_M);
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int r_in_tile = q * 32 + lane;
+            const long long row = static_cast<long long>(lt) * TILE_M + r_in_tile;
+            const bool row_valid = r_in_tile < valid;
+            const bool row_store = row_valid || (a.flags & EPI_ZERO_PAD);
+            const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = nt * BN + c * 32;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * a.out_scale;
+                if (a.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(a.bias + static_cast<size_t>(e) * a.N + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(bp + j);
+                        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+                    }
+                }
+                if (a.aux && row_valid) {
+                    const uint4* ap = reinterpret_cast<const uint4*>(a.aux + row * a.ld_aux + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 u = ldg_nc_v4(ap + j);
+                        f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
+                        f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);
+                        f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
+                        f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
+                    }
+                }
+                if (a.gate && row_valid) {
+                    const uint4* gp = reinterpret_cast<const uint4*>(a.gate + row * a.ld_gate + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 u = ldg_nc_v4(gp + j);
+                        // gate holds ReLU outputs (>= 0): "> 0" is "bits != 0" on the bf16 payload.
+                        if ((u.x & 0x0000ffffu) == 0) f[8 * j + 0] = 0.f;
+                        if ((u.x & 0xffff0000u) == 0) f[8 * j + 1] = 0.f;
+                        if ((u.y & 0x0000ffffu) == 0) f[8 * j + 2] = 0.f;
+                        if ((u.y & 0xffff0000u) == 0) f[8 * j + 3] = 0.f;
+                        if ((u.z & 0x0000ffffu) == 0) f[8 * j + 4] = 0.f;
+                        if ((u.z & 0xffff0000u) == 0) f[8 * j + 5] = 0.f;
+                        if ((u.w & 0x0000ffffu) == 0) f[8 * j + 6] = 0.f;
+                        if ((u.w & 0xffff0000u) == 0) f[8 * j + 7] = 0.f;
+                    }
+                }
+                if (a.flags & EPI_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (!row_valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                }
+                if (row_store) {
+                    if constexpr (OUT_F32) {
+                        float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + row * a.ld_out + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(a.out) + row * a.ld_out + col0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                            u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                            u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                            u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                            stg_v4(ob + 8 * j, u);
+                        }
+                    }
+                }
+                if (a.colsum) {
+                    const float cs = warp_colsum32(f, lane);
+                    atomicAdd(a.colsum + static_cast<size_t>(e) * a.N + col0 + lane, cs);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------
+// gemm_wgrad_kernel: dW[e][i][j] += sum over rows m of chunk: A[m][i] * B[m][j]
+// ------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const WgradArgs a) {
+    using S = GemmSmem<BN, STAGES>;
+    static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 (MN-major SW128 chunks)");
+    constexpr int NB_CHUNKS = BN / 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * S::A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int per_chunk = a.n_i * a.n_j;
+    const int total_work = a.chunk_count * per_chunk;
+
+    if (threadIdx.x == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int c = w / per_chunk, rem = w - c * per_chunk;
+            const int it = rem / a.n_j, jt = rem - it * a.n_j;
+            const int4 ch = a.chunks[a.chunk_begin + c];
+            if (ch.z <= 0) continue;
+            const int row0 = (ch.y - a.tile_base) * TILE_M;
+            const int num_kb = ch.z * 2;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], S::A_BYTES + NB_CHUNKS * 8192);
+                uint8_t* dA = sA + stage * S::A_BYTES;
+                uint8_t* dB = sB + stage * S::B_BYTES;
+                const int r = row0 + kb * 64;
+                tma_load_2d(dA, &tmA, &full[stage], it * 128, r);
+                tma_load_2d(dA + 8192, &tmA, &full[stage], it * 128 + 64, r);
+#pragma unroll
+                for (int j = 0; j < NB_CHUNKS; ++j)
+                    tma_load_2d(dB + j * 8192, &tmB, &full[stage], jt * BN + j * 64, r);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int c = w / per_chunk;
+            const int4 ch = a.chunks[a.chunk_begin + c];
+            if (ch.z <= 0) continue;
+            const int num_kb = ch.z * 2;
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + stage * S::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // 16 k-rows per MMA = 2048 B; 64-element MN chunks are 8192 B apart (LBO),
+                    // 8-row k groups 1024 B apart (SBO).
+                    const uint64_t da = make_smem_desc(a_addr + k * 2048, 8192, 1024);
+                    const uint64_t db = make_smem_desc(b_addr + k * 2048, 8192, 1024);
+                    umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int c = w / per_chunk, rem = w - c * per_chunk;
+            const int it = rem / a.n_j, jt = rem - it * a.n_j;
+            const int4 ch = a.chunks[a.chunk_begin + c];
+            if (ch.z <= 0) continue;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int i = it * 128 + q * 32 + lane;
+            const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+            float* orow = a.out + (static_cast<size_t>(ch.x) * a.N1 + i) * a.N2;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + cc * 32, v);
+                tmem_ld_wait();
+                const int col0 = jt * BN + cc * 32;
+                if (i < a.N1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = col0 + 4 * j;
+                        if (col + 3 < a.N2) {
+                            red_add_v4_f32(orow + col, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        } else {
+                            for (int t = 0; t < 4; ++t)
+                                if (col + t < a.N2) atomicAdd(orow + col + t, __uint_as_float(v[4 * j + t]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace mm

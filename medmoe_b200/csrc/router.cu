@@ -1,0 +1,163 @@
+// medmoe_b200 — router gate (north-star kernel 1).
+//
+// Forward restates reference swin.py:98-100:
+//     probs = softmax(Linear(128,K)(ReLU(Linear(768,128)(swin_feat)))) ; top = argmax(probs)
+// entirely in fp32 (argmax parity: ties break to the lowest index like torch.argmax).
+// top-k (k > 1) is the documented extension: k largest probs, gate weights =
+// those probs renormalised to sum 1; k = 1 gives weight 1.0, i.e. the reference gather.
+//
+// Backward is the gradient of the returned probabilities (the only path into the router
+// in the reference: F.cross_entropy(probs, label), medmoe_module.py:235-237).
+#include "mm_common.cuh"
+#include "api_internal.h"
+
+namespace mm {
+
+constexpr int ROUTER_HID = 128;   // fixed by the reference (swin.py:88-90)
+constexpr int ROUTER_MAX_K = 64;
+
+// One CTA (128 threads = 4 warps) per image.
+__global__ void __launch_bounds__(128)
+router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ W1, const float* __restrict__ b1,
+                  const float* __restrict__ W2, const float* __restrict__ b2, int K, int topk,
+                  float* __restrict__ hidden, float* __restrict__ probs, int* __restrict__ topk_idx,
+                  float* __restrict__ topk_w) {
+    extern __shared__ float sm[];
+    float* sx = sm;                 // [D]
+    float* sh = sm + D;             // [128]
+    float* sl = sh + ROUTER_HID;    // [K]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sx[i] = x[static_cast<size_t>(b) * D + i];
+    __syncthreads();
+    // hidden: each warp owns 32 outputs; lanes stride the 768-long dot (coalesced W1 reads).
+    for (int o = warp * 32; o < warp * 32 + 32; ++o) {
+        const float* w = W1 + static_cast<size_t>(o) * D;
+        float acc = 0.f;
+        for (int i = lane; i < D; i += 32) acc = fmaf(w[i], sx[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float h = fmaxf(acc + b1[o], 0.f);
+            sh[o] = h;
+            hidden[static_cast<size_t>(b) * ROUTER_HID + o] = h;
+        }
+    }
+    __syncthreads();
+    for (int e = warp; e < K; e += 4) {
+        const float* w = W2 + static_cast<size_t>(e) * ROUTER_HID;
+        float acc = 0.f;
+        for (int i = lane; i < ROUTER_HID; i += 32) acc = fmaf(w[i], sh[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) sl[e] = acc + b2[e];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mx = sl[0];
+        for (int e = 1; e < K; ++e) mx = fmaxf(mx, sl[e]);
+        float sum = 0.f;
+        for (int e = 0; e < K; ++e) { const float t = expf(sl[e] - mx); sl[e] = t; sum += t; }
+        const float inv = 1.0f / sum;
+        for (int e = 0; e < K; ++e) {
+            sl[e] *= inv;
+            probs[static_cast<size_t>(b) * K + e] = sl[e];
+        }
+        // top-k by repeated first-max selection (k is 1 or 2 in every configuration)
+        unsigned long long taken = 0ull;
+        float wsum = 0.f;
+        for (int j = 0; j < topk; ++j) {
+            int best = -1; float bv = -1.f;
+            for (int e = 0; e < K; ++e)
+                if (!((taken >> e) & 1ull) && sl[e] > bv) { bv = sl[e]; best = e; }
+            taken |= 1ull << best;
+            topk_idx[static_cast<size_t>(b) * topk + j] = best;
+            topk_w[static_cast<size_t>(b) * topk + j] = bv;
+            wsum += bv;
+        }
+        for (int j = 0; j < topk; ++j)
+            topk_w[static_cast<size_t>(b) * topk + j] = (topk == 1) ? 1.0f : topk_w[static_cast<size_t>(b) * topk + j] / wsum;
+    }
+}
+
+// Per image: dlogit = p * (dp - <p, dp>); dh = (dlogit W2) * [h > 0]; dx = dh W1.
+__global__ void __launch_bounds__(128)
+router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restrict__ probs,
+                         const float* __restrict__ hidden, const float* __restrict__ W1,
+                         const float* __restrict__ W2, int D, int K, float* __restrict__ dlogit,
+                         float* __restrict__ dhidden, float* __restrict__ dx) {
+    __shared__ float sdl[ROUTER_MAX_K];
+    __shared__ float sdh[ROUTER_HID];
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        float dot = 0.f;
+        for (int e = 0; e < K; ++e) dot += probs[b * K + e] * dprobs[b * K + e];
+        for (int e = 0; e < K; ++e) {
+            const float d = probs[b * K + e] * (dprobs[b * K + e] - dot);
+            sdl[e] = d;
+            dlogit[b * K + e] = d;
+        }
+    }
+    __syncthreads();
+    {
+        const int o = threadIdx.x;   // 128 hidden units
+        float acc = 0.f;
+        for (int e = 0; e < K; ++e) acc = fmaf(sdl[e], W2[e * ROUTER_HID + o], acc);
+        const float dh = hidden[static_cast<size_t>(b) * ROUTER_HID + o] > 0.f ? acc : 0.f;
+        sdh[o] = dh;
+        dhidden[static_cast<size_t>(b) * ROUTER_HID + o] = dh;
+    }
+    __syncthreads();
+    if (dx) {
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int o = 0; o < ROUTER_HID; ++o) acc = fmaf(sdh[o], W1[static_cast<size_t>(o) * D + i], acc);
+            dx[static_cast<size_t>(b) * D + i] = acc;
+        }
+    }
+}
+
+// out[r, c] = sum_b L[b, r] * R[b, c]   (dW = dOut^T * In, batch reduction, deterministic order)
+// grid = (ceil(C/256), R); optional bias out_b[r] = sum_b L[b, r].
+__global__ void __launch_bounds__(256)
+batch_outer_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ R, int ldr, int B, int C,
+                   float* __restrict__ out, float* __restrict__ out_b) {
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float l = L[static_cast<size_t>(b) * ldl + r];
+        accb += l;
+        if (c < C) acc = fmaf(l, R[static_cast<size_t>(b) * ldr + c], acc);
+    }
+    if (c < C) out[static_cast<size_t>(r) * C + c] = acc;
+    if (out_b && c == 0) out_b[r] = accb;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" int mm_router_topk(const float* x, int B, int D, const float* W1, const float* b1, const float* W2,
+                              const float* b2, int K, int topk, float* hidden, float* probs, int32_t* topk_idx,
+                              float* topk_w, void* stream) {
+    MM_REQUIRE(B >= 0 && D > 0 && K > 0 && K <= ROUTER_MAX_K && topk >= 1 && topk <= K, MM_ERR_BAD_SHAPE,
+               "mm_router_topk: need 0 < K <= 64, 1 <= topk <= K");
+    if (B == 0) return MM_OK;
+    const size_t smem = (static_cast<size_t>(D) + ROUTER_HID + K) * sizeof(float);
+    router_fwd_kernel<<<B, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, D, W1, b1, W2, b2, K, topk, hidden,
+                                                                          probs, topk_idx, topk_w);
+    return mm_check_launch("mm_router_topk");
+}
+
+extern "C" int mm_router_bwd(const float* dprobs, const float* probs, const float* hidden, const float* x,
+                             const float* W1, const float* W2, int B, int D, int K, float* dlogit, float* dhidden,
+                             float* dx, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+    MM_REQUIRE(B > 0 && D > 0 && K > 0 && K <= ROUTER_MAX_K, MM_ERR_BAD_SHAPE, "mm_router_bwd: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    router_bwd_sample_kernel<<<B, 128, 0, st>>>(dprobs, probs, hidden, W1, W2, D, K, dlogit, dhidden, dx);
+    // dW1[128, D] = dh^T x ; db1 = sum_b dh
+    batch_outer_kernel<<<dim3((D + 255) / 256, ROUTER_HID), 256, 0, st>>>(dhidden, ROUTER_HID, x, D, B, D, dW1, db1);
+    // dW2[K, 128] = dlogit^T h ; db2 = sum_b dlogit
+    batch_outer_kernel<<<dim3(1, K), 256, 0, st>>>(dlogit, K, hidden, ROUTER_HID, B, ROUTER_HID, dW2, db2);
+    return mm_check_launch("mm_router_bwd");
+}

@@ -1,0 +1,164 @@
+"""GPU unit tests of the tcgen05 grouped GEMM kernels through the C-ABI.
+
+Reference here is a plain PyTorch fp32 matmul of the same bf16-rounded operands (a
+floating-point kernel: tolerance = bf16 output rounding, 2^-8 relative, plus fp32
+accumulation-order noise).
+"""
+import pytest
+import torch
+
+from medmoe_b200 import _lib, plan as mmplan
+
+pytestmark = pytest.mark.gpu
+
+EPI_RELU, EPI_ZERO_PAD = 1, 2
+
+
+def _bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def gemm_rows(A, W, N, *, tile_info=None, tile_begin=0, tile_count=0, M=0, bias=None, aux=None, gate=None,
+              out=None, out_f32=False, colsum=None, flags=0, out_scale=1.0):
+    E = W.shape[0] // N
+    K = A.shape[1]
+    _lib.call("mm_grouped_gemm_rows", _lib.ptr(A), A.shape[0], K, A.stride(0), _lib.ptr(W), E, N, W.stride(0),
+              _lib.ptr(tile_info), tile_begin, tile_count, M, _lib.ptr(bias),
+              _lib.ptr(aux), aux.stride(0) if aux is not None else 0,
+              _lib.ptr(gate), gate.stride(0) if gate is not None else 0,
+              _lib.ptr(out), out.stride(0), int(out_f32), _lib.ptr(colsum), float(out_scale), flags,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (300, 96, 768), (517, 192, 768), (1000, 768, 384),
+                                   (256, 384, 96), (130, 768, 192), (64, 768, 128), (2048, 768, 2048)])
+@pytest.mark.parametrize("out_f32", [False, True])
+def test_dense_rows_gemm(M, K, N, out_f32):
+    A = _bf16(M, K, seed=1)
+    W = _bf16(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    gemm_rows(A, W, N, M=M, bias=bias, out=out, out_f32=out_f32, flags=EPI_RELU)
+    ref = torch.relu(A.float() @ W.float().t() + bias)
+    got = out.float()
+    assert torch.isfinite(got).all()
+    tol = 2e-5 if out_f32 else 2 ** -7
+    err = (got - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def _random_plan(n_items, K, P, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    item_expert = torch.randint(0, K, (n_items,), generator=g, dtype=torch.int32)
+    layout = mmplan.make_layout(n_items, 1, K, P, target_chunks=4)
+    plan = mmplan.build_plan(item_expert.cuda(), layout)
+    torch.cuda.synchronize()
+    return item_expert, layout, plan
+
+
+def test_dispatch_build_matches_host_logic():
+    for seed, (n, K, P) in enumerate([(7, 4, [49, 13]), (64, 6, [196, 49, 16]), (1500, 8, [3, 1]), (5, 3, [300])]):
+        item_expert, layout, plan = _random_plan(n, K, P, seed)
+        ref = mmplan.reference_plan(item_expert.tolist(), layout)
+        assert plan.counts.tolist() == ref["counts"]
+        assert plan.offsets.tolist() == ref["offsets"]
+        assert plan.perm.tolist() == ref["perm"]
+        assert plan.inv_perm.tolist() == ref["inv_perm"]
+        assert plan.slot_expert.tolist() == ref["slot_expert"]
+        assert plan.seg_start.tolist() == ref["seg_start"]
+        assert plan.slot_row.tolist() == ref["slot_row"]
+        assert [tuple(t) for t in plan.tile_info.tolist()] == ref["tile_info"]
+        assert [tuple(t) for t in plan.chunks.tolist()] == ref["chunks"]
+
+
+def _row_expert(layout, plan):
+    """expert id per global row (-1 = padding / unused), from the device-built tables."""
+    row_e = torch.full((layout.total_rows,), -1, dtype=torch.long)
+    ti = plan.tile_info.cpu()
+    for t in range(layout.total_tiles):
+        e, v = ti[t].tolist()
+        if e >= 0:
+            row_e[t * 128: t * 128 + v] = e
+    return row_e.cuda()
+
+
+@pytest.mark.parametrize("K,N", [(96, 768), (768, 384), (384, 768), (768, 192)])
+def test_grouped_rows_gemm_full_epilogue(K, N):
+    n_items, E, P = 37, 4, [49, 20]
+    _, layout, plan = _random_plan(n_items, E, P, seed=3)
+    rows = layout.total_rows
+    A = _bf16(rows, K, seed=4)
+    W = _bf16(E * N, K, scale=K ** -0.5, seed=5)
+    bias = torch.randn(E, N, device="cuda")
+    aux = _bf16(rows, N, seed=6)
+    gate = torch.relu(_bf16(rows, N, seed=7))
+    out = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    colsum = torch.zeros(E, N, device="cuda")
+    gemm_rows(A, W, N, tile_info=plan.tile_info, tile_begin=0, tile_count=layout.total_tiles, bias=bias, aux=aux,
+              gate=gate, out=out, colsum=colsum, flags=EPI_ZERO_PAD)
+    row_e = _row_expert(layout, plan)
+    valid = row_e >= 0
+    Wf = W.float().view(E, N, K)
+    ref = torch.zeros(rows, N, device="cuda")
+    for e in range(E):
+        m = row_e == e
+        ref[m] = (A[m].float() @ Wf[e].t() + bias[e] + aux[m].float()) * (gate[m] > 0)
+    got = out.float()
+    # tiles that belong to an expert are fully written (valid rows: result, padding: zeros)
+    ti = plan.tile_info.cpu()
+    owned = torch.zeros(rows, dtype=torch.bool)
+    for t in range(layout.total_tiles):
+        if ti[t, 0] >= 0:
+            owned[t * 128:(t + 1) * 128] = True
+    owned = owned.cuda()
+    assert torch.isfinite(got[owned]).all()
+    assert (got[owned & ~valid] == 0).all()
+    err = (got[valid] - ref[valid]).abs().max().item()
+    assert err <= 2 ** -7 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+    ref_cs = torch.stack([got[row_e == e].sum(0) for e in range(E)])
+    assert torch.allclose(colsum, ref_cs, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("N1,N2", [(384, 768), (768, 96), (768, 192), (768, 384), (768, 768)])
+def test_grouped_wgrad(N1, N2):
+    n_items, E, P = 29, 3, [196, 49]
+    _, layout, plan = _random_plan(n_items, E, P, seed=8)
+    rows = layout.total_rows
+    row_e = _row_expert(layout, plan)
+    A = _bf16(rows, N1, seed=9)
+    A[row_e < 0] = 0          # contract: the A-side operand is zero in padding rows
+    Bm = _bf16(rows, N2, seed=10)
+    out = torch.zeros(E, N1, N2, device="cuda")
+    _lib.call("mm_grouped_gemm_wgrad", _lib.ptr(A), rows, N1, A.stride(0), _lib.ptr(Bm), rows, N2, Bm.stride(0),
+              _lib.ptr(plan.chunks), 0, layout.total_chunks, 0, _lib.ptr(out), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    for e in range(E):
+        m = row_e == e
+        ref = A[m].float().t() @ Bm[m].float()
+        err = (out[e] - ref).abs().max().item()
+        assert err <= 1e-3 * max(1.0, ref.abs().max().item()), f"expert {e}: max abs err {err}"
+
+
+def test_wgrad_region_subrange():
+    """Per-scale launch: chunk sub-range + tile_base offset + pointer offset into the row space."""
+    n_items, E, P = 21, 3, [100, 36]
+    _, layout, plan = _random_plan(n_items, E, P, seed=11)
+    s = 1
+    r0, r1 = layout.region_base[s], layout.region_base[s] + layout.region_rows[s]
+    row_e = _row_expert(layout, plan)[r0:r1]
+    A = _bf16(r1 - r0, 768, seed=12)
+    A[row_e < 0] = 0
+    Bm = _bf16(r1 - r0, 192, seed=13)
+    out = torch.zeros(E, 768, 192, device="cuda")
+    _lib.call("mm_grouped_gemm_wgrad", _lib.ptr(A), r1 - r0, 768, A.stride(0), _lib.ptr(Bm), r1 - r0, 192, Bm.stride(0),
+              _lib.ptr(plan.chunks), layout.chunk_base[s], layout.chunk_cap[s], layout.tile_base[s], _lib.ptr(out),
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    for e in range(E):
+        m = row_e == e
+        ref = A[m].float().t() @ Bm[m].float()
+        err = (out[e] - ref).abs().max().item()
+        assert err <= 1e-3 * max(1.0, ref.abs().max().item()), f"expert {e}: max abs err {err}"
