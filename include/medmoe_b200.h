@@ -39,6 +39,8 @@ enum mm_epilogue_flags { MM_EPI_RELU = 1, MM_EPI_ZERO_PAD = 2 };
 const char* mm_last_error(void);
 int mm_abi_version(void);
 int mm_device_sm_count(void);
+/* kernels launched through this library since it was loaded (bench evidence). */
+long long mm_launch_count(void);
 
 /* ---- (1) router gate: softmax + top-k -------------------------------------------------
  * replaces src/models/components/swin.py:98-100 (router MLP, softmax, argmax).

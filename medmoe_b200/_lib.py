@@ -20,6 +20,7 @@ SIGNATURES = {
     "mm_last_error": (C.c_char_p, []),
     "mm_abi_version": (c_int, []),
     "mm_device_sm_count": (c_int, []),
+    "mm_launch_count": (c_ll, []),
     "mm_router_topk": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mm_router_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp]),
@@ -53,7 +54,7 @@ SIGNATURES = {
 }
 
 # entry points that return a plain value, not an mm_status
-_VALUE_FUNCS = {"mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_combine_num_token_blocks",
+_VALUE_FUNCS = {"mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_gloria_workspace_floats"}
 
 
@@ -88,13 +89,41 @@ def last_error() -> str:
     return load().mm_last_error().decode("utf-8", "replace")
 
 
-def call(name: str, *args):
+class EventProfiler:
+    """Optional per-call CUDA-event timing on the launching stream (bench.py's roofline evidence).
+    Enabled by assigning an instance to `_lib.PROFILER`; costs two event records per C call."""
+
+    def __init__(self):
+        self.records = []   # (label, start_event, end_event)
+
+    def summary(self):
+        """label -> (calls, total_ms). Call after a device synchronize."""
+        out = {}
+        for label, a, b in self.records:
+            n, t = out.get(label, (0, 0.0))
+            out[label] = (n + 1, t + a.elapsed_time(b))
+        return out
+
+
+PROFILER = None
+
+
+def call(name: str, *args, label: str = None):
     """Call an mm_status entry point; raise RuntimeError(mm_last_error()) on failure."""
     lib = load()
     fn = getattr(lib, name)
-    rc = fn(*args)
     if name in _VALUE_FUNCS:
-        return rc
+        return fn(*args)
+    prof = PROFILER
+    if prof is not None:
+        import torch
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        prof.records.append((label or name, a, b))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
     return rc

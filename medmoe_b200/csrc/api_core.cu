@@ -6,11 +6,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 namespace mm {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -107,6 +111,7 @@ static int launch_rows(const CUtensorMap& tA, const CUtensorMap& tB, const RowsG
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
     kern<<<grid, 256, S::TOTAL, st>>>(tA, tB, args);
+    note_launches(1);
     return check_launch("gemm_rows");
 }
 
@@ -128,6 +133,7 @@ static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const Wgra
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
     kern<<<grid, 256, S::TOTAL, st>>>(tA, tB, args);
+    note_launches(1);
     return check_launch("gemm_wgrad");
 }
 
@@ -145,6 +151,8 @@ using namespace mm;
 extern "C" const char* mm_last_error(void) { return g_err; }
 
 extern "C" int mm_abi_version(void) { return 1; }
+
+extern "C" long long mm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int mm_device_sm_count(void) { return sm_count(); }
 

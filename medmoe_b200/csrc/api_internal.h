@@ -15,6 +15,8 @@ int check_launch(const char* what);
 int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
                      uint32_t box_inner, uint32_t box_rows, const char* what);
 int sm_count();
+// number of kernels launched through the C-ABI since load (bench.py's gpu_launches evidence)
+void note_launches(int n);
 }  // namespace mm
 
 #define MM_REQUIRE(cond, code, msg)        \

@@ -499,9 +499,11 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid(a.nblk, B);
     MM_DISPATCH_D(D, out_f32, combine_fwd_kernel, grid, st, a)
+    mm::note_launches(1);
     rc = mm_check_launch("mm_interp_softmax_combine_fwd");
     if (rc) return rc;
     global_mean_kernel<<<dim3((D + 255) / 256, B), 256, 0, st>>>(gpart, a.nblk, D, 1.0f / static_cast<float>(P), global_feat);
+    mm::note_launches(1);
     return mm_check_launch("mm_interp_softmax_combine_fwd(global mean)");
 }
 
@@ -528,16 +530,19 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     {
         dim3 grid(a.nblk, B);
         MM_DISPATCH_D(D, dlocal_f32, combine_bwd_logit_kernel, grid, st, a)
+        mm::note_launches(1);
         rc = mm_check_launch("mm_interp_softmax_combine_bwd(logit)");
         if (rc) return rc;
     }
     {
         dim3 grid(a.nrb, a.n_items + K);
         MM_DISPATCH_D(D, dlocal_f32, combine_bwd_rows_kernel, grid, st, a)
+        mm::note_launches(1);
         rc = mm_check_launch("mm_interp_softmax_combine_bwd(rows)");
         if (rc) return rc;
     }
     const int C = 2 * (D / 2) + 1;
     expert_reduce_kernel<<<dim3((C + 255) / 256, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
+    mm::note_launches(1);
     return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");
 }

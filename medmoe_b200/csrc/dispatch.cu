@@ -273,6 +273,7 @@ extern "C" int mm_dispatch_build(const int32_t* item_expert, int n_items, int K,
     dispatch_build_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
         item_expert, a, counts, offsets, perm, inv_perm, slot_expert, seg_start, slot_row,
         reinterpret_cast<int2*>(tile_info), reinterpret_cast<int4*>(chunks));
+    mm::note_launches(1);
     return mm_check_launch("mm_dispatch_build");
 }
 
@@ -300,6 +301,7 @@ extern "C" int mm_dispatch_rows(const void* const* src, int src_is_f32, void* co
         dispatch_rows_kernel<float><<<grid, 256, 0, st>>>(a, perm, slot_row, counts, seg_start);
     else
         dispatch_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, perm, slot_row, counts, seg_start);
+    mm::note_launches(1);
     return mm_check_launch("mm_dispatch_rows");
 }
 
@@ -325,6 +327,7 @@ extern "C" int mm_undispatch_rows(const void* const* src, void* const* dst, int 
         undispatch_rows_kernel<float><<<grid, 256, 0, st>>>(a, inv_perm, slot_row);
     else
         undispatch_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, inv_perm, slot_row);
+    mm::note_launches(1);
     return mm_check_launch("mm_undispatch_rows");
 }
 
@@ -337,6 +340,7 @@ extern "C" int mm_cast_f32_bf16(const float* src, void* dst, long long n, void* 
     if (blocks > 148 * 16) blocks = 148 * 16;
     cast_f32_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, static_cast<__nv_bfloat16*>(dst), n);
+    mm::note_launches(1);
     return mm_check_launch("mm_cast_f32_bf16");
 }
 
@@ -344,5 +348,6 @@ extern "C" int mm_transpose_cast_f32_bf16(const float* src, void* dst, int batch
     MM_REQUIRE(batch > 0 && R > 0 && C > 0, MM_ERR_BAD_SHAPE, "mm_transpose_cast_f32_bf16: bad shape");
     dim3 grid((C + 31) / 32, (R + 31) / 32, batch);
     transpose_cast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), R, C);
+    mm::note_launches(1);
     return mm_check_launch("mm_transpose_cast_f32_bf16");
 }

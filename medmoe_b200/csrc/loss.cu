@@ -271,6 +271,7 @@ static int run_sgemm(const SgemmArgs& a, cudaStream_t st, const char* what) {
     if (a.M <= 0 || a.N <= 0) return MM_OK;
     dim3 grid((a.N + 63) / 64, (a.M + 63) / 64);
     sgemm_kernel<<<grid, 256, 0, st>>>(a);
+    mm::note_launches(1);
     return check_launch(what);
 }
 
@@ -291,17 +292,24 @@ extern "C" int mm_gloria_global_fwd(const float* img, const float* txt, int B, i
     float* S = ws; float* na = ws + 2LL * B * B; float* nb = na + B; float* lse_r = nb + B; float* lse_c = lse_r + B;
     float* diag = lse_c + B; float* tmp = diag + 3LL * B;
     row_norm_kernel<<<warp_rows_grid(B), 256, 0, st>>>(img, B, D, na);
+    mm::note_launches(1);
     row_norm_kernel<<<warp_rows_grid(B), 256, 0, st>>>(txt, B, D, nb);
+    mm::note_launches(1);
     SgemmArgs g{};
     g.A = img; g.sam = D; g.sak = 1; g.B = txt; g.sbk = 1; g.sbn = D; g.C = S; g.ldc = B; g.M = B; g.N = B; g.K = D;
     g.alpha = temp; g.na = na; g.nb = nb; g.eps = eps;
     int rc = run_sgemm(g, st, "mm_gloria_global_fwd(sgemm)");
     if (rc) return rc;
     lse_rows_kernel<<<warp_rows_grid(B), 256, 0, st>>>(S, B, B, B, 0, lse_r, diag);
+    mm::note_launches(1);
     lse_cols_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, B, B, lse_c);
+    mm::note_launches(1);
     ce_reduce_kernel<<<1, 256, 0, st>>>(lse_r, diag, nullptr, B, tmp);
+    mm::note_launches(1);
     ce_reduce_kernel<<<1, 256, 0, st>>>(lse_c, diag, nullptr, B, tmp + 1);
+    mm::note_launches(1);
     sum_reduce_kernel<<<1, 256, 0, st>>>(tmp, 2, loss, 0);
+    mm::note_launches(1);
     return mm_check_launch("mm_gloria_global_fwd");
 }
 
@@ -312,7 +320,9 @@ extern "C" int mm_gloria_global_bwd(const float* img, const float* txt, int B, i
     float* S = ws; float* G = ws + 1LL * B * B; float* na = ws + 2LL * B * B; float* nb = na + B; float* lse_r = nb + B;
     float* lse_c = lse_r + B; float* rs = lse_c + 2LL * B; float* cs = rs + B;
     gloria_bwd_rows_kernel<<<warp_rows_grid(B), 256, 0, st>>>(S, B, lse_r, lse_c, na, nb, temp, eps, gout, G, rs);
+    mm::note_launches(1);
     gloria_bwd_cols_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, B, lse_r, lse_c, na, nb, eps, gout, cs);
+    mm::note_launches(1);
     int rc = MM_OK;
     if (dimg) {   // dI = G T + rs * I
         SgemmArgs g{};
@@ -343,7 +353,9 @@ extern "C" int mm_infonce_fwd(const float* a, const float* b_all, int R, int N, 
     int rc = run_sgemm(g, st, "mm_infonce_fwd(sgemm)");
     if (rc) return rc;
     lse_rows_kernel<<<warp_rows_grid(R), 256, 0, st>>>(logits, R, N, N, label0, lse, picked);
+    mm::note_launches(1);
     ce_reduce_kernel<<<1, 256, 0, st>>>(lse, picked, row_w, R, loss);
+    mm::note_launches(1);
     return mm_check_launch("mm_infonce_fwd");
 }
 
@@ -356,7 +368,11 @@ extern "C" int mm_infonce_bwd(const float* a, const float* b_all, int R, int N, 
     MM_REQUIRE(R > 0 && N > 0 && D > 0, MM_ERR_BAD_SHAPE, "mm_infonce_bwd: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     softmax_ce_bwd_kernel<<<warp_rows_grid(R), 256, 0, st>>>(logits, R, N, N, label0, lse, row_w, gout, gmul, dlogits, row_tmp);
-    if (dscale) sum_reduce_kernel<<<1, 256, 0, st>>>(row_tmp, R, dscale, accumulate_dscale);
+    mm::note_launches(1);
+    if (dscale) {
+        sum_reduce_kernel<<<1, 256, 0, st>>>(row_tmp, R, dscale, accumulate_dscale);
+        mm::note_launches(1);
+    }
     int rc = MM_OK;
     if (da) {
         SgemmArgs g{};
@@ -377,11 +393,13 @@ extern "C" int mm_infonce_bwd(const float* a, const float* b_all, int R, int N, 
 extern "C" int mm_l2_normalize_fwd(const float* x, int R, int D, float eps, float* y, float* norms, void* stream) {
     MM_REQUIRE(R > 0 && D > 0, MM_ERR_BAD_SHAPE, "mm_l2_normalize_fwd: bad shape");
     l2_normalize_kernel<<<warp_rows_grid(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, R, D, eps, y, norms);
+    mm::note_launches(1);
     return mm_check_launch("mm_l2_normalize_fwd");
 }
 extern "C" int mm_l2_normalize_bwd(const float* dy, const float* y, const float* norms, int R, int D, float eps, float* dx, void* stream) {
     MM_REQUIRE(R > 0 && D > 0, MM_ERR_BAD_SHAPE, "mm_l2_normalize_bwd: bad shape");
     l2_normalize_bwd_kernel<<<warp_rows_grid(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, norms, R, D, eps, dx);
+    mm::note_launches(1);
     return mm_check_launch("mm_l2_normalize_bwd");
 }
 
@@ -389,5 +407,6 @@ extern "C" int mm_zeroshot_argmax(const float* img, const float* txt, int M, int
                                   float* sim, void* stream) {
     MM_REQUIRE(M > 0 && C > 0 && D > 0, MM_ERR_BAD_SHAPE, "mm_zeroshot_argmax: bad shape");
     zeroshot_kernel<<<warp_rows_grid(M), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, txt, M, C, D, eps, pred, sim);
+    mm::note_launches(1);
     return mm_check_launch("mm_zeroshot_argmax");
 }

@@ -146,6 +146,7 @@ extern "C" int mm_router_topk(const float* x, int B, int D, const float* W1, con
     const size_t smem = (static_cast<size_t>(D) + ROUTER_HID + K) * sizeof(float);
     router_fwd_kernel<<<B, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, D, W1, b1, W2, b2, K, topk, hidden,
                                                                           probs, topk_idx, topk_w);
+    mm::note_launches(1);
     return mm_check_launch("mm_router_topk");
 }
 
@@ -155,9 +156,12 @@ extern "C" int mm_router_bwd(const float* dprobs, const float* probs, const floa
     MM_REQUIRE(B > 0 && D > 0 && K > 0 && K <= ROUTER_MAX_K, MM_ERR_BAD_SHAPE, "mm_router_bwd: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     router_bwd_sample_kernel<<<B, 128, 0, st>>>(dprobs, probs, hidden, W1, W2, D, K, dlogit, dhidden, dx);
+    mm::note_launches(1);
     // dW1[128, D] = dh^T x ; db1 = sum_b dh
     batch_outer_kernel<<<dim3((D + 255) / 256, ROUTER_HID), 256, 0, st>>>(dhidden, ROUTER_HID, x, D, B, D, dW1, db1);
+    mm::note_launches(1);
     // dW2[K, 128] = dlogit^T h ; db2 = sum_b dlogit
     batch_outer_kernel<<<dim3(1, K), 256, 0, st>>>(dlogit, K, hidden, ROUTER_HID, B, ROUTER_HID, dW2, db2);
+    mm::note_launches(1);
     return mm_check_launch("mm_router_bwd");
 }

@@ -1,0 +1,252 @@
+"""`MoE` — drop-in for the reference's modality-specialised mixture-of-experts block.
+
+Mirrors `src/models/components/swin.py` of the reference:
+  * `Expert(hidden_dims, output_dim)`                       swin.py:11-30   (parameter container, same submodule names)
+  * `MoE(num_experts=6, hidden_dims=[96,192,384,768], output_dim=768, router_input_dim=768)`   swin.py:83-92
+  * `MoE.forward(multi_scale_feats, swin_feat) -> (global_feat, local_feat, router_probs)`     swin.py:94-117
+with identical `state_dict` keys (`experts.{e}.proj_convs.{s}.0.weight`, `experts.{e}.attn_proj.{0,2}.*`,
+`router.{0,2}.*`), identical default initialisation (the same nn modules are constructed in the
+same order, so a given torch seed yields the same weights as the reference) and the same
+autograd-visible behaviour (zero — not None — gradients for experts no image selected; the
+router is trained only through the returned probabilities).
+
+The arithmetic runs in hand-written sm_100a kernels behind the C-ABI (`medmoe_b200._lib`):
+router gate -> dispatch (counting sort by expert) -> grouped tcgen05 GEMMs -> fused
+interpolate/softmax/combine, and the matching backward.  bf16 operands, fp32 accumulation;
+router, softmaxes and reductions in fp32.  There is no CPU path.
+
+`topk > 1` is an extension the reference does not have: out = sum_j g_j expert_j(x)
+with g the renormalised top-k router probabilities; `topk=1` (default) is the reference.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .plan import build_plan, make_layout
+
+
+class Expert(nn.Module):
+    """Parameter container with the reference's layout (swin.py:11-30).
+
+    The per-expert arithmetic is executed by `MoE.forward` on the fused CUDA path; calling an
+    expert on its own routes every image to it through the same kernels."""
+
+    def __init__(self, hidden_dims: Sequence[int] = (96, 192, 384, 768), output_dim: int = 768):
+        super().__init__()
+        self.output_dim = output_dim
+        self.num_scales = len(hidden_dims)
+        self.proj_convs = nn.ModuleList([
+            nn.Sequential(nn.Conv1d(dim, output_dim, kernel_size=1), nn.ReLU()) for dim in hidden_dims
+        ])
+        self.attn_proj = nn.Sequential(
+            nn.Linear(output_dim, output_dim // 2),
+            nn.ReLU(),
+            nn.Linear(output_dim // 2, 1),
+        )
+
+    def forward(self, multi_scale_feats):
+        B = multi_scale_feats[0].shape[0]
+        item_expert = torch.zeros(B, 1, dtype=torch.int32, device=multi_scale_feats[0].device)
+        out, _ = _run_experts([self], list(multi_scale_feats), item_expert, None, 1)
+        return out
+
+
+def _expert_param_list(experts: Sequence[Expert]) -> List[torch.Tensor]:
+    ps: List[torch.Tensor] = []
+    for ex in experts:
+        for seq in ex.proj_convs:
+            ps += [seq[0].weight, seq[0].bias]
+        ps += [ex.attn_proj[0].weight, ex.attn_proj[0].bias, ex.attn_proj[2].weight, ex.attn_proj[2].bias]
+    return ps
+
+
+class _ExpertsFunction(torch.autograd.Function):
+    """(feats..., expert params...) -> (fused [B, P, D], global_feat [B, D]) for a given routing."""
+
+    @staticmethod
+    def forward(ctx, item_expert, gate, topk, num_experts, n_scales, *tensors):
+        feats = list(tensors[:n_scales])
+        params = tensors[n_scales:]
+        per = 2 * n_scales + 4
+        assert len(params) == num_experts * per
+        dev = feats[0].device
+        B = feats[0].shape[0]
+        P = [f.shape[1] for f in feats]
+        widths = [f.shape[2] for f in feats]
+        if P[0] != max(P):
+            raise RuntimeError("stage features must be ordered finest first (reference swin.py:139)")
+        E, S = num_experts, n_scales
+        if S != 4:
+            raise RuntimeError("medmoe_b200 supports exactly 4 feature scales (reference default hidden_dims)")
+        D = params[0].shape[0]
+        H = D // 2
+        in_dtype = feats[0].dtype
+
+        # ---- bf16 shadows of the fp32 master weights (stacked over experts) ----
+        def ex(e, i):
+            return params[e * per + i]
+        with torch.no_grad():
+            Wp32 = [torch.stack([ex(e, 2 * s).reshape(D, widths[s]) for e in range(E)]) for s in range(S)]   # [E, D, D_s]
+            bp = [torch.stack([ex(e, 2 * s + 1) for e in range(E)]).float().contiguous() for s in range(S)]    # [E, D]
+            W1_32 = torch.stack([ex(e, 2 * S) for e in range(E)])                                              # [E, H, D]
+            b1 = torch.stack([ex(e, 2 * S + 1) for e in range(E)]).float().contiguous()                         # [E, H]
+            w2 = torch.stack([ex(e, 2 * S + 2).reshape(H) for e in range(E)]).float().contiguous()              # [E, H]
+            b2 = torch.stack([ex(e, 2 * S + 3).reshape(()) for e in range(E)]).float().contiguous()             # [E]
+            Wp = [ops.cast_bf16(w.float()).view(E * D, widths[s]) for s, w in enumerate(Wp32)]
+            W1 = ops.cast_bf16(W1_32.float()).view(E * H, D)
+
+        layout = make_layout(B, topk, E, P)
+        plan = build_plan(item_expert.reshape(-1).contiguous(), layout)
+        feats_c = [f.contiguous() for f in feats]
+        fs = ops.dispatch_rows(feats_c, plan, widths)
+
+        Y = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
+        Z = torch.empty(layout.total_rows, H, dtype=torch.bfloat16, device=dev)
+        for s in range(S):   # E1: Y_s = ReLU(f_s W_s^T + b_s)
+            r0 = layout.region_base[s]
+            ops.gemm_rows(fs[s], Wp[s], D, Y[r0:r0 + layout.region_rows[s]], plan=plan, tile_begin=layout.tile_base[s],
+                          tile_count=layout.region_tiles[s], bias=bp[s], flags=ops.EPI_RELU | ops.EPI_ZERO_PAD, tag=f"E1.s{s}")
+        # E4 at native resolution: Z = Y W1^T + b1 (the lerp commutes with the affine map)
+        ops.gemm_rows(Y, W1, H, Z, plan=plan, tile_begin=0, tile_count=layout.total_tiles, bias=b1, flags=ops.EPI_ZERO_PAD,
+                      tag="E4")
+        gate_flat = gate.reshape(-1).float().contiguous() if gate is not None else None
+        fused, gfeat, beta = ops.combine_fwd(Y, Z, w2, b2, plan, D, gate_flat, in_dtype)
+
+        ctx.plan, ctx.layout = plan, layout
+        ctx.dims = (B, E, S, D, H, widths, topk, per, in_dtype)
+        ctx.saved = (fs, Y, Z, beta, w2, W1_32, Wp32, gate_flat)
+        ctx.feat_needs_grad = [f.requires_grad for f in feats]
+        ctx.param_needs_grad = any(p.requires_grad for p in params)
+        ctx.gate_needs_grad = gate is not None and gate.requires_grad
+        ctx.set_materialize_grads(False)
+        return fused, gfeat.to(in_dtype)
+
+    @staticmethod
+    def backward(ctx, dfused, dglobal):
+        plan, layout = ctx.plan, ctx.layout
+        B, E, S, D, H, widths, topk, per, in_dtype = ctx.dims
+        fs, Y, Z, beta, w2, W1_32, Wp32, gate_flat = ctx.saved
+        dev = Y.device
+        n_in = 5 + S + E * per
+        if dfused is None and dglobal is None:
+            return (None,) * n_in
+        if dfused is not None:
+            if dfused.dtype not in (torch.float32, torch.bfloat16):
+                dfused = dfused.float()
+            dfused = dfused.contiguous()
+        dglobal32 = dglobal.float().contiguous() if dglobal is not None else None
+
+        dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
+                                                        ctx.gate_needs_grad)
+        # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT; column sums -> conv bias gradients
+        W1T = ops.transpose_cast_bf16(W1_32.float()).view(E * D, H)          # [E, D, H]
+        dbp = [torch.zeros(E, D, dtype=torch.float32, device=dev) for _ in range(S)]
+        for s in range(S):
+            r0, nr = layout.region_base[s], layout.region_rows[s]
+            ops.gemm_rows(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
+                          tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr], colsum=dbp[s],
+                          flags=ops.EPI_ZERO_PAD, tag=f"dY.s{s}")
+        dPre = dUT
+
+        grads_feats: List = [None] * S
+        if any(ctx.feat_needs_grad):
+            dfs = []
+            for s in range(S):   # df_s = dPre_s W_s
+                r0, nr = layout.region_base[s], layout.region_rows[s]
+                WsT = ops.transpose_cast_bf16(Wp32[s].float()).view(E * widths[s], D)   # [E, D_s, D]
+                out = torch.empty(nr, widths[s], dtype=torch.bfloat16, device=dev)
+                ops.gemm_rows(dPre[r0:r0 + nr], WsT, widths[s], out, plan=plan, tile_begin=layout.tile_base[s],
+                              tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
+                dfs.append(out)
+            outs = ops.undispatch_rows(dfs, plan, widths, in_dtype)
+            grads_feats = [o if need else None for o, need in zip(outs, ctx.feat_needs_grad)]
+
+        grads_params: List = [None] * (E * per)
+        if ctx.param_needs_grad:
+            dW1 = torch.zeros(E, H, D, dtype=torch.float32, device=dev)
+            ops.gemm_wgrad(dZ, Y, dW1, plan, 0, layout.total_chunks, 0, tag="dW1")
+            dWp = []
+            for s in range(S):
+                r0, nr = layout.region_base[s], layout.region_rows[s]
+                g = torch.zeros(E, D, widths[s], dtype=torch.float32, device=dev)
+                ops.gemm_wgrad(dPre[r0:r0 + nr], fs[s], g, plan, layout.chunk_base[s], layout.chunk_cap[s],
+                               layout.tile_base[s], tag=f"dWp.s{s}")
+                dWp.append(g)
+            for e in range(E):
+                for s in range(S):
+                    grads_params[e * per + 2 * s] = dWp[s][e].unsqueeze(-1)       # Conv1d weight [D, D_s, 1]
+                    grads_params[e * per + 2 * s + 1] = dbp[s][e]
+                grads_params[e * per + 2 * S] = dW1[e]
+                grads_params[e * per + 2 * S + 1] = db1[e]
+                grads_params[e * per + 2 * S + 2] = dw2[e].unsqueeze(0)           # Linear(H, 1) weight [1, H]
+                grads_params[e * per + 2 * S + 3] = db2[e].reshape(1)
+        dgate_out = dgate.view(B, topk) if dgate is not None else None
+        return (None, dgate_out, None, None, None, *grads_feats, *grads_params)
+
+
+def _run_experts(experts, feats, item_expert, gate, topk):
+    params = _expert_param_list(experts)
+    return _ExpertsFunction.apply(item_expert, gate, topk, len(experts), len(feats), *feats, *params)
+
+
+class _RouterFunction(torch.autograd.Function):
+    """swin_feat -> (probs [B, K] fp32, topk_idx [B, k] int32, topk_w [B, k]); probs is differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, topk):
+        x32 = x.float().contiguous()
+        W1c, b1c, W2c, b2c = (t.float().contiguous() for t in (W1, b1, W2, b2))
+        hidden, probs, idx, w = ops.router_topk(x32, W1c, b1c, W2c, b2c, topk)
+        ctx.save_for_backward(x32, W1c, W2c, hidden, probs)
+        ctx.x_dtype = x.dtype
+        ctx.need_dx = x.requires_grad
+        ctx.mark_non_differentiable(idx, w)
+        ctx.set_materialize_grads(False)
+        return probs, idx, w
+
+    @staticmethod
+    def backward(ctx, dprobs, _didx, _dw):
+        if dprobs is None:
+            return (None,) * 6
+        x32, W1c, W2c, hidden, probs = ctx.saved_tensors
+        dx, dW1, db1, dW2, db2 = ops.router_bwd(dprobs.float().contiguous(), probs, hidden, x32, W1c, W2c, ctx.need_dx)
+        return (dx.to(ctx.x_dtype) if dx is not None else None), dW1, db1, dW2, db2, None
+
+
+class MoE(nn.Module):
+    def __init__(self, num_experts: int = 6, hidden_dims: Sequence[int] = (96, 192, 384, 768), output_dim: int = 768,
+                 router_input_dim: int = 768, topk: int = 1):
+        super().__init__()
+        hidden_dims = list(hidden_dims)
+        self.experts = nn.ModuleList([Expert(hidden_dims, output_dim) for _ in range(num_experts)])
+        self.router = nn.Sequential(
+            nn.Linear(router_input_dim, 128),
+            nn.ReLU(),
+            nn.Linear(128, num_experts),
+        )
+        self.topk = int(topk)
+        self.last_top_expert = None   # int32 [B, topk] of the most recent forward (device tensor, no sync)
+
+    def forward(self, multi_scale_feats, swin_feat):
+        """multi_scale_feats: list of 4 tensors [B, P_s, D_s] (finest first); swin_feat [B, router_input_dim].
+        Returns (global_feat [B, D], local_feat [B, D, sqrt(P), sqrt(P)], router_probs [B, K])."""
+        feats = list(multi_scale_feats)
+        if not feats[0].is_cuda:
+            raise RuntimeError("medmoe_b200.MoE runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        probs, idx, w = _RouterFunction.apply(swin_feat, self.router[0].weight, self.router[0].bias,
+                                              self.router[2].weight, self.router[2].bias, self.topk)
+        self.last_top_expert = idx
+        gate = None
+        if self.topk > 1:
+            # extension: renormalised top-k probabilities, differentiable w.r.t. the router (tiny torch ops)
+            sel = probs.gather(1, idx.long())
+            gate = sel / sel.sum(dim=1, keepdim=True)
+        fused, global_feat = _run_experts(list(self.experts), feats, idx, gate, self.topk)
+        B, P, D = fused.shape
+        Hh = Ww = int(P ** 0.5)                                       # swin.py:111
+        local_feat = fused.transpose(1, 2).reshape(B, D, Hh, Ww)      # a stride view, as in the reference
+        return global_feat, local_feat, probs

@@ -1,0 +1,233 @@
+"""Thin tensor-level wrappers over the C-ABI (include/medmoe_b200.h).
+
+Each wrapper only checks device / dtype / contiguity and forwards raw pointers plus the
+current CUDA stream.  There is deliberately no CPU or PyTorch fallback: a tensor that is
+not on a CUDA device raises.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .plan import DispatchPlan, RowLayout
+
+EPI_RELU, EPI_ZERO_PAD = 1, 2
+_P = _lib.ptr
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("medmoe_b200 kernels run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _st():
+    return _lib.stream_ptr()
+
+
+# ---- router ---------------------------------------------------------------------------
+def router_topk(x, W1, b1, W2, b2, topk: int):
+    _need_cuda(x, W1, b1, W2, b2)
+    B, D = x.shape
+    K = W2.shape[0]
+    f32 = dict(dtype=torch.float32, device=x.device)
+    hidden = torch.empty(B, 128, **f32)
+    probs = torch.empty(B, K, **f32)
+    idx = torch.empty(B, topk, dtype=torch.int32, device=x.device)
+    w = torch.empty(B, topk, **f32)
+    _lib.call("mm_router_topk", _P(x), B, D, _P(W1), _P(b1), _P(W2), _P(b2), K, topk, _P(hidden), _P(probs), _P(idx),
+              _P(w), _st())
+    return hidden, probs, idx, w
+
+
+def router_bwd(dprobs, probs, hidden, x, W1, W2, need_dx: bool):
+    _need_cuda(dprobs, probs, hidden, x, W1, W2)
+    B, D = x.shape
+    K = W2.shape[0]
+    f32 = dict(dtype=torch.float32, device=x.device)
+    dlogit = torch.empty(B, K, **f32)
+    dhidden = torch.empty(B, 128, **f32)
+    dx = torch.empty(B, D, **f32) if need_dx else None
+    dW1 = torch.empty(128, D, **f32); db1 = torch.empty(128, **f32)
+    dW2 = torch.empty(K, 128, **f32); db2 = torch.empty(K, **f32)
+    _lib.call("mm_router_bwd", _P(dprobs), _P(probs), _P(hidden), _P(x), _P(W1), _P(W2), B, D, K, _P(dlogit), _P(dhidden),
+              _P(dx), _P(dW1), _P(db1), _P(dW2), _P(db2), _st())
+    return dx, dW1, db1, dW2, db2
+
+
+# ---- dispatch -------------------------------------------------------------------------
+def dispatch_rows(feats: Sequence[torch.Tensor], plan: DispatchPlan, widths: Sequence[int]) -> List[torch.Tensor]:
+    """[B, P_s, D_s] (fp32|bf16, image order) -> bf16 [region_rows_s, D_s] (expert-sorted, padded)."""
+    lay = plan.layout
+    _need_cuda(*feats)
+    src_f32 = feats[0].dtype == torch.float32
+    for f in feats:
+        if f.dtype != feats[0].dtype or f.dtype not in (torch.float32, torch.bfloat16) or not f.is_contiguous():
+            raise RuntimeError("stage features must be contiguous and all fp32 or all bf16")
+    dst = [torch.empty(lay.region_rows[s], widths[s], dtype=torch.bfloat16, device=feats[0].device) for s in range(lay.S)]
+    _lib.call("mm_dispatch_rows", _lib.host_ptrs(feats), int(src_f32), _lib.host_ptrs(dst), lay.n_items, lay.topk,
+              lay.num_experts, lay.S, _lib.host_i32(lay.P), _lib.host_i32(widths), _lib.host_i32(lay.region_base),
+              _P(plan.perm), _P(plan.slot_row), _P(plan.counts), _P(plan.seg_start), _st())
+    return dst
+
+
+def undispatch_rows(srcs: Sequence[torch.Tensor], plan: DispatchPlan, widths: Sequence[int], out_dtype) -> List[torch.Tensor]:
+    lay = plan.layout
+    _need_cuda(*srcs)
+    dst = [torch.empty(lay.n_images, lay.P[s], widths[s], dtype=out_dtype, device=srcs[0].device) for s in range(lay.S)]
+    _lib.call("mm_undispatch_rows", _lib.host_ptrs(srcs), _lib.host_ptrs(dst), int(out_dtype == torch.float32),
+              lay.n_images, lay.topk, lay.S, _lib.host_i32(lay.P), _lib.host_i32(widths),
+              _lib.host_i32(lay.region_base), _P(plan.inv_perm), _P(plan.slot_row), _st())
+    return dst
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    _need_cuda(src)
+    src = src.contiguous()
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _lib.call("mm_cast_f32_bf16", _P(src), _P(dst), src.numel(), _st())
+    return dst
+
+
+def transpose_cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    """fp32 [batch, R, C] -> bf16 [batch, C, R]."""
+    _need_cuda(src)
+    src = src.contiguous()
+    b, R, Cc = src.shape
+    dst = torch.empty(b, Cc, R, dtype=torch.bfloat16, device=src.device)
+    _lib.call("mm_transpose_cast_f32_bf16", _P(src), _P(dst), b, R, Cc, _st())
+    return dst
+
+
+# ---- grouped GEMMs --------------------------------------------------------------------
+def gemm_rows(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, plan: Optional[DispatchPlan] = None,
+              tile_begin: int = 0, tile_count: int = 0, M: int = 0, bias=None, aux=None, gate=None, colsum=None,
+              flags: int = 0, out_scale: float = 1.0, tag: str = ""):
+    """out[rows, N] = epi(A[rows, K] W_e[N, K]^T); W is the stacked [E * N, K] bf16 weight."""
+    _need_cuda(A, W, out)
+    E = W.shape[0] // N
+    _lib.call("mm_grouped_gemm_rows", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(W), E, N, W.stride(0),
+              _P(plan.tile_info) if plan is not None else 0, tile_begin, tile_count, M, _P(bias),
+              _P(aux), aux.stride(0) if aux is not None else 0, _P(gate), gate.stride(0) if gate is not None else 0,
+              _P(out), out.stride(0), int(out.dtype == torch.float32), _P(colsum), float(out_scale), flags, _st(),
+              label=f"{tag}:gemm_rows[K={A.shape[1]},N={N}]")
+    return out
+
+
+def gemm_wgrad(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, plan: DispatchPlan, chunk_begin: int,
+               chunk_count: int, tile_base: int, tag: str = ""):
+    """out[e] (+)= A_e^T B_e over the rows of expert e; out fp32 [E, N1, N2] must be pre-zeroed."""
+    _need_cuda(A, Bm, out)
+    _lib.call("mm_grouped_gemm_wgrad", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(Bm), Bm.shape[0], Bm.shape[1],
+              Bm.stride(0), _P(plan.chunks), chunk_begin, chunk_count, tile_base, _P(out), _st(),
+              label=f"{tag}:gemm_wgrad[N1={A.shape[1]},N2={Bm.shape[1]}]")
+    return out
+
+
+# ---- combine --------------------------------------------------------------------------
+def combine_fwd(Y, Z, w2, b2, plan: DispatchPlan, D: int, gate, out_dtype):
+    lay = plan.layout
+    _need_cuda(Y, Z, w2, b2)
+    B, P = lay.n_images, lay.P[0]
+    dev = Y.device
+    nblk = _lib.call("mm_combine_num_token_blocks", P)
+    beta = torch.empty(lay.n_items, P, 4, dtype=torch.float32, device=dev)
+    out = torch.empty(B, P, D, dtype=out_dtype, device=dev)
+    gpart = torch.empty(B, nblk, D, dtype=torch.float32, device=dev)
+    gfeat = torch.empty(B, D, dtype=torch.float32, device=dev)
+    _lib.call("mm_interp_softmax_combine_fwd", _P(Y), _P(Z), _P(w2), _P(b2), B, lay.topk, P, _lib.host_i32(lay.P), D,
+              _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(gate), _P(beta), _P(out),
+              int(out_dtype == torch.float32), _P(gpart), _P(gfeat), _st())
+    return out, gfeat, beta
+
+
+def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool):
+    lay = plan.layout
+    _need_cuda(Y, Z, w2, beta, dlocal, dglobal)
+    B, P, K = lay.n_images, lay.P[0], lay.num_experts
+    dev = Y.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    nrb = _lib.call("mm_combine_num_row_blocks", _lib.host_i32(lay.P))
+    dlogit = torch.empty(lay.n_items, P, 4, **f32)
+    dgate = torch.zeros(lay.n_items, **f32) if need_dgate else None
+    dUT = torch.empty(lay.total_rows, D, dtype=torch.bfloat16, device=dev)
+    dZ = torch.empty(lay.total_rows, D // 2, dtype=torch.bfloat16, device=dev)
+    part = torch.empty(lay.n_items, nrb, D + 1, **f32)
+    red = torch.empty(K, D + 1, **f32)
+    dl_f32 = dlocal is not None and dlocal.dtype == torch.float32
+    _lib.call("mm_interp_softmax_combine_bwd", _P(Y), _P(Z), _P(w2), B, lay.topk, P, _lib.host_i32(lay.P), D, K,
+              _P(plan.perm), _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(plan.counts),
+              _P(plan.seg_start), _P(plan.offsets), _P(gate), _P(beta), _P(dlocal), int(dl_f32), _P(dglobal),
+              _P(dlogit), _P(dgate), _P(dUT), _P(dZ), _P(part), _P(red), _st())
+    H = D // 2
+    return dUT, dZ, red[:, :H], red[:, H:2 * H], red[:, 2 * H], dgate
+
+
+# ---- losses ---------------------------------------------------------------------------
+def gloria_fwd(img, txt, temp: float, eps: float):
+    _need_cuda(img, txt)
+    B, D = img.shape
+    ws = torch.empty(_lib.call("mm_gloria_workspace_floats", B), dtype=torch.float32, device=img.device)
+    loss = torch.empty((), dtype=torch.float32, device=img.device)
+    _lib.call("mm_gloria_global_fwd", _P(img), _P(txt), B, D, float(temp), float(eps), _P(ws), _P(loss), _st())
+    return loss, ws
+
+
+def gloria_bwd(img, txt, temp: float, eps: float, ws, gout, need_dimg: bool, need_dtxt: bool):
+    B, D = img.shape
+    dimg = torch.empty_like(img) if need_dimg else None
+    dtxt = torch.empty_like(txt) if need_dtxt else None
+    _lib.call("mm_gloria_global_bwd", _P(img), _P(txt), B, D, float(temp), float(eps), _P(ws), _P(gout), _P(dimg),
+              _P(dtxt), _st())
+    return dimg, dtxt
+
+
+def infonce_fwd(a, b_all, scale_exp, label0: int, row_w):
+    _need_cuda(a, b_all, scale_exp)
+    R, D = a.shape
+    N = b_all.shape[0]
+    f32 = dict(dtype=torch.float32, device=a.device)
+    logits = torch.empty(R, N, **f32); lse = torch.empty(R, **f32); picked = torch.empty(R, **f32)
+    loss = torch.empty((), **f32)
+    _lib.call("mm_infonce_fwd", _P(a), _P(b_all), R, N, D, _P(scale_exp), label0, _P(row_w), _P(logits), _P(lse),
+              _P(picked), _P(loss), _st())
+    return loss, logits, lse
+
+
+def infonce_bwd(a, b_all, scale_exp, label0: int, row_w, logits, lse, gout, gmul: float, dscale, accumulate_dscale: bool):
+    R, D = a.shape
+    N = b_all.shape[0]
+    f32 = dict(dtype=torch.float32, device=a.device)
+    dlogits = torch.empty(R, N, **f32); row_tmp = torch.empty(R, **f32)
+    da = torch.empty(R, D, **f32); db_all = torch.empty(N, D, **f32)
+    _lib.call("mm_infonce_bwd", _P(a), _P(b_all), R, N, D, _P(scale_exp), label0, _P(row_w), _P(logits), _P(lse),
+              _P(gout), float(gmul), _P(dlogits), _P(row_tmp), _P(da), _P(db_all), _P(dscale), int(accumulate_dscale),
+              _st())
+    return da, db_all
+
+
+def l2_normalize_fwd(x, eps: float = 1e-12):
+    _need_cuda(x)
+    R, D = x.shape
+    y = torch.empty_like(x); n = torch.empty(R, dtype=torch.float32, device=x.device)
+    _lib.call("mm_l2_normalize_fwd", _P(x), R, D, float(eps), _P(y), _P(n), _st())
+    return y, n
+
+
+def l2_normalize_bwd(dy, y, n, eps: float = 1e-12):
+    R, D = y.shape
+    dx = torch.empty_like(y)
+    _lib.call("mm_l2_normalize_bwd", _P(dy), _P(y), _P(n), R, D, float(eps), _P(dx), _st())
+    return dx
+
+
+def zeroshot_argmax(img, txt, eps: float = 1e-8, return_sim: bool = False):
+    _need_cuda(img, txt)
+    M, D = img.shape
+    Cn = txt.shape[0]
+    pred = torch.empty(M, dtype=torch.int64, device=img.device)
+    sim = torch.empty(M, Cn, dtype=torch.float32, device=img.device) if return_sim else None
+    _lib.call("mm_zeroshot_argmax", _P(img), _P(txt), M, Cn, D, float(eps), _P(pred), _P(sim), _st())
+    return (pred, sim) if return_sim else pred

@@ -118,8 +118,9 @@ def test_grouped_rows_gemm_full_epilogue(K, N):
     assert (got[owned & ~valid] == 0).all()
     err = (got[valid] - ref[valid]).abs().max().item()
     assert err <= 2 ** -7 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
-    ref_cs = torch.stack([got[row_e == e].sum(0) for e in range(E)])
-    assert torch.allclose(colsum, ref_cs, rtol=1e-3, atol=1e-2)
+    # column sums are taken from the fp32 values before the bf16 store
+    ref_cs = torch.stack([ref[row_e == e].sum(0) for e in range(E)])
+    assert torch.allclose(colsum, ref_cs, rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("N1,N2", [(384, 768), (768, 96), (768, 192), (768, 384), (768, 768)])

@@ -1,0 +1,225 @@
+"""GPU parity tests of `medmoe_b200.MoE` (through the C-ABI) against the oracle and the golden
+vectors generated from the reference.
+
+Tolerances (north star: "within a stated bf16 tolerance, e.g. rel 1e-2 vs the fp32 reference"):
+  * integer results (expert assignment, dispatch tables, permutation round trips): bit-exact;
+  * router probabilities / router gradients (fp32 kernels): 1e-5 absolute / 1e-4 relative;
+  * activations (global_feat, local_feat): norm-wise relative error <= 1e-2 vs the fp32 reference;
+  * gradients, TIGHT mode — against the reference evaluated at the operands the kernels actually
+    see (GEMM weights and stage features rounded to bf16, fixtures `*_bf16w`, oracle `round_operands`):
+    norm-wise relative error <= 1e-2.  Exception: the gradients of attn_proj.0 (W1, b1) flow through
+    ReLU(interp(Z)) whose gate is decided on the bf16-stored Z; ~0.4 % of the hidden units sit
+    within bf16 rounding of zero and flip, and a flipped gate is a 100 % error on that entry, so the
+    L2 error is ~sqrt(flip fraction) (<= 1e-1 asserted, cosine >= 0.995);
+  * gradients, FP32-REFERENCE mode — against the untouched fp32 reference: rounding the operands to
+    bf16 flips ~0.2 % of the conv ReLU gates in the same way (measured 3-5 % L2 error, median
+    per-token error 0.4 %), which any bf16 execution of the reference shares; asserted: cosine
+    similarity >= 0.995 and norm-wise error <= 8e-2.
+"""
+import pytest
+import torch
+
+import medmoe_b200
+from medmoe_b200 import ops, plan as mmplan
+from oracle import moe_oracle as mo
+from tests.util import cosine, golden_params, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-2
+TIGHT = dict(grad=1e-2, attn0=1e-1, cos=0.995)
+FP32REF = dict(grad=8e-2, attn0=1.5e-1, cos=0.995)
+
+
+def _grad_ok(got, ref, tol, name, key="grad"):
+    r, c = rel_err(got, ref), cosine(got, ref)
+    assert r < tol[key] and c > tol["cos"], f"{name}: rel {r:.4g} cos {c:.6f}"
+
+
+def _module_from(params, K, hidden, D, topk=1):
+    moe = medmoe_b200.MoE(num_experts=K, hidden_dims=hidden, output_dim=D, router_input_dim=params["router.0.weight"].shape[1],
+                          topk=topk)
+    moe.load_state_dict(params)
+    return moe.cuda()
+
+
+def _check_against(moe, feats_cpu, sw_cpu, ref_out, ref_grads, cot_g, cot_l, labels, dtype=torch.float32,
+                   act_tol=ACT_TOL, tol=TIGHT):
+    feats = [f.cuda().to(dtype).requires_grad_(True) for f in feats_cpu]
+    sw = sw_cpu.cuda().requires_grad_(True)
+    gf, lf, probs = moe(feats, sw)
+    assert gf.dtype == dtype and lf.dtype == dtype and probs.dtype == torch.float32
+    B, D = gf.shape
+    assert lf.shape == ref_out["local_feat"].shape and not lf.is_contiguous()   # stride view like the reference
+    assert torch.equal(torch.argmax(probs, -1).cpu(), ref_out["top_expert"])
+    assert torch.equal(moe.last_top_expert[:, 0].long().cpu(), ref_out["top_expert"])
+    assert (probs.cpu() - ref_out["probs"]).abs().max().item() < 1e-5
+    assert rel_err(gf.float().cpu(), ref_out["global_feat"]) < act_tol
+    assert rel_err(lf.float().cpu(), ref_out["local_feat"]) < act_tol
+    ce = torch.nn.functional.cross_entropy(probs, labels.cuda())
+    obj = (gf.float() * cot_g.cuda()).sum() + (lf.float() * cot_l.cuda()).sum() + 2.0 * ce
+    obj.backward()
+    for s in range(4):
+        _grad_ok(feats[s].grad.float().cpu(), ref_grads[f"d_feat{s}"], tol, f"d_feat{s}")
+    assert rel_err(sw.grad.cpu(), ref_grads["d_swin_feat"]) < 1e-4
+    return {k: p.grad for k, p in moe.named_parameters()}
+
+
+def _check_param_grads(grads, ref_of, used, tol):
+    for k, gr in grads.items():
+        assert gr is not None, f"{k}: gradient must be a tensor (zeros for idle experts), not None"
+        ref = ref_of(k)
+        if k.startswith("experts.") and int(k.split(".")[1]) not in used:
+            assert float(gr.abs().max()) == 0.0, f"{k}: idle expert must get an all-zero gradient"
+        elif k.endswith("attn_proj.2.bias"):
+            assert float(gr.abs().max()) < 1e-2      # identically zero in exact arithmetic (softmax shift invariance)
+        elif ref is None:
+            continue
+        elif k.startswith("router."):
+            assert rel_err(gr.float().cpu(), ref) < 1e-4, k
+        else:
+            _grad_ok(gr.float().cpu(), ref, tol, k, key="attn0" if ".attn_proj.0." in k else "grad")
+
+
+@pytest.mark.parametrize("case", ["moe_small", "moe_k6", "moe_small_bf16w", "moe_k6_bf16w"])
+def test_moe_matches_reference_golden(case):
+    tol = TIGHT if case.endswith("bf16w") else FP32REF
+    g = load_golden(case)
+    params = golden_params(g)
+    K = g["probs"].shape[1]
+    hidden = [g[f"feat{s}"].shape[2] for s in range(4)]
+    D = g["global_feat"].shape[1]
+    moe = _module_from(params, K, hidden, D)
+    grads = _check_against(moe, [g[f"feat{s}"] for s in range(4)], g["swin_feat"], g, g, g["cot_global"], g["cot_local"],
+                           g["labels"], tol=tol)
+    used = set(g["top_expert"].tolist())
+    _check_param_grads(grads, lambda k: g["grad." + k] if ("grad." + k in g and g["grad." + k].numel()) else None, used, tol)
+    for k, gr in grads.items():      # every gradient norm is pinned even where the full tensor is not stored
+        gn = g["gradnorm." + k].item()
+        if gn > 1e-6:
+            assert abs(gr.double().norm().item() - gn) <= (tol["attn0"] if ".attn_proj.0." in k else tol["grad"]) * gn, k
+
+
+def _oracle_case(K, hidden, D, Ps, B, seed, dtype=torch.float32):
+    """Oracle evaluated at the operands the kernels see (TIGHT mode): GEMM weights and stage features bf16-representable."""
+    params = mo.init_params(K, hidden, D, D, seed=seed)
+    params = {k: (v.to(torch.bfloat16).float() if (".proj_convs." in k or ".attn_proj.0." in k) and k.endswith("weight") else v)
+              for k, v in params.items()}
+    torch.manual_seed(seed + 1)
+    feats = [torch.randn(B, p, d).to(torch.bfloat16).float() for p, d in zip(Ps, hidden)]
+    sw = torch.randn(B, D)
+    labels = torch.randint(0, K, (B,))
+    cg = torch.randn(B, D)
+    P = max(Ps)
+    cl = torch.randn(B, D, int(P ** 0.5), int(P ** 0.5)) / P
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    sr = sw.clone().requires_grad_(True)
+    (gf, lf, probs), idx = mo.moe_forward_sparse(pr, fr, sr)
+    obj = (gf * cg).sum() + (lf * cl).sum() + 2.0 * mo.router_ce(probs, labels)
+    obj.backward()
+    ref_out = {"global_feat": gf.detach(), "local_feat": lf.detach(), "probs": probs.detach(), "top_expert": idx[:, 0]}
+    ref_grads = {f"d_feat{s}": fr[s].grad for s in range(4)}
+    ref_grads["d_swin_feat"] = sr.grad
+    pgrads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in pr.items()}
+    return params, feats, sw, labels, cg, cl, ref_out, ref_grads, pgrads
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_moe_full_token_counts_vs_oracle(dtype):
+    """Real Swin-T token counts (224^2: 3136/784/196/49), K = 4 experts, B = 6: ragged segments, padding tiles."""
+    K, hidden, D, Ps, B = 4, [96, 192, 384, 768], 768, [3136, 784, 196, 49], 6
+    params, feats, sw, labels, cg, cl, ref_out, ref_grads, pgrads = _oracle_case(K, hidden, D, Ps, B, seed=11, dtype=dtype)
+    moe = _module_from(params, K, hidden, D)
+    act_tol = ACT_TOL if dtype == torch.float32 else 1.5e-2   # + bf16 rounding of the returned activations
+    grads = _check_against(moe, feats, sw, ref_out, ref_grads, cg, cl, labels, dtype=dtype, act_tol=act_tol)
+    _check_param_grads(grads, lambda k: pgrads[k], set(ref_out["top_expert"].tolist()), TIGHT)
+
+
+def test_moe_384_tokens_vs_oracle():
+    """384^2 input: 9216/2304/576/144 tokens (BASELINE config 4 geometry), K = 8."""
+    K, hidden, D, Ps, B = 8, [96, 192, 384, 768], 768, [9216, 2304, 576, 144], 3
+    params, feats, sw, labels, cg, cl, ref_out, ref_grads, pgrads = _oracle_case(K, hidden, D, Ps, B, seed=5)
+    moe = _module_from(params, K, hidden, D)
+    _check_against(moe, feats, sw, ref_out, ref_grads, cg, cl, labels)
+
+
+def test_expert_forward_alone():
+    K, hidden, D, Ps, B = 2, [96, 192, 384, 768], 768, [64, 16, 4, 1], 3
+    params = mo.init_params(K, hidden, D, D, seed=3)
+    moe = _module_from(params, K, hidden, D)
+    torch.manual_seed(0)
+    feats = [torch.randn(B, p, d) for p, d in zip(Ps, hidden)]
+    ref = mo.expert_forward_as_written(params, 1, feats)
+    got = moe.experts[1]([f.cuda() for f in feats])
+    assert rel_err(got.float().cpu(), ref) < ACT_TOL
+
+
+def test_dispatch_rows_round_trip_bit_exact():
+    """permute -> un-permute is the identity on bf16 payloads; fp32 sources are rounded exactly like torch."""
+    B, K, Ps, widths = 37, 5, [49, 16, 4, 1], [96, 192, 384, 768]
+    g = torch.Generator().manual_seed(0)
+    item_expert = torch.randint(0, K, (B,), generator=g, dtype=torch.int32).cuda()
+    layout = mmplan.make_layout(B, 1, K, Ps)
+    plan = mmplan.build_plan(item_expert, layout)
+    feats32 = [torch.randn(B, p, d, device="cuda") for p, d in zip(Ps, widths)]
+    feats16 = [f.to(torch.bfloat16) for f in feats32]
+    for src in (feats32, feats16):
+        sorted_rows = ops.dispatch_rows(src, plan, widths)
+        torch.cuda.synchronize()
+        # every slot holds its image, padding rows are zero
+        perm = plan.perm.cpu().tolist()
+        slot_row = plan.slot_row.cpu()
+        for s in range(4):
+            buf = sorted_rows[s]
+            seen = torch.zeros(buf.shape[0], dtype=torch.bool)
+            for slot, item in enumerate(perm):
+                r = int(slot_row[s, slot]) - layout.region_base[s]
+                assert torch.equal(buf[r:r + Ps[s]], feats16[s][item])
+                seen[r:r + Ps[s]] = True
+            ti = plan.tile_info.cpu()[layout.tile_base[s]:layout.tile_base[s] + layout.region_tiles[s]]
+            for t in range(layout.region_tiles[s]):
+                if ti[t, 0] >= 0:
+                    pad = ~seen[t * 128:(t + 1) * 128]
+                    assert (buf[t * 128:(t + 1) * 128][pad.cuda()] == 0).all()
+        back = ops.undispatch_rows(sorted_rows, plan, widths, torch.bfloat16)
+        for s in range(4):
+            assert torch.equal(back[s], feats16[s])
+
+
+def test_full_batch_properties():
+    """BASELINE config-2 size (B = 256, K = 4, 224^2 tokens): size-independent properties."""
+    K, hidden, D, Ps, B = 4, [96, 192, 384, 768], 768, [3136, 784, 196, 49], 256
+    torch.manual_seed(0)
+    moe = medmoe_b200.MoE(num_experts=K).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feats = [torch.randn(B, p, d, device="cuda", dtype=torch.bfloat16, generator=g) for p, d in zip(Ps, hidden)]
+    sw = torch.randn(B, D, device="cuda", generator=g)
+    with torch.no_grad():
+        gf, lf, probs = moe(feats, sw)
+        top = moe.last_top_expert.clone()
+        # (1) run-to-run determinism of the forward
+        gf2, lf2, _ = moe(feats, sw)
+        assert torch.equal(gf, gf2) and torch.equal(lf, lf2)
+        # (2) permutation equivariance: images are independent, sorting must not leak across slots
+        perm = torch.randperm(B, device="cuda", generator=g)
+        gfp, lfp, probsp = moe([f[perm] for f in feats], sw[perm])
+        assert torch.equal(probsp, probs[perm]) and torch.equal(moe.last_top_expert, top[perm])
+        assert torch.equal(lfp, lf[perm]) and torch.equal(gfp, gf[perm])
+    assert torch.isfinite(lf.float()).all() and torch.isfinite(gf.float()).all()
+    # (3) global_feat is the token mean of local_feat
+    assert rel_err(gf.float(), lf.float().flatten(2).mean(-1)) < 5e-3
+    # (4) linearity of the backward in the cotangent + idle-expert zero grads under forced skew
+    feats_g = [f.clone().requires_grad_(True) for f in feats]
+    gf, lf, probs = moe(feats_g, sw)
+    cot = torch.randn_like(gf)
+    (g1,) = torch.autograd.grad((gf * cot).sum(), feats_g[3], retain_graph=True)
+    (g2,) = torch.autograd.grad((gf * (2 * cot)).sum(), feats_g[3])
+    assert rel_err(g2.float(), 2 * g1.float()) < 1e-2
+    counts = torch.bincount(top[:, 0].long(), minlength=K)
+    moe.zero_grad()
+    gf, lf, probs = moe(feats, sw)
+    gf.float().sum().backward()
+    for e in range(K):
+        gn = moe.experts[e].attn_proj[0].weight.grad.abs().max().item()
+        assert (gn == 0.0) == (counts[e].item() == 0)
