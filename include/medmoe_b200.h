@@ -108,20 +108,24 @@ int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda
  * out [B, P, D] (bf16 or fp32), beta [n_items, P, 4], gpart [B, nblk, D] scratch, global_feat [B, D] fp32. */
 int mm_combine_num_token_blocks(int P);
 int mm_combine_num_row_blocks(const int32_t* Ps);
+int mm_combine_num_runs(int P);
+int mm_combine_num_part_blocks(int P, const int32_t* Ps);
 int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk, int P,
                                   const int32_t* Ps, int D, const int32_t* inv_perm, const int32_t* slot_expert,
                                   const int32_t* slot_row, const float* gate, float* beta, void* out, int out_f32,
                                   float* gpart, float* global_feat, void* stream);
 /* backward: dlocal [B, P, D] (bf16/fp32, may be NULL), dglobal [B, D] fp32 (may be NULL) ->
  * dlogit [n_items, P, 4], dgate [n_items] (+=, may be NULL), dUT [rows, D] bf16, dZ [rows, D/2] bf16,
- * part [n_items, nrb, D + 1] scratch, dw2_db1_db2 [K, D + 1] = per expert {dw2 (D/2) | db1 (D/2) | db2}. */
+ * part [n_items, mm_combine_num_part_blocks, D + 1] scratch, dw2_db1_db2 [K, D + 1] = per expert
+ * {dw2 (D/2) | db1 (D/2) | db2}.  mom_u [n_items, mm_combine_num_runs, 2, D] and mom_z [.., 2, D/2] fp32 scratch enable
+ * the token-centric path (integer scale ratios); NULL or force_generic selects the generic gather kernel. */
 int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
                                   const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,
                                   const int32_t* slot_expert, const int32_t* slot_row, const int32_t* counts,
                                   const int32_t* seg_start, const int32_t* offsets, const float* gate,
                                   const float* beta, const void* dlocal, int dlocal_f32, const float* dglobal,
                                   float* dlogit, float* dgate, void* dUT, void* dZ, float* part, float* dw2_db1_db2,
-                                  void* stream);
+                                  float* mom_u, float* mom_z, int force_generic, void* stream);
 
 /* ---- (5) global contrastive loss -------------------------------------------------------
  * GLORIA semantics: replaces GLORIAGlobalContrastiveLoss.forward, src/losses.py:766-794.

@@ -56,7 +56,18 @@ struct CombineArgs {
     __nv_bfloat16* dZ;              // [rows, D/2]
     float* part;                    // [n_items, nrb, 2*(D/2) + 1] per-CTA partials: dw2 | db1 | db2
     int nrb;
+    // token-centric ("fast") backward: integer scale ratios only
+    int ratio[4];                   // P / Ps[s]
+    int mode[4];                    // SCALE_IDENT / SCALE_DIRECT / SCALE_MOMENT
+    int halo;                       // max over DIRECT scales of ratio / 2
+    int nruns;                      // ceil(P / 32)
+    float* mom_u;                   // [n_items, nruns, 2, D]   zeroth / first moments of beta_s * dF per 32-token run
+    float* mom_z;                   // [n_items, nruns, 2, D/2] same for dlogit_s * w2 * gate
 };
+
+enum : int { SCALE_IDENT = 0, SCALE_DIRECT = 1, SCALE_MOMENT = 2, SCALE_UNSUPPORTED = 3 };
+constexpr int RUN_TOKENS = 32;      // tokens per warp-run in the token-centric backward
+constexpr int RUNS_PER_BLOCK = 8;
 
 template <int N>
 MM_DEVINL void load_row_bf16x8(const __nv_bfloat16* row, int lane, float (&f)[N * 8]) {
@@ -441,6 +452,330 @@ combine_bwd_rows_kernel(const CombineArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Token-centric backward (integer scale ratios r_s = P / P_s).  Each warp owns a run of 32
+// consecutive tokens of one slot and streams over them once:
+//   * r = 1      (IDENT)  : the transposed lerp is the identity;
+//   * r <= 32    (DIRECT) : the warp also owns the native rows i with r*i inside its run; their
+//                           token windows reach r/2 tokens outside the run (halo), contributions of
+//                           halo tokens to rows owned by the neighbour are dropped, so no atomics;
+//   * r/2 % 32 == 0 (MOMENT, the coarsest scale): inside a run the lerp weight of a native row is
+//                           affine in the token index, so the run only emits M0 = sum g(p) and
+//                           M1 = sum (p - p0) g(p); a finalize kernel combines the <= 4 runs of a
+//                           row's window:  dRow = sum_runs w(p0) M0 + slope M1.
+// g(p) = beta_s(p) dF(p) for dUT and g(p) = dlogit_s(p) w2 [interp(Z_s)(p) > 0] for dZ.
+// ------------------------------------------------------------------------------------
+template <int NE, typename T>
+MM_DEVINL void load_slab(const T* p, int lane, float (&f)[NE * 4]) {
+    if constexpr (sizeof(T) == 2) load_row_bf16x4<NE>(reinterpret_cast<const __nv_bfloat16*>(p), lane, f);
+    else load_row_f32x4<NE>(reinterpret_cast<const float*>(p), lane, f);
+}
+template <int NE>
+MM_DEVINL void store_slab_bf16(__nv_bfloat16* p, int lane, const float (&f)[NE * 4]) {
+#pragma unroll
+    for (int t = 0; t < NE; ++t)
+        *reinterpret_cast<uint2*>(p + 4 * (lane + 32 * t)) =
+            make_uint2(pack_bf16x2(f[4 * t], f[4 * t + 1]), pack_bf16x2(f[4 * t + 2], f[4 * t + 3]));
+}
+template <int NE>
+MM_DEVINL void store_slab_f32(float* p, int lane, const float (&f)[NE * 4]) {
+#pragma unroll
+    for (int t = 0; t < NE; ++t)
+        *reinterpret_cast<float4*>(p + 4 * (lane + 32 * t)) = make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
+}
+
+// dUT: grid = (ceil(2 * nruns / 8), n_items); warp = (run, column half).
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256)
+combine_bwd_u_kernel(const CombineArgs a) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * 8 + warp;
+    const int c = unit >> 1, j = unit & 1;
+    if (c >= a.nruns) return;
+    const int slot = blockIdx.y;
+    const int item = a.perm[slot];
+    const int b = item / a.topk;
+    const float g = a.gate ? a.gate[item] : 1.0f;
+    const int t0 = c * RUN_TOKENS;
+    const int col0 = j * H;
+
+    float dg[E];
+    if (a.dglobal) {
+        load_slab<NE, float>(a.dglobal + static_cast<size_t>(b) * D + col0, lane, dg);
+        const float inv_p = 1.0f / static_cast<float>(a.P);
+#pragma unroll
+        for (int k = 0; k < E; ++k) dg[k] *= inv_p;
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k) dg[k] = 0.f;
+    }
+    float acc[3][2][E];
+    int cur[3] = {-1, -1, -1};
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int k = 0; k < E; ++k) { acc[s][0][k] = 0.f; acc[s][1][k] = 0.f; }
+
+    long long base[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) base[s] = a.slot_row[s * a.n_items + slot];
+
+    const int p_lo = max(0, t0 - a.halo), p_hi = min(a.P, t0 + RUN_TOKENS + a.halo);
+    for (int p = p_lo; p < p_hi; ++p) {
+        const bool in_run = (p >= t0) && (p < t0 + RUN_TOKENS);
+        float df[E];
+        if (a.dlocal) {
+            load_slab<NE, OutT>(static_cast<const OutT*>(a.dlocal) + (static_cast<size_t>(b) * a.P + p) * D + col0, lane, df);
+#pragma unroll
+            for (int k = 0; k < E; ++k) df[k] += dg[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; ++k) df[k] = dg[k];
+        }
+        const float4 bt4 = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+        const float bt[4] = {bt4.x * g, bt4.y * g, bt4.z * g, bt4.w * g};
+        if (in_run) {   // scale 0: identity
+            float o[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) o[k] = bt[0] * df[k];
+            store_slab_bf16<NE>(a.dUT + (base[0] + p) * D + col0, lane, o);
+        }
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const int r = a.ratio[s];
+            if (a.mode[s] == SCALE_DIRECT) {
+                const int hs = r >> 1;
+                if (p < t0 - hs || p >= t0 + RUN_TOKENS + hs) continue;
+                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                if (L.i0 != cur[s - 1]) {
+                    const int done = cur[s - 1];
+                    if (done >= 0 && done * r >= t0 && done * r < t0 + RUN_TOKENS)
+                        store_slab_bf16<NE>(a.dUT + (base[s] + done) * D + col0, lane, acc[s - 1][0]);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) { acc[s - 1][0][k] = acc[s - 1][1][k]; acc[s - 1][1][k] = 0.f; }
+                    cur[s - 1] = L.i0;
+                }
+                const float c0 = bt[s] * (1.0f - L.lam), c1 = bt[s] * L.lam;
+                if (L.i1 == L.i0) {
+#pragma unroll
+                    for (int k = 0; k < E; ++k) acc[s - 1][0][k] = fmaf(c0 + c1, df[k], acc[s - 1][0][k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < E; ++k) {
+                        acc[s - 1][0][k] = fmaf(c0, df[k], acc[s - 1][0][k]);
+                        acc[s - 1][1][k] = fmaf(c1, df[k], acc[s - 1][1][k]);
+                    }
+                }
+            } else if (a.mode[s] == SCALE_MOMENT) {
+                if (!in_run) continue;
+                const float c0 = bt[s], c1 = bt[s] * static_cast<float>(p - t0);
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    acc[s - 1][0][k] = fmaf(c0, df[k], acc[s - 1][0][k]);
+                    acc[s - 1][1][k] = fmaf(c1, df[k], acc[s - 1][1][k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 1; s < 4; ++s) {
+        const int r = a.ratio[s];
+        if (a.mode[s] == SCALE_DIRECT) {
+            const int i = cur[s - 1];
+            if (i >= 0 && i * r >= t0 && i * r < t0 + RUN_TOKENS)
+                store_slab_bf16<NE>(a.dUT + (base[s] + i) * D + col0, lane, acc[s - 1][0]);
+            if (i >= 0 && i + 1 < a.Ps[s] && (i + 1) * r >= t0 && (i + 1) * r < t0 + RUN_TOKENS)
+                store_slab_bf16<NE>(a.dUT + (base[s] + i + 1) * D + col0, lane, acc[s - 1][1]);
+        } else if (a.mode[s] == SCALE_MOMENT) {
+            float* m = a.mom_u + ((static_cast<size_t>(slot) * a.nruns + c) * 2) * D + col0;
+            store_slab_f32<NE>(m, lane, acc[s - 1][0]);
+            store_slab_f32<NE>(m + D, lane, acc[s - 1][1]);
+        }
+    }
+}
+
+// dZ + the per-token parameter gradients (dw2, db1, db2): grid = (ceil(nruns / 8), n_items + K); warp = run.
+template <int D>
+__global__ void __launch_bounds__(256)
+combine_bwd_z_kernel(const CombineArgs a) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    constexpr int PART = 2 * H + 1;
+    __shared__ float s_part[RUNS_PER_BLOCK][PART];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (blockIdx.y >= a.n_items) {   // zero the 128-row padding behind every expert segment of dZ
+        const int e = blockIdx.y - a.n_items;
+        for (int s = 0; s < 4; ++s) {
+            const long long rows = static_cast<long long>(a.counts[e]) * a.Ps[s];
+            const long long pad = (rows + TILE_M - 1) / TILE_M * TILE_M - rows;
+            __nv_bfloat16* dz = a.dZ + (static_cast<long long>(a.seg_start[s * a.K + e]) + rows) * H;
+            for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4; i < pad * H;
+                 i += static_cast<long long>(gridDim.x) * 256 * 4)
+                *reinterpret_cast<uint2*>(dz + i) = make_uint2(0, 0);
+        }
+        return;
+    }
+
+    const int c = blockIdx.x * RUNS_PER_BLOCK + warp;
+    const int slot = blockIdx.y;
+    const int e = a.slot_expert[slot];
+    const int t0 = c * RUN_TOKENS;
+    float dw2[E], db1[E], db2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < E; ++k) { dw2[k] = 0.f; db1[k] = 0.f; }
+
+    if (c < a.nruns) {
+        float w2[E];
+        load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+        const float* dlg = a.dlogit + static_cast<size_t>(slot) * a.P * 4;
+        for (int s = 0; s < 4; ++s) {
+            const int mode = a.mode[s];
+            const int r = a.ratio[s];
+            const long long base = a.slot_row[s * a.n_items + slot];
+            const int hs = (mode == SCALE_DIRECT) ? (r >> 1) : 0;
+            const int p_lo = max(0, t0 - hs), p_hi = min(a.P, t0 + RUN_TOKENS + hs);
+            float lo[E], hi[E], za[E], zb[E];
+            int cur = -1, za_row = -1, zb_row = -1;
+#pragma unroll
+            for (int k = 0; k < E; ++k) { lo[k] = 0.f; hi[k] = 0.f; za[k] = 0.f; zb[k] = 0.f; }
+            for (int p = p_lo; p < p_hi; ++p) {
+                const bool in_run = (p >= t0) && (p < t0 + RUN_TOKENS);
+                const float dl = dlg[p * 4 + s];
+                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                if (L.i0 != za_row) {
+                    if (L.i0 == zb_row) {
+#pragma unroll
+                        for (int k = 0; k < E; ++k) za[k] = zb[k];
+                    } else {
+                        load_row_bf16x4<NE>(a.Z + (base + L.i0) * H, lane, za);
+                    }
+                    za_row = L.i0;
+                }
+                const bool two = (L.i1 != L.i0) && (L.lam != 0.f);
+                if (two && L.i1 != zb_row) {
+                    load_row_bf16x4<NE>(a.Z + (base + L.i1) * H, lane, zb);
+                    zb_row = L.i1;
+                }
+                const float l0 = 1.0f - L.lam;
+                float gk[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    const float h = two ? (l0 * za[k] + L.lam * zb[k]) : za[k];
+                    gk[k] = h > 0.f ? dl * w2[k] : 0.f;
+                    if (in_run && h > 0.f) dw2[k] = fmaf(dl, h, dw2[k]);
+                }
+                if (in_run) {
+                    db2 += dl;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) db1[k] += gk[k];
+                }
+                if (mode == SCALE_IDENT) {
+                    if (in_run) store_slab_bf16<NE>(a.dZ + (base + p) * H, lane, gk);
+                } else if (mode == SCALE_DIRECT) {
+                    if (L.i0 != cur) {
+                        if (cur >= 0 && cur * r >= t0 && cur * r < t0 + RUN_TOKENS)
+                            store_slab_bf16<NE>(a.dZ + (base + cur) * H, lane, lo);
+#pragma unroll
+                        for (int k = 0; k < E; ++k) { lo[k] = hi[k]; hi[k] = 0.f; }
+                        cur = L.i0;
+                    }
+                    if (L.i1 == L.i0) {
+#pragma unroll
+                        for (int k = 0; k < E; ++k) lo[k] += gk[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < E; ++k) { lo[k] = fmaf(l0, gk[k], lo[k]); hi[k] = fmaf(L.lam, gk[k], hi[k]); }
+                    }
+                } else {   // SCALE_MOMENT
+                    const float t = static_cast<float>(p - t0);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) { lo[k] += gk[k]; hi[k] = fmaf(t, gk[k], hi[k]); }
+                }
+            }
+            if (mode == SCALE_DIRECT) {
+                if (cur >= 0 && cur * r >= t0 && cur * r < t0 + RUN_TOKENS)
+                    store_slab_bf16<NE>(a.dZ + (base + cur) * H, lane, lo);
+                if (cur >= 0 && cur + 1 < a.Ps[s] && (cur + 1) * r >= t0 && (cur + 1) * r < t0 + RUN_TOKENS)
+                    store_slab_bf16<NE>(a.dZ + (base + cur + 1) * H, lane, hi);
+            } else if (mode == SCALE_MOMENT) {
+                float* m = a.mom_z + ((static_cast<size_t>(slot) * a.nruns + c) * 2) * H;
+                store_slab_f32<NE>(m, lane, lo);
+                store_slab_f32<NE>(m + H, lane, hi);
+            }
+        }
+    }
+    // per-CTA partials: [dw2 (H) | db1 (H) | db2 (1)]
+#pragma unroll
+    for (int t = 0; t < NE; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s_part[warp][4 * (lane + 32 * t) + k] = dw2[4 * t + k];
+            s_part[warp][H + 4 * (lane + 32 * t) + k] = db1[4 * t + k];
+        }
+    if (lane == 0) s_part[warp][2 * H] = db2;
+    __syncthreads();
+    float* dst = a.part + (static_cast<size_t>(slot) * a.nrb + blockIdx.x) * PART;
+    for (int cc = threadIdx.x; cc < PART; cc += blockDim.x) {
+        float accv = 0.f;
+#pragma unroll
+        for (int w = 0; w < RUNS_PER_BLOCK; ++w) accv += s_part[w][cc];
+        dst[cc] = accv;
+    }
+}
+
+// MOMENT scale: combine the runs of each native row's window.  grid = (ceil(Ps[s] / 8), n_items); warp = native row.
+template <int D>
+__global__ void __launch_bounds__(256)
+combine_bwd_finalize_kernel(const CombineArgs a, int s) {
+    constexpr int N = D / 256;
+    constexpr int NE = D / 256;
+    constexpr int H = D / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    const int Ps = a.Ps[s];
+    if (i >= Ps) return;
+    const int slot = blockIdx.y;
+    const int r = a.ratio[s];
+    const long long base = a.slot_row[s * a.n_items + slot];
+    float u[N * 8], z[NE * 4];
+#pragma unroll
+    for (int k = 0; k < N * 8; ++k) u[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NE * 4; ++k) z[k] = 0.f;
+    const int p_first = max(0, r * i - (r >> 1)), p_last = min(a.P, r * i + r + (r >> 1));   // [first, last)
+    for (int c = p_first / RUN_TOKENS; c * RUN_TOKENS < p_last; ++c) {
+        const int pa = c * RUN_TOKENS, pb = min(pa + RUN_TOKENS - 1, a.P - 1);
+        float wa, wb;
+        {
+            const LerpSrc L = lerp_src(pa, a.scale[s], Ps);
+            wa = (L.i0 == i ? 1.0f - L.lam : 0.f) + (L.i1 == i ? L.lam : 0.f);
+            const LerpSrc M = lerp_src(pb, a.scale[s], Ps);
+            wb = (M.i0 == i ? 1.0f - M.lam : 0.f) + (M.i1 == i ? M.lam : 0.f);
+        }
+        if (wa == 0.f && wb == 0.f) continue;
+        const float slope = pb > pa ? (wb - wa) / static_cast<float>(pb - pa) : 0.f;
+        const float* mu = a.mom_u + ((static_cast<size_t>(slot) * a.nruns + c) * 2) * D;
+        const float* mz = a.mom_z + ((static_cast<size_t>(slot) * a.nruns + c) * 2) * H;
+        float m0[N * 8], m1[N * 8];
+        load_row_x8<N, float>(mu, lane, m0);
+        load_row_x8<N, float>(mu + D, lane, m1);
+#pragma unroll
+        for (int k = 0; k < N * 8; ++k) u[k] = fmaf(wa, m0[k], fmaf(slope, m1[k], u[k]));
+        float n0[NE * 4], n1[NE * 4];
+        load_row_f32x4<NE>(mz, lane, n0);
+        load_row_f32x4<NE>(mz + H, lane, n1);
+#pragma unroll
+        for (int k = 0; k < NE * 4; ++k) z[k] = fmaf(wa, n0[k], fmaf(slope, n1[k], z[k]));
+    }
+    store_row_x8<N, __nv_bfloat16>(a.dUT + (base + i) * D, lane, u);
+    store_slab_bf16<NE>(a.dZ + (base + i) * H, lane, z);
+}
+
 // out[e, c] = sum over the slots of expert e and their nrb blocks of part[slot, blk, c]; grid = (ceil(C/256), K)
 __global__ void __launch_bounds__(256)
 expert_reduce_kernel(const float* __restrict__ part, const int* __restrict__ offsets, int nrb, int C, float* __restrict__ out) {
@@ -507,13 +842,47 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     return mm_check_launch("mm_interp_softmax_combine_fwd(global mean)");
 }
 
+extern "C" int mm_combine_num_runs(int P) { return (P + RUN_TOKENS - 1) / RUN_TOKENS; }
+// number of per-slot partial blocks `part` must hold (max over the two backward paths)
+extern "C" int mm_combine_num_part_blocks(int P, const int32_t* Ps) {
+    const int fast = (mm_combine_num_runs(P) + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
+    const int generic = mm_combine_num_row_blocks(Ps);
+    return fast > generic ? fast : generic;
+}
+
+// classify the scale ratios for the token-centric backward; returns 1 when it applies
+static int classify_scales(CombineArgs& a) {
+    int n_moment = 0;
+    a.halo = 0;
+    for (int s = 0; s < 4; ++s) {
+        a.ratio[s] = 0; a.mode[s] = SCALE_UNSUPPORTED;
+        if (a.Ps[s] <= 0 || a.P % a.Ps[s] != 0) return 0;
+        const int r = a.P / a.Ps[s];
+        a.ratio[s] = r;
+        if (s == 0) {
+            if (r != 1) return 0;
+            a.mode[s] = SCALE_IDENT;
+        } else if (r <= RUN_TOKENS && RUN_TOKENS % r == 0) {
+            a.mode[s] = SCALE_DIRECT;
+            if (r / 2 > a.halo) a.halo = r / 2;
+        } else if (r % 2 == 0 && (r / 2) % RUN_TOKENS == 0) {
+            a.mode[s] = SCALE_MOMENT;
+            ++n_moment;
+        } else {
+            return 0;
+        }
+    }
+    return n_moment <= 1;
+}
+
 extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
                                              const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,
                                              const int32_t* slot_expert, const int32_t* slot_row, const int32_t* counts,
                                              const int32_t* seg_start, const int32_t* offsets, const float* gate,
                                              const float* beta, const void* dlocal, int dlocal_f32, const float* dglobal,
                                              float* dlogit, float* dgate, void* dUT, void* dZ, float* part,
-                                             float* dw2_db1_db2, void* stream) {
+                                             float* dw2_db1_db2, float* mom_u, float* mom_z, int force_generic,
+                                             void* stream) {
     CombineArgs a{};
     int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_bwd");
     if (rc) return rc;
@@ -523,9 +892,11 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     a.w2 = w2; a.beta = const_cast<float*>(beta);
     a.dlocal = dlocal; a.dglobal = dglobal; a.dlogit = dlogit; a.dgate = dgate;
     a.dUT = static_cast<__nv_bfloat16*>(dUT); a.dZ = static_cast<__nv_bfloat16*>(dZ);
-    a.part = part;
+    a.part = part; a.mom_u = mom_u; a.mom_z = mom_z;
     a.nblk = mm_combine_num_token_blocks(P);
-    a.nrb = mm_combine_num_row_blocks(Ps);
+    a.nruns = mm_combine_num_runs(P);
+    const bool fast = !force_generic && mom_u && mom_z && classify_scales(a);
+    a.nrb = fast ? (a.nruns + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK : mm_combine_num_row_blocks(Ps);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
         dim3 grid(a.nblk, B);
@@ -534,7 +905,34 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
         rc = mm_check_launch("mm_interp_softmax_combine_bwd(logit)");
         if (rc) return rc;
     }
-    {
+    if (fast) {
+        {
+            dim3 grid((2 * a.nruns + 7) / 8, a.n_items);
+            MM_DISPATCH_D(D, dlocal_f32, combine_bwd_u_kernel, grid, st, a)
+            mm::note_launches(1);
+        }
+        dim3 gridz(a.nrb, a.n_items + K);
+        switch (D) {
+            case 256: combine_bwd_z_kernel<256><<<gridz, 256, 0, st>>>(a); break;
+            case 512: combine_bwd_z_kernel<512><<<gridz, 256, 0, st>>>(a); break;
+            case 768: combine_bwd_z_kernel<768><<<gridz, 256, 0, st>>>(a); break;
+            case 1024: combine_bwd_z_kernel<1024><<<gridz, 256, 0, st>>>(a); break;
+        }
+        mm::note_launches(1);
+        for (int s = 1; s < 4; ++s) {
+            if (a.mode[s] != SCALE_MOMENT) continue;
+            dim3 gridf((a.Ps[s] + 7) / 8, a.n_items);
+            switch (D) {
+                case 256: combine_bwd_finalize_kernel<256><<<gridf, 256, 0, st>>>(a, s); break;
+                case 512: combine_bwd_finalize_kernel<512><<<gridf, 256, 0, st>>>(a, s); break;
+                case 768: combine_bwd_finalize_kernel<768><<<gridf, 256, 0, st>>>(a, s); break;
+                case 1024: combine_bwd_finalize_kernel<1024><<<gridf, 256, 0, st>>>(a, s); break;
+            }
+            mm::note_launches(1);
+        }
+        rc = mm_check_launch("mm_interp_softmax_combine_bwd(token-centric)");
+        if (rc) return rc;
+    } else {
         dim3 grid(a.nrb, a.n_items + K);
         MM_DISPATCH_D(D, dlocal_f32, combine_bwd_rows_kernel, grid, st, a)
         mm::note_launches(1);

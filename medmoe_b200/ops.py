@@ -15,6 +15,8 @@ from .plan import DispatchPlan, RowLayout
 
 EPI_RELU, EPI_ZERO_PAD = 1, 2
 _P = _lib.ptr
+# test hook: run the generic (any scale ratio) backward-combine kernel instead of the token-centric one
+FORCE_GENERIC_COMBINE_BWD = False
 
 
 def _need_cuda(*tensors):
@@ -143,13 +145,17 @@ def combine_fwd(Y, Z, w2, b2, plan: DispatchPlan, D: int, gate, out_dtype):
     return out, gfeat, beta
 
 
-def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool):
+def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool,
+                force_generic: bool = False):
     lay = plan.layout
     _need_cuda(Y, Z, w2, beta, dlocal, dglobal)
     B, P, K = lay.n_images, lay.P[0], lay.num_experts
     dev = Y.device
     f32 = dict(dtype=torch.float32, device=dev)
-    nrb = _lib.call("mm_combine_num_row_blocks", _lib.host_i32(lay.P))
+    nrb = _lib.call("mm_combine_num_part_blocks", P, _lib.host_i32(lay.P))
+    nruns = _lib.call("mm_combine_num_runs", P)
+    mom_u = torch.empty(lay.n_items, nruns, 2, D, **f32)
+    mom_z = torch.empty(lay.n_items, nruns, 2, D // 2, **f32)
     dlogit = torch.empty(lay.n_items, P, 4, **f32)
     dgate = torch.zeros(lay.n_items, **f32) if need_dgate else None
     dUT = torch.empty(lay.total_rows, D, dtype=torch.bfloat16, device=dev)
@@ -160,7 +166,8 @@ def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dgloba
     _lib.call("mm_interp_softmax_combine_bwd", _P(Y), _P(Z), _P(w2), B, lay.topk, P, _lib.host_i32(lay.P), D, K,
               _P(plan.perm), _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(plan.counts),
               _P(plan.seg_start), _P(plan.offsets), _P(gate), _P(beta), _P(dlocal), int(dl_f32), _P(dglobal),
-              _P(dlogit), _P(dgate), _P(dUT), _P(dZ), _P(part), _P(red), _st())
+              _P(dlogit), _P(dgate), _P(dUT), _P(dZ), _P(part), _P(red), _P(mom_u), _P(mom_z),
+              int(force_generic or FORCE_GENERIC_COMBINE_BWD), _st())
     H = D // 2
     return dUT, dZ, red[:, :H], red[:, H:2 * H], red[:, 2 * H], dgate
 

@@ -223,3 +223,42 @@ def test_full_batch_properties():
     for e in range(K):
         gn = moe.experts[e].attn_proj[0].weight.grad.abs().max().item()
         assert (gn == 0.0) == (counts[e].item() == 0)
+
+
+def test_token_centric_and_generic_backward_agree():
+    """The fast (token-centric, integer scale ratios) and the generic (any ratio) backward-combine
+    kernels compute the same gradients up to bf16 storage and summation order."""
+    K, hidden, D, Ps, B = 3, [96, 192, 384, 768], 768, [3136, 784, 196, 49], 5
+    params = mo.init_params(K, hidden, D, D, seed=21)
+    moe = _module_from(params, K, hidden, D)
+    torch.manual_seed(22)
+    feats = [torch.randn(B, p, d, device="cuda") for p, d in zip(Ps, hidden)]
+    sw = torch.randn(B, D, device="cuda")
+    cg = torch.randn(B, D, device="cuda")
+    cl = torch.randn(B, D, 56, 56, device="cuda") / 3136
+    results = []
+    for force in (False, True):
+        ops.FORCE_GENERIC_COMBINE_BWD = force
+        try:
+            moe.zero_grad()
+            fg = [f.clone().requires_grad_(True) for f in feats]
+            gf, lf, _ = moe(fg, sw)
+            ((gf * cg).sum() + (lf * cl).sum()).backward()
+            results.append(([f.grad.clone() for f in fg], {k: p.grad.clone() for k, p in moe.named_parameters() if p.grad is not None}))
+        finally:
+            ops.FORCE_GENERIC_COMBINE_BWD = False
+    (fa, pa), (fb, pb) = results
+    for s in range(4):
+        assert rel_err(fa[s], fb[s]) < 5e-3, f"d_feat{s}"
+    for k in pa:
+        if k.startswith("experts.") and pb[k].abs().max() > 0 and not k.endswith("attn_proj.2.bias"):
+            assert rel_err(pa[k], pb[k]) < 5e-3, k
+
+
+def test_non_integer_scale_ratio_uses_generic_backward():
+    """Token counts that are not integer multiples (e.g. 100 -> 30 -> 7 -> 1) still work (generic kernels)."""
+    K, hidden, D, Ps, B = 2, [96, 192, 384, 768], 768, [100, 30, 7, 1], 3
+    params, feats, sw, labels, cg, cl, ref_out, ref_grads, pgrads = _oracle_case(K, hidden, D, Ps, B, seed=31)
+    moe = _module_from(params, K, hidden, D)
+    grads = _check_against(moe, feats, sw, ref_out, ref_grads, cg, cl, labels)
+    _check_param_grads(grads, lambda k: pgrads[k], set(ref_out["top_expert"].tolist()), TIGHT)
