@@ -43,7 +43,7 @@ SIGNATURES = {
                                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "mm_interp_softmax_combine_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
-                                              c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "mm_gloria_workspace_floats": (c_ll, [c_int]),
     "mm_gloria_global_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_vp, c_vp, c_vp]),
     "mm_gloria_global_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
