@@ -3,10 +3,10 @@
 #include "api_internal.h"
 #include "gemm.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <atomic>
 #include <mutex>
 
 namespace mm {
@@ -63,8 +63,8 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
-                     uint32_t box_inner, uint32_t box_rows, const char* what) {
+static int encode_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                       uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz, const char* what) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver)", what);
@@ -79,7 +79,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu pitch=%llu box=%ux%u)", what,
@@ -90,14 +90,23 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
     return MM_OK;
 }
 
+int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                     uint32_t box_inner, uint32_t box_rows, const char* what) {
+    return encode_tmap(out, base, inner, rows, row_stride, box_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_128B, what);
+}
+
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-template <int BN, bool OUT_F32>
-static int launch_rows(const CUtensorMap& tA, const CUtensorMap& tB, const RowsGemmArgs& args, cudaStream_t st) {
-    constexpr int STAGES = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
-    using S = GemmSmem<BN, STAGES>;
-    auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32>;
+struct RowsMaps { CUtensorMap a, b, out, aux, gate; };
+
+template <int BN, bool OUT_F32, bool AUX>
+static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
+    // smem: pipeline stages + 16 KB output staging (+ 32 KB aux/gate staging) must fit 227 KB
+    constexpr int STAGES = AUX ? ((BN > 192) ? 3 : (BN > 128 ? 4 : 5)) : ((BN > 192) ? 4 : (BN > 128 ? 5 : 6));
+    using S = GemmSmem<BN, STAGES, AUX>;
+    static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32, AUX>;
     static bool configured = false;   // benign race: attribute set is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -110,7 +119,7 @@ static int launch_rows(const CUtensorMap& tA, const CUtensorMap& tB, const RowsG
     const int work = args.tile_count * args.n_tiles;
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
-    kern<<<grid, 256, S::TOTAL, st>>>(tA, tB, args);
+    kern<<<grid, 256, S::TOTAL, st>>>(m.a, m.b, m.out, m.aux, m.gate, args);
     note_launches(1);
     return check_launch("gemm_rows");
 }
@@ -164,6 +173,9 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
                                     float out_scale, int flags, void* stream) {
     MM_REQUIRE(A && W && out, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: null operand");
     MM_REQUIRE(K > 0 && K % 8 == 0 && N > 0 && E > 0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: K must be a positive multiple of 8");
+    MM_REQUIRE((aux == nullptr) == (gate == nullptr), MM_ERR_UNSUPPORTED,
+               "mm_grouped_gemm_rows: aux and gate must be given together");
+    MM_REQUIRE(!(aux && out_f32), MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: aux/gate need a bf16 output");
     const int BN = pick_bn_rows(N);
     MM_REQUIRE(BN != 0, MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: N must be a multiple of 32");
     if (!tile_info) {
@@ -172,19 +184,30 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
         tile_begin = 0;
     }
     if (tile_count <= 0) return MM_OK;
+    const uint64_t io_rows = tile_info ? static_cast<uint64_t>(tile_count) * TILE_M : static_cast<uint64_t>(M);
     MM_REQUIRE((ld_out * (out_f32 ? 4 : 2)) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, MM_ERR_MISALIGNED,
                "mm_grouped_gemm_rows: out must be 16-byte aligned");
-    MM_REQUIRE(!aux || ((ld_aux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0), MM_ERR_MISALIGNED,
-               "mm_grouped_gemm_rows: aux must be 16-byte aligned");
-    MM_REQUIRE(!gate || ((ld_gate * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0), MM_ERR_MISALIGNED,
-               "mm_grouped_gemm_rows: gate must be 16-byte aligned");
-    CUtensorMap tA, tB;
-    int rc = encode_tmap_bf16(&tA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(a_rows), static_cast<uint64_t>(lda), 64,
+    RowsMaps m;
+    int rc = encode_tmap_bf16(&m.a, A, static_cast<uint64_t>(K), static_cast<uint64_t>(a_rows), static_cast<uint64_t>(lda), 64,
                               TILE_M, "mm_grouped_gemm_rows(A)");
     if (rc) return rc;
-    rc = encode_tmap_bf16(&tB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64, BN,
+    rc = encode_tmap_bf16(&m.b, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64, BN,
                           "mm_grouped_gemm_rows(W)");
     if (rc) return rc;
+    m.out = m.a; m.aux = m.a; m.gate = m.a;   // placeholders when unused
+    if (!out_f32) {
+        rc = encode_tmap(&m.out, out, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_out), 32, 32,
+                         CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(out)");
+        if (rc) return rc;
+    }
+    if (aux) {
+        rc = encode_tmap(&m.aux, aux, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_aux), 32, 32,
+                         CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(aux)");
+        if (rc) return rc;
+        rc = encode_tmap(&m.gate, gate, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_gate), 32, 32,
+                         CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(gate)");
+        if (rc) return rc;
+    }
     RowsGemmArgs g;
     g.tile_info = reinterpret_cast<const int2*>(tile_info);
     g.tile_begin = tile_begin;
@@ -194,19 +217,16 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
     g.K = K;
     g.n_tiles = N / BN;
     g.bias = bias;
-    g.aux = static_cast<const __nv_bfloat16*>(aux);
-    g.ld_aux = ld_aux;
-    g.gate = static_cast<const __nv_bfloat16*>(gate);
-    g.ld_gate = ld_gate;
     g.out = out;
     g.ld_out = ld_out;
     g.colsum = colsum;
     g.out_scale = out_scale;
     g.flags = flags;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MM_ROWS_CASE(bn)                                                   \
-    case bn:                                                               \
-        return out_f32 ? launch_rows<bn, true>(tA, tB, g, st) : launch_rows<bn, false>(tA, tB, g, st);
+#define MM_ROWS_CASE(bn)                                                                          \
+    case bn:                                                                                      \
+        if (out_f32) return launch_rows<bn, true, false>(m, g, st);                               \
+        return aux ? launch_rows<bn, false, true>(m, g, st) : launch_rows<bn, false, false>(m, g, st);
     switch (BN) {
         MM_ROWS_CASE(256)
         MM_ROWS_CASE(192)

@@ -19,6 +19,12 @@
 // warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp_idx % 4).
 // Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Epilogue data movement (bf16 output): every epilogue warp owns 32 rows.  Per 32-column chunk
+// it reads the accumulator with tcgen05.ld (thread = row), optionally combines it with the
+// `aux` / `gate` tiles that it TMA-loaded into its private, double-buffered staging slots,
+// writes the bf16 result into a 64-byte-swizzled staging slot and hands that slot to a TMA
+// store — so global memory only ever sees whole 64-byte row segments of 32 consecutive rows.
 #pragma once
 #include "mm_common.cuh"
 
@@ -26,7 +32,7 @@ namespace mm {
 
 enum : int {
     EPI_RELU = 1,       // out = max(out, 0)
-    EPI_ZERO_PAD = 2,   // rows >= valid_rows of a tile are written as zeros
+    EPI_ZERO_PAD = 2,   // kept for ABI compatibility: padding rows of an owned tile are always written as zeros
 };
 
 struct RowsGemmArgs {
@@ -37,11 +43,7 @@ struct RowsGemmArgs {
     int N, K;
     int n_tiles;             // N / BN
     const float* bias;       // [E, N] fp32 or nullptr
-    const __nv_bfloat16* aux;   // [rows, ld_aux] added to the accumulator, or nullptr
-    long long ld_aux;
-    const __nv_bfloat16* gate;  // [rows, ld_gate]; out = gate > 0 ? out : 0, or nullptr
-    long long ld_gate;
-    void* out;               // bf16 (or fp32 when OUT_F32) [rows, ld_out]
+    void* out;               // fp32 [rows, ld_out] (OUT_F32 only; the bf16 path stores through tmOut)
     long long ld_out;
     float* colsum;           // [E, N] fp32, += column sums of the written tile (bias gradients) or nullptr
     float out_scale;         // multiplies the accumulator before bias (1.0 for the MoE path)
@@ -57,13 +59,17 @@ struct WgradArgs {
     float* out;              // [E, N1, N2] fp32, accumulated with red.add
 };
 
-template <int BN, int STAGES>
+constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
+
+template <int BN, int STAGES, bool AUX = false>
 struct GemmSmem {
     static constexpr int A_BYTES = TILE_M * 64 * 2;                 // 16 KB: 128 rows x 64 bf16 (K-major) or 2 x (64 k-rows x 64 mn)
     static constexpr int B_BYTES = ((BN + 63) / 64) * 64 * 64 * 2;   // BN rounded up to 64-wide chunks
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int EPI_OUT_BYTES = 4 * 2 * EPI_SLOT_BYTES;                    // 4 warps x double buffer
+    static constexpr int EPI_IN_BYTES = AUX ? 4 * 2 * 2 * EPI_SLOT_BYTES : 0;       // x {aux, gate}
+    static constexpr int BAR_BYTES = (2 * STAGES + 4 + 8) * 8 + 16;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
 
 // ------------------------------------------------------------------------------------
@@ -84,25 +90,33 @@ MM_DEVINL float warp_colsum32(float (&f)[32], int lane) {
     return f[0];
 }
 
+// 16-byte chunk j (0..3) of row r inside a 32-row x 64-byte staging slot written/read by TMA with
+// CU_TENSOR_MAP_SWIZZLE_64B (address bits [4,6) ^= bits [7,9)).
+MM_DEVINL uint32_t epi_slot_off(int r, int j) { return static_cast<uint32_t>(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
 // ------------------------------------------------------------------------------------
 // gemm_rows_kernel
 // ------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool OUT_F32>
+template <int BN, int STAGES, bool OUT_F32, bool AUX>
 __global__ void __launch_bounds__(256, 1)
 gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const RowsGemmArgs a) {
-    using S = GemmSmem<BN, STAGES>;
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
+                 const __grid_constant__ CUtensorMap tmGate, const RowsGemmArgs a) {
+    using S = GemmSmem<BN, STAGES, AUX>;
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
     static_assert(BN % 16 == 0, "UMMA N constraint for M = 128");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * S::A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint8_t* sOut = smem + STAGES * S::STAGE_BYTES;
+    uint8_t* sIn = sOut + S::EPI_OUT_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sIn + S::EPI_IN_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* inbar = tempty + 2;          // [4 warps][2 slots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -110,10 +124,13 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (!OUT_F32) tma_prefetch_desc(&tmOut);
+        if (AUX) { tma_prefetch_desc(&tmAux); tma_prefetch_desc(&tmGate); }
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 8; ++s) mbar_init(&inbar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -173,28 +190,57 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;
+        constexpr int NCH = BN / 32;
+        uint8_t* my_out = sOut + q * 2 * EPI_SLOT_BYTES;
+        uint8_t* my_in = sIn + q * 4 * EPI_SLOT_BYTES;      // slot b: aux at b * 2 * SLOT, gate right after it
+        uint64_t* my_bar = inbar + q * 2;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int oslot = 0;                 // staging slot for the next output chunk
+        int islot = 0; uint32_t iphase[2] = {0, 0};
+
+        // first valid work item of this CTA (for the aux/gate prefetch chain)
+        auto next_valid = [&](int w) {
+            for (; w < total_work; w += gridDim.x) {
+                if (!a.tile_info || a.tile_info[a.tile_begin + w / a.n_tiles].x >= 0) break;
+            }
+            return w;
+        };
+        auto issue_in = [&](int w, int c, int slot) {   // lane 0 only
+            const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
+            const int row0 = lt * TILE_M + q * 32, col0 = nt * BN + c * 32;
+            mbar_expect_tx(&my_bar[slot], 2 * EPI_SLOT_BYTES);
+            tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES, &tmAux, &my_bar[slot], col0, row0);
+            tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES + EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
+        };
+
+        int w = next_valid(blockIdx.x);
+        if (AUX && w < total_work && lane == 0) issue_in(w, 0, 0);
+        while (w < total_work) {
             const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
             int e = 0, valid = TILE_M;
             if (a.tile_info) {
                 const int2 ti = a.tile_info[a.tile_begin + lt];
                 e = ti.x; valid = ti.y;
-                if (e < 0) continue;
             } else {
                 valid = min(TILE_M, a.M - lt * TILE_M);
             }
+            const int w_next = next_valid(w + gridDim.x);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int r_in_tile = q * 32 + lane;
             const long long row = static_cast<long long>(lt) * TILE_M + r_in_tile;
             const bool row_valid = r_in_tile < valid;
-            const bool row_store = row_valid || (a.flags & EPI_ZERO_PAD);
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c * 32, v);
+                if (AUX) {   // prefetch the next chunk's aux/gate into the other slot (its readers finished last iteration)
+                    if (lane == 0) {
+                        if (c + 1 < NCH) issue_in(w, c + 1, islot ^ 1);
+                        else if (w_next < total_work) issue_in(w_next, 0, islot ^ 1);
+                    }
+                }
                 tmem_ld_wait();
                 const int col0 = nt * BN + c * 32;
                 float f[32];
@@ -208,32 +254,31 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
                     }
                 }
-                if (a.aux && row_valid) {
-                    const uint4* ap = reinterpret_cast<const uint4*>(a.aux + row * a.ld_aux + col0);
+                if (AUX) {
+                    mbar_wait(&my_bar[islot], iphase[islot]);
+                    iphase[islot] ^= 1;
+                    const uint8_t* ax = my_in + islot * 2 * EPI_SLOT_BYTES;
+                    const uint8_t* gt = ax + EPI_SLOT_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 u = ldg_nc_v4(ap + j);
+                        const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
+                        const uint4 g = *reinterpret_cast<const uint4*>(gt + epi_slot_off(lane, j));
                         f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
                         f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);
                         f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
                         f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
-                    }
-                }
-                if (a.gate && row_valid) {
-                    const uint4* gp = reinterpret_cast<const uint4*>(a.gate + row * a.ld_gate + col0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 u = ldg_nc_v4(gp + j);
                         // gate holds ReLU outputs (>= 0): "> 0" is "bits != 0" on the bf16 payload.
-                        if ((u.x & 0x0000ffffu) == 0) f[8 * j + 0] = 0.f;
-                        if ((u.x & 0xffff0000u) == 0) f[8 * j + 1] = 0.f;
-                        if ((u.y & 0x0000ffffu) == 0) f[8 * j + 2] = 0.f;
-                        if ((u.y & 0xffff0000u) == 0) f[8 * j + 3] = 0.f;
-                        if ((u.z & 0x0000ffffu) == 0) f[8 * j + 4] = 0.f;
-                        if ((u.z & 0xffff0000u) == 0) f[8 * j + 5] = 0.f;
-                        if ((u.w & 0x0000ffffu) == 0) f[8 * j + 6] = 0.f;
-                        if ((u.w & 0xffff0000u) == 0) f[8 * j + 7] = 0.f;
+                        if ((g.x & 0x0000ffffu) == 0) f[8 * j + 0] = 0.f;
+                        if ((g.x & 0xffff0000u) == 0) f[8 * j + 1] = 0.f;
+                        if ((g.y & 0x0000ffffu) == 0) f[8 * j + 2] = 0.f;
+                        if ((g.y & 0xffff0000u) == 0) f[8 * j + 3] = 0.f;
+                        if ((g.z & 0x0000ffffu) == 0) f[8 * j + 4] = 0.f;
+                        if ((g.z & 0xffff0000u) == 0) f[8 * j + 5] = 0.f;
+                        if ((g.w & 0x0000ffffu) == 0) f[8 * j + 6] = 0.f;
+                        if ((g.w & 0xffff0000u) == 0) f[8 * j + 7] = 0.f;
                     }
+                    __syncwarp();       // every lane is done with slot `islot` before lane 0 refills it next iteration
+                    islot ^= 1;
                 }
                 if (a.flags & EPI_RELU) {
 #pragma unroll
@@ -243,23 +288,33 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = 0.f;
                 }
-                if (row_store) {
-                    if constexpr (OUT_F32) {
+                if constexpr (OUT_F32) {
+                    if (row_valid) {
                         float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + row * a.ld_out + col0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-                        __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(a.out) + row * a.ld_out + col0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                            u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                            u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                            u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                            stg_v4(ob + 8 * j, u);
-                        }
                     }
+                } else {
+                    // staging slot `oslot` is free once the store issued two chunks ago has read it
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    uint8_t* so = my_out + oslot * EPI_SLOT_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(so + epi_slot_off(lane, j)) = u;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, so, col0, lt * TILE_M + q * 32);
+                        tma_store_commit();
+                    }
+                    oslot ^= 1;
                 }
                 if (a.colsum) {
                     const float cs = warp_colsum32(f, lane);
@@ -270,7 +325,9 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            w = w_next;
         }
+        if (!OUT_F32 && lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -125,6 +125,19 @@ MM_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
         : "memory");
 }
 
+// 2-D tile store smem -> global (bulk async group); out-of-bounds rows/cols are clipped by the tensor map.
+MM_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+MM_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk store groups still READ their shared-memory source
+template <int N>
+MM_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+MM_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------
