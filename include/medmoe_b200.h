@@ -115,7 +115,7 @@ int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2,
                                   const int32_t* slot_row, const float* gate, float* beta, void* out, int out_f32,
                                   float* gpart, float* global_feat, void* stream);
 /* backward: dlocal [B, P, D] (bf16/fp32, may be NULL), dglobal [B, D] fp32 (may be NULL) ->
- * dlogit [n_items, P, 4], dgate [n_items] (+=, may be NULL), dUT [rows, D] bf16, dZ [rows, D/2] bf16,
+ * dlogit [n_items, P, 8] scratch (dlogit, or the two column-half partial dbeta of the token-centric path), dgate [n_items] (+=, may be NULL), dUT [rows, D] bf16, dZ [rows, D/2] bf16,
  * part [n_items, mm_combine_num_part_blocks, D + 1] scratch, dw2_db1_db2 [K, D + 1] = per expert
  * {dw2 (D/2) | db1 (D/2) | db2}.  mom_u [n_items, mm_combine_num_runs, 2, D] and mom_z [.., 2, D/2] fp32 scratch enable
  * the token-centric path (integer scale ratios); NULL or force_generic selects the generic gather kernel. */

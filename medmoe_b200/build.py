@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("MEDMOE_NVCC_EXTRA", "").split()   # e.g. -DMM_COMBINE_MINBLOCKS=1 for tuning experiments
 
 
 def _nvcc() -> str:

@@ -22,6 +22,9 @@
 
 namespace mm {
 
+#ifndef MM_COMBINE_MINBLOCKS
+#define MM_COMBINE_MINBLOCKS 1   // resident CTAs/SM the run-based kernels are compiled for (register cap = 65536 / (256 * n))
+#endif
 constexpr int CB_TOKENS_PER_WARP = 8;
 constexpr int CB_TOKENS_PER_BLOCK = 64;   // 8 warps x 8 tokens
 constexpr int CB_ROWS_PER_WARP = 8;
@@ -484,9 +487,304 @@ MM_DEVINL void store_slab_f32(float* p, int lane, const float (&f)[NE * 4]) {
         *reinterpret_cast<float4*>(p + 4 * (lane + 32 * t)) = make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
 }
 
+// Row cache: the two native rows (i0, i1) a token interpolates between change only every
+// r = P / P_s tokens, so a warp that walks consecutive tokens keeps them in registers.
+template <int NE>
+struct RowPair {
+    float a[NE * 4], b[NE * 4];
+    int row_a = -1, row_b = -1;
+};
+// make `c.a` / `c.b` hold rows L.i0 / L.i1 of the [rows, ld] bf16 matrix (column offset already applied)
+template <int NE>
+MM_DEVINL bool row_pair_update(RowPair<NE>& c, const __nv_bfloat16* mat, long long base, long long ld, const LerpSrc& L, int lane) {
+    if (L.i0 != c.row_a) {
+        if (L.i0 == c.row_b) {
+#pragma unroll
+            for (int k = 0; k < NE * 4; ++k) c.a[k] = c.b[k];
+        } else {
+            load_row_bf16x4<NE>(mat + (base + L.i0) * ld, lane, c.a);
+        }
+        c.row_a = L.i0;
+    }
+    const bool two = (L.i1 != L.i0) && (L.lam != 0.f);
+    if (two && L.i1 != c.row_b) {
+        load_row_bf16x4<NE>(mat + (base + L.i1) * ld, lane, c.b);
+        c.row_b = L.i1;
+    }
+    return two;
+}
+
+// ------------------------------------------------------------------------------------
+// forward, run-based (requires Ps[0] == P).
+//   pass 1  combine_logits_kernel : warp = 32-token run; per scale the 32 partial dots are reduced
+//           with one 31-shuffle transpose-reduction; lane t ends up with the 4 logits of token t,
+//           applies the softmax over scales and writes beta coalesced.
+//   pass 2  combine_out_kernel    : warp = (run, column half); beta comes in by one coalesced load
+//           + shuffle broadcast, coarse Y rows live in registers, one 8-byte load per 4 channels.
+// ------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
+combine_logits_kernel(const CombineArgs a) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;
+    if (c >= a.nruns) return;
+    const int item = blockIdx.y;
+    const int slot = a.inv_perm[item];
+    const int e = a.slot_expert[slot];
+    const int t0 = c * RUN_TOKENS;
+    float w2[E];
+    load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+    const float b2 = a.b2[e];
+    float lg0 = 0.f, lg1 = 0.f, lg2 = 0.f, lg3 = 0.f;
+    for (int s = 0; s < 4; ++s) {
+        const long long base = a.slot_row[s * a.n_items + slot];
+        const int Ps = a.Ps[s];
+        const float scale = a.scale[s];
+        RowPair<NE> z;
+        float part[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int p = t0 + t;
+            float acc = 0.f;
+            if (p < a.P) {
+                const LerpSrc L = lerp_src(p, scale, Ps);
+                const bool two = row_pair_update<NE>(z, a.Z, base, H, L, lane);
+                const float l0 = 1.0f - L.lam;
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    const float h = two ? (l0 * z.a[k] + L.lam * z.b[k]) : z.a[k];
+                    acc = fmaf(fmaxf(h, 0.f), w2[k], acc);
+                }
+            }
+            part[t] = acc;
+        }
+        const float tot = warp_colsum32(part, lane) + b2;     // lane t: logit of token t0 + t at scale s
+        if (s == 0) lg0 = tot; else if (s == 1) lg1 = tot; else if (s == 2) lg2 = tot; else lg3 = tot;
+    }
+    const float mx = fmaxf(fmaxf(lg0, lg1), fmaxf(lg2, lg3));
+    const float e0 = expf(lg0 - mx), e1 = expf(lg1 - mx), e2 = expf(lg2 - mx), e3 = expf(lg3 - mx);
+    const float inv = 1.0f / (e0 + e1 + e2 + e3);
+    if (t0 + lane < a.P)
+        *reinterpret_cast<float4*>(a.beta + (static_cast<size_t>(slot) * a.P + t0 + lane) * 4) =
+            make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
+}
+
+constexpr int OUT_RUNS_PER_BLOCK = 4;   // 8 warps = 4 runs x 2 column halves
+
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
+combine_out_kernel(const CombineArgs a) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    __shared__ float s_g[OUT_RUNS_PER_BLOCK][D];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * OUT_RUNS_PER_BLOCK + (warp >> 1);
+    const int col0 = (warp & 1) * H;
+    const int b = blockIdx.y;
+    const int t0 = c * RUN_TOKENS;
+    float gsum[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) gsum[k] = 0.f;
+    if (c < a.nruns) {
+        const int n_tok = min(RUN_TOKENS, a.P - t0);
+        for (int jk = 0; jk < a.topk; ++jk) {
+            const int item = b * a.topk + jk;
+            const int slot = a.inv_perm[item];
+            const float g = a.gate ? a.gate[item] : 1.0f;
+            float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < n_tok) bl = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + t0 + lane) * 4);
+            long long base[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) base[s] = a.slot_row[s * a.n_items + slot];
+            RowPair<NE> y1, y2, y3;
+            float y0[E];
+            load_row_bf16x4<NE>(a.Y + (base[0] + t0) * D + col0, lane, y0);
+            for (int t = 0; t < n_tok; ++t) {
+                const int p = t0 + t;
+                float yn[E];     // next token's finest-scale row: issued before this token's math
+#pragma unroll
+                for (int k = 0; k < E; ++k) yn[k] = 0.f;
+                if (t + 1 < n_tok) load_row_bf16x4<NE>(a.Y + (base[0] + p + 1) * D + col0, lane, yn);
+                const float bt0 = __shfl_sync(0xffffffffu, bl.x, t) * g;
+                const float bt1 = __shfl_sync(0xffffffffu, bl.y, t) * g;
+                const float bt2 = __shfl_sync(0xffffffffu, bl.z, t) * g;
+                const float bt3 = __shfl_sync(0xffffffffu, bl.w, t) * g;
+                float o[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) o[k] = bt0 * y0[k];
+                {
+                    const LerpSrc L = lerp_src(p, a.scale[1], a.Ps[1]);
+                    const bool two = row_pair_update<NE>(y1, a.Y + col0, base[1], D, L, lane);
+                    const float c0 = bt1 * (1.0f - L.lam), c1 = bt1 * L.lam;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) o[k] = two ? fmaf(c0, y1.a[k], fmaf(c1, y1.b[k], o[k])) : fmaf(bt1, y1.a[k], o[k]);
+                }
+                {
+                    const LerpSrc L = lerp_src(p, a.scale[2], a.Ps[2]);
+                    const bool two = row_pair_update<NE>(y2, a.Y + col0, base[2], D, L, lane);
+                    const float c0 = bt2 * (1.0f - L.lam), c1 = bt2 * L.lam;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) o[k] = two ? fmaf(c0, y2.a[k], fmaf(c1, y2.b[k], o[k])) : fmaf(bt2, y2.a[k], o[k]);
+                }
+                {
+                    const LerpSrc L = lerp_src(p, a.scale[3], a.Ps[3]);
+                    const bool two = row_pair_update<NE>(y3, a.Y + col0, base[3], D, L, lane);
+                    const float c0 = bt3 * (1.0f - L.lam), c1 = bt3 * L.lam;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) o[k] = two ? fmaf(c0, y3.a[k], fmaf(c1, y3.b[k], o[k])) : fmaf(bt3, y3.a[k], o[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < E; ++k) gsum[k] += o[k];
+                OutT* orow = static_cast<OutT*>(a.out) + (static_cast<size_t>(b) * a.P + p) * D + col0;
+                if (jk > 0) {   // top-k extension: accumulate onto the previous choice's contribution
+                    float prev[E];
+                    load_slab<NE, OutT>(orow, lane, prev);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) o[k] += prev[k];
+                }
+                if constexpr (sizeof(OutT) == 2) store_slab_bf16<NE>(reinterpret_cast<__nv_bfloat16*>(orow), lane, o);
+                else store_slab_f32<NE>(reinterpret_cast<float*>(orow), lane, o);
+#pragma unroll
+                for (int k = 0; k < E; ++k) y0[k] = yn[k];
+            }
+        }
+    }
+    // deterministic per-block partial of the global mean: [b, block, D]
+#pragma unroll
+    for (int t = 0; t < NE; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_g[warp >> 1][col0 + 4 * (lane + 32 * t) + k] = gsum[4 * t + k];
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < OUT_RUNS_PER_BLOCK; ++w) acc += s_g[w][d];
+        a.gpart[(static_cast<size_t>(b) * a.nblk + blockIdx.x) * D + d] = acc;
+    }
+}
+
+// Per-lane token scalars for the token-centric backward: lane t keeps the value of tokens
+// p_lo + t and p_lo + 32 + t (a run plus its halo spans at most 64 tokens); the loop reads
+// them back with one shuffle instead of a dependent global load per token.
+MM_DEVINL float lane_pick(float va, float vb, int idx) {
+    const float x = __shfl_sync(0xffffffffu, va, idx & 31);
+    const float y = __shfl_sync(0xffffffffu, vb, idx & 31);
+    return idx < 32 ? x : y;
+}
+
+// backward pass A, run-based: partial dbeta_s = <dF, interp(Y_s)> over one column half.
+// grid = (ceil(nruns / 4), B); warp = (run, column half).  dbeta [n_items, P, 2, 4].
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
+combine_bwd_dbeta_kernel(const CombineArgs a) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * OUT_RUNS_PER_BLOCK + (warp >> 1);
+    const int half = warp & 1;
+    const int col0 = half * H;
+    const int b = blockIdx.y;
+    const int t0 = c * RUN_TOKENS;
+    if (c >= a.nruns) return;
+    const int n_tok = min(RUN_TOKENS, a.P - t0);
+    float dg[E];
+    if (a.dglobal) {
+        load_slab<NE, float>(a.dglobal + static_cast<size_t>(b) * D + col0, lane, dg);
+        const float inv_p = 1.0f / static_cast<float>(a.P);
+#pragma unroll
+        for (int k = 0; k < E; ++k) dg[k] *= inv_p;
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k) dg[k] = 0.f;
+    }
+    const OutT* dl_base = a.dlocal ? static_cast<const OutT*>(a.dlocal) + (static_cast<size_t>(b) * a.P + t0) * D + col0 : nullptr;
+    for (int jk = 0; jk < a.topk; ++jk) {
+        const int item = b * a.topk + jk;
+        const int slot = a.inv_perm[item];
+        long long base[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) base[s] = a.slot_row[s * a.n_items + slot];
+        RowPair<NE> y1, y2, y3;
+        float y0[E], df[E];
+        load_row_bf16x4<NE>(a.Y + (base[0] + t0) * D + col0, lane, y0);
+        if (dl_base) {
+            load_slab<NE, OutT>(dl_base, lane, df);
+#pragma unroll
+            for (int k = 0; k < E; ++k) df[k] += dg[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; ++k) df[k] = dg[k];
+        }
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < n_tok; ++t) {
+            const int p = t0 + t;
+            float yn[E], dfn[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) { yn[k] = 0.f; dfn[k] = dg[k]; }
+            if (t + 1 < n_tok) {
+                load_row_bf16x4<NE>(a.Y + (base[0] + p + 1) * D + col0, lane, yn);
+                if (dl_base) {
+                    load_slab<NE, OutT>(dl_base + static_cast<size_t>(t + 1) * D, lane, dfn);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) dfn[k] += dg[k];
+                }
+            }
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < E; ++k) d0 = fmaf(df[k], y0[k], d0);
+            {
+                const LerpSrc L = lerp_src(p, a.scale[1], a.Ps[1]);
+                const bool two = row_pair_update<NE>(y1, a.Y + col0, base[1], D, L, lane);
+                const float l0 = 1.0f - L.lam;
+#pragma unroll
+                for (int k = 0; k < E; ++k) d1 = fmaf(df[k], two ? (l0 * y1.a[k] + L.lam * y1.b[k]) : y1.a[k], d1);
+            }
+            {
+                const LerpSrc L = lerp_src(p, a.scale[2], a.Ps[2]);
+                const bool two = row_pair_update<NE>(y2, a.Y + col0, base[2], D, L, lane);
+                const float l0 = 1.0f - L.lam;
+#pragma unroll
+                for (int k = 0; k < E; ++k) d2 = fmaf(df[k], two ? (l0 * y2.a[k] + L.lam * y2.b[k]) : y2.a[k], d2);
+            }
+            {
+                const LerpSrc L = lerp_src(p, a.scale[3], a.Ps[3]);
+                const bool two = row_pair_update<NE>(y3, a.Y + col0, base[3], D, L, lane);
+                const float l0 = 1.0f - L.lam;
+#pragma unroll
+                for (int k = 0; k < E; ++k) d3 = fmaf(df[k], two ? (l0 * y3.a[k] + L.lam * y3.b[k]) : y3.a[k], d3);
+            }
+            d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3);
+            if (lane == t) mine = make_float4(d0, d1, d2, d3);
+#pragma unroll
+            for (int k = 0; k < E; ++k) { y0[k] = yn[k]; df[k] = dfn[k]; }
+        }
+        if (lane < n_tok)
+            *reinterpret_cast<float4*>(a.dlogit + ((static_cast<size_t>(slot) * a.P + t0 + lane) * 2 + half) * 4) = mine;
+    }
+}
+
+// dlogit of one token from beta and the two dbeta halves (softmax-over-scales backward), scaled by the gate.
+MM_DEVINL float4 token_dlogit(const CombineArgs& a, int slot, int p, float g, float& dot_out) {
+    dot_out = 0.f;
+    if (p < 0 || p >= a.P) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t tok = static_cast<size_t>(slot) * a.P + p;
+    const float4 bt = *reinterpret_cast<const float4*>(a.beta + tok * 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(a.dlogit + tok * 8);
+    const float4 h1 = *reinterpret_cast<const float4*>(a.dlogit + tok * 8 + 4);
+    const float d0 = h0.x + h1.x, d1 = h0.y + h1.y, d2 = h0.z + h1.z, d3 = h0.w + h1.w;
+    const float dot = bt.x * d0 + bt.y * d1 + bt.z * d2 + bt.w * d3;
+    dot_out = dot;
+    return make_float4(g * bt.x * (d0 - dot), g * bt.y * (d1 - dot), g * bt.z * (d2 - dot), g * bt.w * (d3 - dot));
+}
+
 // dUT: grid = (ceil(2 * nruns / 8), n_items); warp = (run, column half).
 template <int D, typename OutT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
 combine_bwd_u_kernel(const CombineArgs a) {
     constexpr int NE = D / 256;
     constexpr int E = NE * 4;
@@ -523,20 +821,40 @@ combine_bwd_u_kernel(const CombineArgs a) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) base[s] = a.slot_row[s * a.n_items + slot];
 
-    const int p_lo = max(0, t0 - a.halo), p_hi = min(a.P, t0 + RUN_TOKENS + a.halo);
-    for (int p = p_lo; p < p_hi; ++p) {
+    const int p_lo = t0 - a.halo, p_hi = min(a.P, t0 + RUN_TOKENS + a.halo);
+    const int p_first = max(0, p_lo);
+    // beta (x gate) of tokens p_lo + lane and p_lo + 32 + lane
+    float4 bA = make_float4(0.f, 0.f, 0.f, 0.f), bB = bA;
+    {
+        const int pa = p_lo + lane, pb = p_lo + 32 + lane;
+        if (pa >= 0 && pa < a.P) bA = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + pa) * 4);
+        if (pb >= 0 && pb < a.P) bB = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + pb) * 4);
+        bA.x *= g; bA.y *= g; bA.z *= g; bA.w *= g;
+        bB.x *= g; bB.y *= g; bB.z *= g; bB.w *= g;
+    }
+    const OutT* dl_base = a.dlocal ? static_cast<const OutT*>(a.dlocal) + static_cast<size_t>(b) * a.P * D + col0 : nullptr;
+    float df[E];
+    if (dl_base) {
+        load_slab<NE, OutT>(dl_base + static_cast<size_t>(p_first) * D, lane, df);
+#pragma unroll
+        for (int k = 0; k < E; ++k) df[k] += dg[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < E; ++k) df[k] = dg[k];
+    }
+    for (int p = p_first; p < p_hi; ++p) {
         const bool in_run = (p >= t0) && (p < t0 + RUN_TOKENS);
-        float df[E];
-        if (a.dlocal) {
-            load_slab<NE, OutT>(static_cast<const OutT*>(a.dlocal) + (static_cast<size_t>(b) * a.P + p) * D + col0, lane, df);
+        float dfn[E];
 #pragma unroll
-            for (int k = 0; k < E; ++k) df[k] += dg[k];
-        } else {
+        for (int k = 0; k < E; ++k) dfn[k] = dg[k];
+        if (dl_base && p + 1 < p_hi) {
+            load_slab<NE, OutT>(dl_base + static_cast<size_t>(p + 1) * D, lane, dfn);
 #pragma unroll
-            for (int k = 0; k < E; ++k) df[k] = dg[k];
+            for (int k = 0; k < E; ++k) dfn[k] += dg[k];
         }
-        const float4 bt4 = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
-        const float bt[4] = {bt4.x * g, bt4.y * g, bt4.z * g, bt4.w * g};
+        const int idx = p - p_lo;
+        const float bt[4] = {lane_pick(bA.x, bB.x, idx), lane_pick(bA.y, bB.y, idx), lane_pick(bA.z, bB.z, idx),
+                             lane_pick(bA.w, bB.w, idx)};
         if (in_run) {   // scale 0: identity
             float o[E];
 #pragma unroll
@@ -579,6 +897,8 @@ combine_bwd_u_kernel(const CombineArgs a) {
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < E; ++k) df[k] = dfn[k];
     }
 #pragma unroll
     for (int s = 1; s < 4; ++s) {
@@ -599,7 +919,7 @@ combine_bwd_u_kernel(const CombineArgs a) {
 
 // dZ + the per-token parameter gradients (dw2, db1, db2): grid = (ceil(nruns / 8), n_items + K); warp = run.
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
 combine_bwd_z_kernel(const CombineArgs a) {
     constexpr int NE = D / 256;
     constexpr int E = NE * 4;
@@ -623,7 +943,9 @@ combine_bwd_z_kernel(const CombineArgs a) {
 
     const int c = blockIdx.x * RUNS_PER_BLOCK + warp;
     const int slot = blockIdx.y;
+    const int item = a.perm[slot];
     const int e = a.slot_expert[slot];
+    const float g = a.gate ? a.gate[item] : 1.0f;
     const int t0 = c * RUN_TOKENS;
     float dw2[E], db1[E], db2 = 0.f;
 #pragma unroll
@@ -632,40 +954,51 @@ combine_bwd_z_kernel(const CombineArgs a) {
     if (c < a.nruns) {
         float w2[E];
         load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
-        const float* dlg = a.dlogit + static_cast<size_t>(slot) * a.P * 4;
+        // dlogit of tokens (t0 - halo) + lane and + 32 + lane; the gate gradient falls out of the same dot product
+        const int p_base = t0 - a.halo;
+        float dotA, dotB;
+        const float4 dlA = token_dlogit(a, slot, p_base + lane, g, dotA);
+        const float4 dlB = token_dlogit(a, slot, p_base + 32 + lane, g, dotB);
+        if (a.dgate) {
+            const int pa = p_base + lane, pb = p_base + 32 + lane;
+            float dsum = ((pa >= t0 && pa < t0 + RUN_TOKENS) ? dotA : 0.f) + ((pb >= t0 && pb < t0 + RUN_TOKENS) ? dotB : 0.f);
+            dsum = warp_sum(dsum);
+            if (lane == 0) atomicAdd(a.dgate + item, dsum);
+        }
         for (int s = 0; s < 4; ++s) {
             const int mode = a.mode[s];
             const int r = a.ratio[s];
             const long long base = a.slot_row[s * a.n_items + slot];
             const int hs = (mode == SCALE_DIRECT) ? (r >> 1) : 0;
             const int p_lo = max(0, t0 - hs), p_hi = min(a.P, t0 + RUN_TOKENS + hs);
-            float lo[E], hi[E], za[E], zb[E];
-            int cur = -1, za_row = -1, zb_row = -1;
+            const float cA = s == 0 ? dlA.x : (s == 1 ? dlA.y : (s == 2 ? dlA.z : dlA.w));
+            const float cB = s == 0 ? dlB.x : (s == 1 ? dlB.y : (s == 2 ? dlB.z : dlB.w));
+            float lo[E], hi[E];
+            RowPair<NE> z;
+            int cur = -1;
 #pragma unroll
-            for (int k = 0; k < E; ++k) { lo[k] = 0.f; hi[k] = 0.f; za[k] = 0.f; zb[k] = 0.f; }
+            for (int k = 0; k < E; ++k) { lo[k] = 0.f; hi[k] = 0.f; }
+            if (mode == SCALE_IDENT) {   // every token has its own row: keep the next row's load in flight
+                load_row_bf16x4<NE>(a.Z + (base + p_lo) * H, lane, z.a);
+            }
             for (int p = p_lo; p < p_hi; ++p) {
                 const bool in_run = (p >= t0) && (p < t0 + RUN_TOKENS);
-                const float dl = dlg[p * 4 + s];
+                const float dl = lane_pick(cA, cB, p - p_base);
                 const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
-                if (L.i0 != za_row) {
-                    if (L.i0 == zb_row) {
+                bool two = false;
+                float zn[E];
+                if (mode == SCALE_IDENT) {
 #pragma unroll
-                        for (int k = 0; k < E; ++k) za[k] = zb[k];
-                    } else {
-                        load_row_bf16x4<NE>(a.Z + (base + L.i0) * H, lane, za);
-                    }
-                    za_row = L.i0;
-                }
-                const bool two = (L.i1 != L.i0) && (L.lam != 0.f);
-                if (two && L.i1 != zb_row) {
-                    load_row_bf16x4<NE>(a.Z + (base + L.i1) * H, lane, zb);
-                    zb_row = L.i1;
+                    for (int k = 0; k < E; ++k) zn[k] = 0.f;
+                    if (p + 1 < p_hi) load_row_bf16x4<NE>(a.Z + (base + p + 1) * H, lane, zn);
+                } else {
+                    two = row_pair_update<NE>(z, a.Z, base, H, L, lane);
                 }
                 const float l0 = 1.0f - L.lam;
                 float gk[E];
 #pragma unroll
                 for (int k = 0; k < E; ++k) {
-                    const float h = two ? (l0 * za[k] + L.lam * zb[k]) : za[k];
+                    const float h = two ? (l0 * z.a[k] + L.lam * z.b[k]) : z.a[k];
                     gk[k] = h > 0.f ? dl * w2[k] : 0.f;
                     if (in_run && h > 0.f) dw2[k] = fmaf(dl, h, dw2[k]);
                 }
@@ -676,6 +1009,8 @@ combine_bwd_z_kernel(const CombineArgs a) {
                 }
                 if (mode == SCALE_IDENT) {
                     if (in_run) store_slab_bf16<NE>(a.dZ + (base + p) * H, lane, gk);
+#pragma unroll
+                    for (int k = 0; k < E; ++k) z.a[k] = zn[k];
                 } else if (mode == SCALE_DIRECT) {
                     if (L.i0 != cur) {
                         if (cur >= 0 && cur * r >= t0 && cur * r < t0 + RUN_TOKENS)
@@ -831,10 +1166,26 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     a.Y = static_cast<const __nv_bfloat16*>(Y); a.Z = static_cast<const __nv_bfloat16*>(Z);
     a.w2 = w2; a.b2 = b2; a.beta = beta; a.out = out; a.gpart = gpart;
     a.nblk = mm_combine_num_token_blocks(P);
+    a.nruns = (P + RUN_TOKENS - 1) / RUN_TOKENS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid(a.nblk, B);
-    MM_DISPATCH_D(D, out_f32, combine_fwd_kernel, grid, st, a)
-    mm::note_launches(1);
+    if (Ps[0] == P) {   // run-based kernels (finest scale at full resolution, as the reference's Swin stages are)
+        dim3 grid1((a.nruns + 7) / 8, a.n_items);
+        switch (D) {
+            case 256: combine_logits_kernel<256><<<grid1, 256, 0, st>>>(a); break;
+            case 512: combine_logits_kernel<512><<<grid1, 256, 0, st>>>(a); break;
+            case 768: combine_logits_kernel<768><<<grid1, 256, 0, st>>>(a); break;
+            case 1024: combine_logits_kernel<1024><<<grid1, 256, 0, st>>>(a); break;
+        }
+        mm::note_launches(1);
+        a.nblk = (a.nruns + OUT_RUNS_PER_BLOCK - 1) / OUT_RUNS_PER_BLOCK;    // <= mm_combine_num_token_blocks(P)
+        dim3 grid2(a.nblk, B);
+        MM_DISPATCH_D(D, out_f32, combine_out_kernel, grid2, st, a)
+        mm::note_launches(1);
+    } else {
+        dim3 grid(a.nblk, B);
+        MM_DISPATCH_D(D, out_f32, combine_fwd_kernel, grid, st, a)
+        mm::note_launches(1);
+    }
     rc = mm_check_launch("mm_interp_softmax_combine_fwd");
     if (rc) return rc;
     global_mean_kernel<<<dim3((D + 255) / 256, B), 256, 0, st>>>(gpart, a.nblk, D, 1.0f / static_cast<float>(P), global_feat);
@@ -898,7 +1249,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     const bool fast = !force_generic && mom_u && mom_z && classify_scales(a);
     a.nrb = fast ? (a.nruns + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK : mm_combine_num_row_blocks(Ps);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    {
+    if (!fast) {
         dim3 grid(a.nblk, B);
         MM_DISPATCH_D(D, dlocal_f32, combine_bwd_logit_kernel, grid, st, a)
         mm::note_launches(1);
@@ -906,6 +1257,11 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
         if (rc) return rc;
     }
     if (fast) {
+        {
+            dim3 grid((a.nruns + OUT_RUNS_PER_BLOCK - 1) / OUT_RUNS_PER_BLOCK, B);
+            MM_DISPATCH_D(D, dlocal_f32, combine_bwd_dbeta_kernel, grid, st, a)
+            mm::note_launches(1);
+        }
         {
             dim3 grid((2 * a.nruns + 7) / 8, a.n_items);
             MM_DISPATCH_D(D, dlocal_f32, combine_bwd_u_kernel, grid, st, a)

@@ -72,24 +72,6 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
 
-// ------------------------------------------------------------------------------------
-// Column sums of a 32x32 register tile: lane r holds row r (f[0..31]); on return lane c
-// holds sum over rows of column c in f[0].  31 shuffles.
-// ------------------------------------------------------------------------------------
-MM_DEVINL float warp_colsum32(float (&f)[32], int lane) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-            float send = up ? f[i] : f[i + o];
-            float keep = up ? f[i + o] : f[i];
-            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    return f[0];
-}
-
 // 16-byte chunk j (0..3) of row r inside a 32-row x 64-byte staging slot written/read by TMA with
 // CU_TENSOR_MAP_SWIZZLE_64B (address bits [4,6) ^= bits [7,9)).
 MM_DEVINL uint32_t epi_slot_off(int r, int j) { return static_cast<uint32_t>(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }

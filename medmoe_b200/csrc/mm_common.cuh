@@ -47,6 +47,22 @@ MM_DEVINL float warp_max(float v) {
     return v;
 }
 
+// Column sums of a 32x32 register tile: lane r holds row r (f[0..31]); on return lane c
+// holds sum over rows of column c in f[0].  31 shuffles.
+MM_DEVINL float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            float send = up ? f[i] : f[i + o];
+            float keep = up ? f[i + o] : f[i];
+            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return f[0];
+}
+
 MM_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
