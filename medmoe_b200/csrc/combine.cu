@@ -64,6 +64,14 @@ struct CombineArgs {
     int mode[4];                    // SCALE_IDENT / SCALE_DIRECT / SCALE_MOMENT
     int halo;                       // max over DIRECT scales of ratio / 2
     int nruns;                      // ceil(P / 32)
+    // TMA-staged persistent kernels: a tile is TT consecutive tokens of one item; per scale the native
+    // rows it touches are one contiguous row range, staged in shared memory by one bulk copy each
+    int tile_tokens;                // TT
+    int tiles_per_img;              // ceil(P / TT)
+    int cap[4];                     // rows reserved per scale in a stage: ceil(TT * Ps / P) + 2
+    int cap_off[4];                 // prefix sums of cap
+    int cap_total;
+    int dlogit_is_halves;           // dlogit holds two column-half partial dbeta ([.., 2, 4]) instead of finished dlogit
     float* mom_u;                   // [n_items, nruns, 2, D]   zeroth / first moments of beta_s * dF per 32-token run
     float* mom_z;                   // [n_items, nruns, 2, D/2] same for dlogit_s * w2 * gate
 };
@@ -667,6 +675,359 @@ combine_out_kernel(const CombineArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------
+// TMA-staged persistent kernels (forward logits, forward combine, backward dbeta).
+//
+// One CTA per SM walks over (item, token-tile) work items.  A producer thread stages, per scale,
+// the contiguous range of native rows the tile touches with ONE bulk copy (cp.async.bulk ->
+// shared memory, completion on an mbarrier), several tiles ahead; eight consumer warps read rows
+// with conflict-free LDS.128 and never issue a dependent global load.  Loads in flight per SM are
+// set by the stage depth (~75 KB), not by registers or occupancy.
+// ------------------------------------------------------------------------------------
+constexpr int ST_CONSUMER_WARPS = 8;
+constexpr int ST_THREADS = (ST_CONSUMER_WARPS + 1) * 32;
+
+struct TileRows { int i_lo[4]; int n[4]; };
+MM_DEVINL TileRows tile_rows(const CombineArgs& a, int t0, int t1) {
+    TileRows r;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const LerpSrc A = lerp_src(t0, a.scale[s], a.Ps[s]);
+        const LerpSrc B = lerp_src(t1 - 1, a.scale[s], a.Ps[s]);
+        r.i_lo[s] = A.i0;
+        r.n[s] = B.i1 - A.i0 + 1;
+    }
+    return r;
+}
+
+// producer: stage the rows of tile (slot, [t0, t1)) of the [rows, W] bf16 matrix `mat`
+template <int W>
+MM_DEVINL void stage_tile(const CombineArgs& a, const __nv_bfloat16* mat, int slot, int t0, int t1, uint8_t* dst, uint64_t* bar,
+                          uint32_t extra_bytes) {
+    const TileRows r = tile_rows(a, t0, t1);
+    uint32_t bytes = extra_bytes;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) bytes += static_cast<uint32_t>(r.n[s]) * W * 2;
+    mbar_expect_tx(bar, bytes);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const long long row = static_cast<long long>(a.slot_row[s * a.n_items + slot]) + r.i_lo[s];
+        bulk_load_1d(dst + static_cast<size_t>(a.cap_off[s]) * W * 2, mat + row * W, static_cast<uint32_t>(r.n[s]) * W * 2, bar);
+    }
+}
+
+// a [W]-wide staged row in the x8 lane layout (lane owns 16-byte chunks lane, lane+32, ...)
+template <int N>
+MM_DEVINL void lds_row_x8(const uint8_t* row, int lane, float (&f)[N * 8]) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const uint4 u = *reinterpret_cast<const uint4*>(row + 16 * (lane + 32 * t));
+        f[8 * t + 0] = bf16lo(u.x); f[8 * t + 1] = bf16hi(u.x); f[8 * t + 2] = bf16lo(u.y); f[8 * t + 3] = bf16hi(u.y);
+        f[8 * t + 4] = bf16lo(u.z); f[8 * t + 5] = bf16hi(u.z); f[8 * t + 6] = bf16lo(u.w); f[8 * t + 7] = bf16hi(u.w);
+    }
+}
+template <int NE>
+MM_DEVINL void lds_row_x4(const uint8_t* row, int lane, float (&f)[NE * 4]) {
+#pragma unroll
+    for (int t = 0; t < NE; ++t) {
+        const uint2 u = *reinterpret_cast<const uint2*>(row + 8 * (lane + 32 * t));
+        f[4 * t + 0] = bf16lo(u.x); f[4 * t + 1] = bf16hi(u.x); f[4 * t + 2] = bf16lo(u.y); f[4 * t + 3] = bf16hi(u.y);
+    }
+}
+
+// ---- forward pass 1: logits over scales + softmax -> beta.  Work item = (item, tile); Z rows staged. ----
+template <int D, int STAGES>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+combine_logits_staged_kernel(const CombineArgs a) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const size_t stage_bytes = static_cast<size_t>(a.cap_total) * H * 2;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int total = a.n_items * a.tiles_per_img;
+    const int TT = a.tile_tokens;
+    if (warp == ST_CONSUMER_WARPS) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int slot = w / a.tiles_per_img, tt = w - slot * a.tiles_per_img;
+                const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
+                mbar_wait(&empty[stage], phase ^ 1);
+                stage_tile<H>(a, a.Z, slot, t0, t1, smem + stage * stage_bytes, &full[stage], 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+    int stage = 0; uint32_t phase = 0;
+    const int tok_per_warp = TT / ST_CONSUMER_WARPS;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int slot = w / a.tiles_per_img, tt = w - slot * a.tiles_per_img;
+        const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
+        const int e = a.slot_expert[slot];
+        float w2[E];
+        load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+        const float b2 = a.b2[e];
+        const TileRows r = tile_rows(a, t0, t1);
+        mbar_wait(&full[stage], phase);
+        const uint8_t* st = smem + stage * stage_bytes;
+        for (int k = 0; k < tok_per_warp; ++k) {
+            const int p = t0 + warp * tok_per_warp + k;
+            if (p >= t1) break;
+            float lg[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                const uint8_t* ra = st + static_cast<size_t>(a.cap_off[s] + L.i0 - r.i_lo[s]) * H * 2;
+                float za[E];
+                lds_row_x4<NE>(ra, lane, za);
+                float acc = 0.f;
+                if (L.i1 != L.i0 && L.lam != 0.f) {
+                    float zb[E];
+                    lds_row_x4<NE>(ra + H * 2, lane, zb);
+                    const float l0 = 1.0f - L.lam;
+#pragma unroll
+                    for (int i = 0; i < E; ++i) acc = fmaf(fmaxf(l0 * za[i] + L.lam * zb[i], 0.f), w2[i], acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < E; ++i) acc = fmaf(fmaxf(za[i], 0.f), w2[i], acc);
+                }
+                lg[s] = warp_sum(acc) + b2;
+            }
+            const float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+            const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx), e3 = expf(lg[3] - mx);
+            const float inv = 1.0f / (e0 + e1 + e2 + e3);
+            if (lane == 0)
+                *reinterpret_cast<float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4) =
+                    make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+}
+
+// ---- forward pass 2: out = sum_s beta_s interp(Y_s); work item = (image, tile, top-k choice); Y rows staged. ----
+template <int D, typename OutT, int STAGES>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+combine_out_staged_kernel(const CombineArgs a) {
+    constexpr int N = D / 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const size_t stage_bytes = static_cast<size_t>(a.cap_total) * D * 2;
+    float* s_g = reinterpret_cast<float*>(smem + STAGES * stage_bytes);          // [8 warps][D]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_g + ST_CONSUMER_WARPS * D);
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int total = a.B * a.tiles_per_img;       // (image, tile); the top-k choices are the inner pipeline items
+    const int TT = a.tile_tokens;
+    if (warp == ST_CONSUMER_WARPS) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
+                const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
+                for (int jk = 0; jk < a.topk; ++jk) {
+                    const int slot = a.inv_perm[b * a.topk + jk];
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    stage_tile<D>(a, a.Y, slot, t0, t1, smem + stage * stage_bytes, &full[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    int stage = 0; uint32_t phase = 0;
+    const int tok_per_warp = TT / ST_CONSUMER_WARPS;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
+        const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
+        const TileRows r = tile_rows(a, t0, t1);
+        float gsum[N * 8];
+#pragma unroll
+        for (int i = 0; i < N * 8; ++i) gsum[i] = 0.f;
+        for (int jk = 0; jk < a.topk; ++jk) {
+            const int item = b * a.topk + jk;
+            const int slot = a.inv_perm[item];
+            const float g = a.gate ? a.gate[item] : 1.0f;
+            mbar_wait(&full[stage], phase);
+            const uint8_t* st = smem + stage * stage_bytes;
+            for (int k = 0; k < tok_per_warp; ++k) {
+                const int p = t0 + warp * tok_per_warp + k;
+                if (p >= t1) break;
+                const float4 bt4 = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+                const float bt[4] = {bt4.x * g, bt4.y * g, bt4.z * g, bt4.w * g};
+                float o[N * 8];
+#pragma unroll
+                for (int i = 0; i < N * 8; ++i) o[i] = 0.f;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                    const uint8_t* ra = st + static_cast<size_t>(a.cap_off[s] + L.i0 - r.i_lo[s]) * D * 2;
+                    float ya[N * 8];
+                    lds_row_x8<N>(ra, lane, ya);
+                    if (L.i1 != L.i0 && L.lam != 0.f) {
+                        float yb[N * 8];
+                        lds_row_x8<N>(ra + D * 2, lane, yb);
+                        const float c0 = bt[s] * (1.0f - L.lam), c1 = bt[s] * L.lam;
+#pragma unroll
+                        for (int i = 0; i < N * 8; ++i) o[i] = fmaf(c0, ya[i], fmaf(c1, yb[i], o[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N * 8; ++i) o[i] = fmaf(bt[s], ya[i], o[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < N * 8; ++i) gsum[i] += o[i];
+                OutT* orow = static_cast<OutT*>(a.out) + (static_cast<size_t>(b) * a.P + p) * D;
+                if (jk > 0) {   // top-k extension: add onto the previous choice's contribution (same thread wrote it)
+                    float prev[N * 8];
+                    load_row_x8<N, OutT>(orow, lane, prev);
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) o[i] += prev[i];
+                }
+                store_row_x8<N, OutT>(orow, lane, o);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        // deterministic partial of the global mean: one [D] vector per (image, tile)
+#pragma unroll
+        for (int t = 0; t < N; ++t)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_g[warp * D + 8 * (lane + 32 * t) + i] = gsum[8 * t + i];
+        named_bar_sync(1, ST_CONSUMER_WARPS * 32);
+        for (int d = threadIdx.x; d < D; d += ST_CONSUMER_WARPS * 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < ST_CONSUMER_WARPS; ++ww) acc += s_g[ww * D + d];
+            a.gpart[(static_cast<size_t>(b) * a.nblk + tt) * D + d] = acc;
+        }
+        named_bar_sync(1, ST_CONSUMER_WARPS * 32);
+    }
+}
+
+// ---- backward pass A: dbeta_s = <dF, interp(Y_s)>, then the softmax-over-scales backward -> dlogit.
+// Work item = (image, tile, top-k choice); stage = Y rows of the tile [+ the dlocal rows of the tile].
+template <int D, typename OutT, int STAGES>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+combine_bwd_logit_staged_kernel(const CombineArgs a) {
+    constexpr int N = D / 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int TT = a.tile_tokens;
+    const size_t y_bytes = static_cast<size_t>(a.cap_total) * D * 2;
+    const size_t df_bytes = a.dlocal ? static_cast<size_t>(TT) * D * sizeof(OutT) : 0;
+    const size_t stage_bytes = y_bytes + df_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int total = a.B * a.tiles_per_img;
+    if (warp == ST_CONSUMER_WARPS) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
+                const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
+                for (int jk = 0; jk < a.topk; ++jk) {
+                    const int slot = a.inv_perm[b * a.topk + jk];
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* dst = smem + stage * stage_bytes;
+                    const uint32_t extra = a.dlocal ? static_cast<uint32_t>(t1 - t0) * D * sizeof(OutT) : 0u;
+                    stage_tile<D>(a, a.Y, slot, t0, t1, dst, &full[stage], extra);
+                    if (a.dlocal)
+                        bulk_load_1d(dst + y_bytes, static_cast<const OutT*>(a.dlocal) + (static_cast<size_t>(b) * a.P + t0) * D, extra,
+                                     &full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    int stage = 0; uint32_t phase = 0;
+    const int tok_per_warp = TT / ST_CONSUMER_WARPS;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
+        const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
+        const TileRows r = tile_rows(a, t0, t1);
+        float dg[N * 8];
+        load_dglobal<N, D>(a, b, lane, dg);
+        for (int jk = 0; jk < a.topk; ++jk) {
+            const int item = b * a.topk + jk;
+            const int slot = a.inv_perm[item];
+            const float g = a.gate ? a.gate[item] : 1.0f;
+            float dgate_acc = 0.f;
+            mbar_wait(&full[stage], phase);
+            const uint8_t* st = smem + stage * stage_bytes;
+            for (int k = 0; k < tok_per_warp; ++k) {
+                const int p = t0 + warp * tok_per_warp + k;
+                if (p >= t1) break;
+                float df[N * 8];
+                if (a.dlocal) {
+                    const OutT* drow = reinterpret_cast<const OutT*>(st + y_bytes) + static_cast<size_t>(p - t0) * D;
+                    load_row_x8<N, OutT>(drow, lane, df);      // generic load from shared memory
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) df[i] += dg[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N * 8; ++i) df[i] = dg[i];
+                }
+                float dbeta[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                    const uint8_t* ra = st + static_cast<size_t>(a.cap_off[s] + L.i0 - r.i_lo[s]) * D * 2;
+                    float ya[N * 8];
+                    lds_row_x8<N>(ra, lane, ya);
+                    float acc = 0.f;
+                    if (L.i1 != L.i0 && L.lam != 0.f) {
+                        float yb[N * 8];
+                        lds_row_x8<N>(ra + D * 2, lane, yb);
+                        const float l0 = 1.0f - L.lam;
+#pragma unroll
+                        for (int i = 0; i < N * 8; ++i) acc = fmaf(df[i], l0 * ya[i] + L.lam * yb[i], acc);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N * 8; ++i) acc = fmaf(df[i], ya[i], acc);
+                    }
+                    dbeta[s] = warp_sum(acc);
+                }
+                const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+                const float dot = bt.x * dbeta[0] + bt.y * dbeta[1] + bt.z * dbeta[2] + bt.w * dbeta[3];
+                dgate_acc += dot;
+                if (lane == 0)
+                    *reinterpret_cast<float4*>(a.dlogit + (static_cast<size_t>(slot) * a.P + p) * 4) =
+                        make_float4(g * bt.x * (dbeta[0] - dot), g * bt.y * (dbeta[1] - dot), g * bt.z * (dbeta[2] - dot),
+                                    g * bt.w * (dbeta[3] - dot));
+            }
+            if (a.dgate && lane == 0) atomicAdd(a.dgate + item, dgate_acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
 // Per-lane token scalars for the token-centric backward: lane t keeps the value of tokens
 // p_lo + t and p_lo + 32 + t (a run plus its halo spans at most 64 tokens); the loop reads
 // them back with one shuffle instead of a dependent global load per token.
@@ -773,6 +1134,8 @@ MM_DEVINL float4 token_dlogit(const CombineArgs& a, int slot, int p, float g, fl
     dot_out = 0.f;
     if (p < 0 || p >= a.P) return make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t tok = static_cast<size_t>(slot) * a.P + p;
+    if (!a.dlogit_is_halves)     // finished dlogit (gate already applied) written by combine_bwd_logit_staged_kernel
+        return *reinterpret_cast<const float4*>(a.dlogit + tok * 4);
     const float4 bt = *reinterpret_cast<const float4*>(a.beta + tok * 4);
     const float4 h0 = *reinterpret_cast<const float4*>(a.dlogit + tok * 8);
     const float4 h1 = *reinterpret_cast<const float4*>(a.dlogit + tok * 8 + 4);
@@ -959,7 +1322,7 @@ combine_bwd_z_kernel(const CombineArgs a) {
         float dotA, dotB;
         const float4 dlA = token_dlogit(a, slot, p_base + lane, g, dotA);
         const float4 dlB = token_dlogit(a, slot, p_base + 32 + lane, g, dotB);
-        if (a.dgate) {
+        if (a.dgate && a.dlogit_is_halves) {
             const int pa = p_base + lane, pb = p_base + 32 + lane;
             float dsum = ((pa >= t0 && pa < t0 + RUN_TOKENS) ? dotA : 0.f) + ((pb >= t0 && pb < t0 + RUN_TOKENS) ? dotB : 0.f);
             dsum = warp_sum(dsum);
@@ -1149,7 +1512,75 @@ static int fill_common(CombineArgs& a, int B, int topk, int P, const int32_t* Ps
         case 1024: if (OUT_F32) KERNEL<1024, float><<<GRID, 256, 0, ST>>>(ARGS); else KERNEL<1024, __nv_bfloat16><<<GRID, 256, 0, ST>>>(ARGS); break; \
     }
 
-extern "C" int mm_combine_num_token_blocks(int P) { return (P + CB_TOKENS_PER_BLOCK - 1) / CB_TOKENS_PER_BLOCK; }
+// global-mean partial blocks per image the forward needs room for (one per 32-token tile)
+extern "C" int mm_combine_num_token_blocks(int P) { return (P + RUN_TOKENS - 1) / RUN_TOKENS; }
+
+// tile geometry of the TMA-staged kernels; returns the bytes of one stage of a [rows, W] bf16 matrix per W element
+static void setup_tiles(CombineArgs& a, int TT) {
+    a.tile_tokens = TT;
+    a.tiles_per_img = (a.P + TT - 1) / TT;
+    int off = 0;
+    for (int s = 0; s < 4; ++s) {
+        a.cap[s] = static_cast<int>((static_cast<long long>(TT) * a.Ps[s] + a.P - 1) / a.P) + 3;
+        a.cap_off[s] = off;
+        off += a.cap[s];
+    }
+    a.cap_total = off;
+}
+constexpr size_t ST_SMEM_LIMIT = 227 * 1024;
+template <typename K>
+static int opt_in_smem(K kern, size_t bytes, const char* what) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) {
+        mm::set_error("%s: cannot opt in to %zu B of shared memory (%s)", what, bytes, cudaGetErrorString(e));
+        return MM_ERR_CUDA;
+    }
+    return MM_OK;
+}
+template <int D>
+static int launch_logits_staged(const CombineArgs& a, cudaStream_t st) {
+    constexpr int STAGES = 4;
+    const size_t smem = STAGES * static_cast<size_t>(a.cap_total) * (D / 2) * 2 + 2 * STAGES * 8 + 128;
+    if (smem > ST_SMEM_LIMIT) return 1;
+    auto kern = combine_logits_staged_kernel<D, STAGES>;
+    if (int rc = opt_in_smem(kern, smem, "combine_logits")) return rc;
+    const int total = a.n_items * a.tiles_per_img;
+    kern<<<total < mm::sm_count() ? total : mm::sm_count(), ST_THREADS, smem, st>>>(a);
+    mm::note_launches(1);
+    return MM_OK;
+}
+template <int D, typename OutT>
+static int launch_out_staged(const CombineArgs& a, cudaStream_t st) {
+    constexpr int STAGES = 2;
+    const size_t smem = STAGES * static_cast<size_t>(a.cap_total) * D * 2 + ST_CONSUMER_WARPS * D * 4 + 2 * STAGES * 8 + 128;
+    if (smem > ST_SMEM_LIMIT) return 1;
+    auto kern = combine_out_staged_kernel<D, OutT, STAGES>;
+    if (int rc = opt_in_smem(kern, smem, "combine_out")) return rc;
+    const int total = a.B * a.tiles_per_img;
+    kern<<<total < mm::sm_count() ? total : mm::sm_count(), ST_THREADS, smem, st>>>(a);
+    mm::note_launches(1);
+    return MM_OK;
+}
+template <int D, typename OutT>
+static int launch_bwd_logit_staged(const CombineArgs& a, cudaStream_t st) {
+    constexpr int STAGES = 2;
+    const size_t stage = static_cast<size_t>(a.cap_total) * D * 2 + (a.dlocal ? static_cast<size_t>(a.tile_tokens) * D * sizeof(OutT) : 0);
+    const size_t smem = STAGES * stage + 2 * STAGES * 8 + 128;
+    if (smem > ST_SMEM_LIMIT) return 1;
+    auto kern = combine_bwd_logit_staged_kernel<D, OutT, STAGES>;
+    if (int rc = opt_in_smem(kern, smem, "combine_bwd_logit")) return rc;
+    const int total = a.B * a.tiles_per_img;
+    kern<<<total < mm::sm_count() ? total : mm::sm_count(), ST_THREADS, smem, st>>>(a);
+    mm::note_launches(1);
+    return MM_OK;
+}
+#define MM_STAGED_D(D, F32, FN, ARGS, ST, RC)                                                            \
+    switch (D) {                                                                                         \
+        case 256: RC = F32 ? FN<256, float>(ARGS, ST) : FN<256, __nv_bfloat16>(ARGS, ST); break;          \
+        case 512: RC = F32 ? FN<512, float>(ARGS, ST) : FN<512, __nv_bfloat16>(ARGS, ST); break;          \
+        case 768: RC = F32 ? FN<768, float>(ARGS, ST) : FN<768, __nv_bfloat16>(ARGS, ST); break;          \
+        case 1024: RC = F32 ? FN<1024, float>(ARGS, ST) : FN<1024, __nv_bfloat16>(ARGS, ST); break;       \
+    }
 extern "C" int mm_combine_num_row_blocks(const int32_t* Ps) {
     return (Ps[0] + Ps[1] + Ps[2] + Ps[3] + CB_ROWS_PER_BLOCK - 1) / CB_ROWS_PER_BLOCK;
 }
@@ -1168,20 +1599,23 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     a.nblk = mm_combine_num_token_blocks(P);
     a.nruns = (P + RUN_TOKENS - 1) / RUN_TOKENS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (Ps[0] == P) {   // run-based kernels (finest scale at full resolution, as the reference's Swin stages are)
-        dim3 grid1((a.nruns + 7) / 8, a.n_items);
-        switch (D) {
-            case 256: combine_logits_kernel<256><<<grid1, 256, 0, st>>>(a); break;
-            case 512: combine_logits_kernel<512><<<grid1, 256, 0, st>>>(a); break;
-            case 768: combine_logits_kernel<768><<<grid1, 256, 0, st>>>(a); break;
-            case 1024: combine_logits_kernel<1024><<<grid1, 256, 0, st>>>(a); break;
-        }
-        mm::note_launches(1);
-        a.nblk = (a.nruns + OUT_RUNS_PER_BLOCK - 1) / OUT_RUNS_PER_BLOCK;    // <= mm_combine_num_token_blocks(P)
-        dim3 grid2(a.nblk, B);
-        MM_DISPATCH_D(D, out_f32, combine_out_kernel, grid2, st, a)
-        mm::note_launches(1);
-    } else {
+    // TMA-staged persistent kernels (any scale ratio); the direct-load kernel remains for shapes whose tile does not fit
+    setup_tiles(a, 32);
+    int staged = 1;
+    switch (D) {
+        case 256: staged = launch_logits_staged<256>(a, st); break;
+        case 512: staged = launch_logits_staged<512>(a, st); break;
+        case 768: staged = launch_logits_staged<768>(a, st); break;
+        case 1024: staged = launch_logits_staged<1024>(a, st); break;
+    }
+    if (staged < 0) return staged;
+    if (staged == 0) {
+        a.nblk = a.tiles_per_img;
+        MM_STAGED_D(D, out_f32, launch_out_staged, a, st, staged)
+        if (staged < 0) return staged;
+    }
+    if (staged != 0) {
+        a.nblk = (P + CB_TOKENS_PER_BLOCK - 1) / CB_TOKENS_PER_BLOCK;
         dim3 grid(a.nblk, B);
         MM_DISPATCH_D(D, out_f32, combine_fwd_kernel, grid, st, a)
         mm::note_launches(1);
@@ -1258,9 +1692,17 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     }
     if (fast) {
         {
-            dim3 grid((a.nruns + OUT_RUNS_PER_BLOCK - 1) / OUT_RUNS_PER_BLOCK, B);
-            MM_DISPATCH_D(D, dlocal_f32, combine_bwd_dbeta_kernel, grid, st, a)
-            mm::note_launches(1);
+            setup_tiles(a, 16);
+            a.dlogit_is_halves = 0;
+            int staged = 1;
+            MM_STAGED_D(D, dlocal_f32, launch_bwd_logit_staged, a, st, staged)
+            if (staged < 0) return staged;
+            if (staged != 0) {   // tile does not fit in shared memory: run-based direct-load kernel (column-half partial dbeta)
+                a.dlogit_is_halves = 1;
+                dim3 grid((a.nruns + OUT_RUNS_PER_BLOCK - 1) / OUT_RUNS_PER_BLOCK, B);
+                MM_DISPATCH_D(D, dlocal_f32, combine_bwd_dbeta_kernel, grid, st, a)
+                mm::note_launches(1);
+            }
         }
         {
             dim3 grid((2 * a.nruns + 7) / 8, a.n_items);

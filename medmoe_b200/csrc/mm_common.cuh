@@ -141,6 +141,15 @@ MM_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): 16-byte aligned, size multiple of 16.
+MM_DEVINL void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// named barrier among a subset of the CTA's warps
+MM_DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // 2-D tile store smem -> global (bulk async group); out-of-bounds rows/cols are clipped by the tensor map.
 MM_DEVINL void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
