@@ -1028,6 +1028,10 @@ combine_bwd_logit_staged_kernel(const CombineArgs a) {
     }
 }
 
+}  // namespace mm
+#include "combine_staged.cuh"
+namespace mm {
+
 // Per-lane token scalars for the token-centric backward: lane t keeps the value of tokens
 // p_lo + t and p_lo + 32 + t (a run plus its halo spans at most 64 tokens); the loop reads
 // them back with one shuffle instead of a dependent global load per token.
@@ -1600,18 +1604,18 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     a.nruns = (P + RUN_TOKENS - 1) / RUN_TOKENS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // TMA-staged persistent kernels (any scale ratio); the direct-load kernel remains for shapes whose tile does not fit
-    setup_tiles(a, 32);
+    sg_setup_tiles(a, 32);
     int staged = 1;
     switch (D) {
-        case 256: staged = launch_logits_staged<256>(a, st); break;
-        case 512: staged = launch_logits_staged<512>(a, st); break;
-        case 768: staged = launch_logits_staged<768>(a, st); break;
-        case 1024: staged = launch_logits_staged<1024>(a, st); break;
+        case 256: staged = sg_launch_logits<256>(a, st); break;
+        case 512: staged = sg_launch_logits<512>(a, st); break;
+        case 768: staged = sg_launch_logits<768>(a, st); break;
+        case 1024: staged = sg_launch_logits<1024>(a, st); break;
     }
     if (staged < 0) return staged;
     if (staged == 0) {
         a.nblk = a.tiles_per_img;
-        MM_STAGED_D(D, out_f32, launch_out_staged, a, st, staged)
+        MM_STAGED_D(D, out_f32, sg_launch_out, a, st, staged)
         if (staged < 0) return staged;
     }
     if (staged != 0) {
@@ -1692,10 +1696,10 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     }
     if (fast) {
         {
-            setup_tiles(a, 16);
-            a.dlogit_is_halves = 0;
+            sg_setup_tiles(a, 16);
+            a.dlogit_is_halves = 1;
             int staged = 1;
-            MM_STAGED_D(D, dlocal_f32, launch_bwd_logit_staged, a, st, staged)
+            MM_STAGED_D(D, dlocal_f32, sg_launch_bwd_dbeta, a, st, staged)
             if (staged < 0) return staged;
             if (staged != 0) {   // tile does not fit in shared memory: run-based direct-load kernel (column-half partial dbeta)
                 a.dlogit_is_halves = 1;
