@@ -41,6 +41,10 @@ int mm_abi_version(void);
 int mm_device_sm_count(void);
 /* kernels launched through this library since it was loaded (bench evidence). */
 long long mm_launch_count(void);
+/* optional per-kernel CUDA-event timing inside the composite entry points (bench.py): enable, run, collect
+ * "name calls total_ms" lines (mm_trace_collect synchronises the device; returns bytes written). */
+void mm_trace_enable(int on);
+int mm_trace_collect(char* buf, int len);
 
 /* ---- (1) router gate: softmax + top-k -------------------------------------------------
  * replaces src/models/components/swin.py:98-100 (router MLP, softmax, argmax).

@@ -21,6 +21,8 @@ SIGNATURES = {
     "mm_abi_version": (c_int, []),
     "mm_device_sm_count": (c_int, []),
     "mm_launch_count": (c_ll, []),
+    "mm_trace_enable": (None, [c_int]),
+    "mm_trace_collect": (c_int, [C.c_char_p, c_int]),
     "mm_router_topk": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mm_router_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp]),
@@ -56,7 +58,7 @@ SIGNATURES = {
 }
 
 # entry points that return a plain value, not an mm_status
-_VALUE_FUNCS = {"mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
+_VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_gloria_workspace_floats"}
 
 
@@ -108,6 +110,17 @@ class EventProfiler:
 
 
 PROFILER = None
+
+
+def trace_collect():
+    """name -> (calls, total_ms) of the kernels traced inside composite C entry points since mm_trace_enable(1)."""
+    buf = C.create_string_buffer(1 << 16)
+    n = load().mm_trace_collect(buf, len(buf))
+    out = {}
+    for line in buf.raw[:n].decode().splitlines():
+        name, calls, ms = line.split()
+        out[name] = (int(calls), float(ms))
+    return out
 
 
 def call(name: str, *args, label: str = None):

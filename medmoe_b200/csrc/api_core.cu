@@ -7,7 +7,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace mm {
 
@@ -15,6 +18,20 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct TraceMark { std::string name; cudaEvent_t ev; };
+static std::atomic<bool> g_trace{false};
+static std::mutex g_trace_mu;
+static std::vector<TraceMark> g_marks;
+
+void trace_mark(const char* name, cudaStream_t st) {
+    if (!g_trace.load(std::memory_order_relaxed)) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_marks.push_back({name, ev});
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -164,6 +181,37 @@ extern "C" int mm_abi_version(void) { return 1; }
 extern "C" long long mm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int mm_device_sm_count(void) { return sm_count(); }
+
+extern "C" void mm_trace_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    for (auto& m : g_marks) cudaEventDestroy(m.ev);
+    g_marks.clear();
+    g_trace.store(on != 0);
+}
+
+// Synchronises the device and writes "name calls total_ms\n" lines for every traced kernel into buf.
+extern "C" int mm_trace_collect(char* buf, int len) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    std::map<std::string, std::pair<int, double>> acc;
+    for (size_t i = 1; i < g_marks.size(); ++i) {
+        if (g_marks[i].name == "begin") continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) continue;
+        auto& a = acc[g_marks[i].name];
+        a.first += 1;
+        a.second += ms;
+    }
+    int off = 0;
+    for (auto& kv : acc) {
+        int n = snprintf(buf + off, off < len ? len - off : 0, "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        if (n < 0 || off + n >= len) break;
+        off += n;
+    }
+    for (auto& m : g_marks) cudaEventDestroy(m.ev);
+    g_marks.clear();
+    return off;
+}
 
 // C[rows, N] = epi(A[rows, K] * W[e][N, K]^T) over 128-row tiles; see include/medmoe_b200.h.
 extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,

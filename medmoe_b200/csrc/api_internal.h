@@ -17,6 +17,9 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 int sm_count();
 // number of kernels launched through the C-ABI since load (bench.py's gpu_launches evidence)
 void note_launches(int n);
+// optional per-kernel timing inside composite entry points: one CUDA event per mark; the time between two
+// consecutive marks on a stream is attributed to the later mark's name ("begin" restarts the chain)
+void trace_mark(const char* name, cudaStream_t st);
 }  // namespace mm
 
 #define MM_REQUIRE(cond, code, msg)        \

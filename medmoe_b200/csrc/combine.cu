@@ -1605,6 +1605,7 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // TMA-staged persistent kernels (any scale ratio); the direct-load kernel remains for shapes whose tile does not fit
     sg_setup_tiles(a, 32);
+    mm::trace_mark("begin", st);
     int staged = 1;
     switch (D) {
         case 256: staged = sg_launch_logits<256>(a, st); break;
@@ -1614,9 +1615,11 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     }
     if (staged < 0) return staged;
     if (staged == 0) {
+        mm::trace_mark("combine_fwd.logits", st);
         a.nblk = a.tiles_per_img;
         MM_STAGED_D(D, out_f32, sg_launch_out, a, st, staged)
         if (staged < 0) return staged;
+        if (staged == 0) mm::trace_mark("combine_fwd.out", st);
     }
     if (staged != 0) {
         a.nblk = (P + CB_TOKENS_PER_BLOCK - 1) / CB_TOKENS_PER_BLOCK;
@@ -1628,6 +1631,7 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     if (rc) return rc;
     global_mean_kernel<<<dim3((D + 255) / 256, B), 256, 0, st>>>(gpart, a.nblk, D, 1.0f / static_cast<float>(P), global_feat);
     mm::note_launches(1);
+    mm::trace_mark("combine_fwd.global_mean", st);
     return mm_check_launch("mm_interp_softmax_combine_fwd(global mean)");
 }
 
@@ -1698,6 +1702,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
         {
             sg_setup_tiles(a, 16);
             a.dlogit_is_halves = 1;
+            mm::trace_mark("begin", st);
             int staged = 1;
             MM_STAGED_D(D, dlocal_f32, sg_launch_bwd_dbeta, a, st, staged)
             if (staged < 0) return staged;
@@ -1710,8 +1715,10 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
         }
         {
             dim3 grid((2 * a.nruns + 7) / 8, a.n_items);
+            mm::trace_mark("combine_bwd.dbeta", st);
             MM_DISPATCH_D(D, dlocal_f32, combine_bwd_u_kernel, grid, st, a)
             mm::note_launches(1);
+            mm::trace_mark("combine_bwd.dUT", st);
         }
         dim3 gridz(a.nrb, a.n_items + K);
         switch (D) {
@@ -1721,6 +1728,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
             case 1024: combine_bwd_z_kernel<1024><<<gridz, 256, 0, st>>>(a); break;
         }
         mm::note_launches(1);
+        mm::trace_mark("combine_bwd.dZ", st);
         for (int s = 1; s < 4; ++s) {
             if (a.mode[s] != SCALE_MOMENT) continue;
             dim3 gridf((a.Ps[s] + 7) / 8, a.n_items);
@@ -1732,6 +1740,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
             }
             mm::note_launches(1);
         }
+        mm::trace_mark("combine_bwd.finalize", st);
         rc = mm_check_launch("mm_interp_softmax_combine_bwd(token-centric)");
         if (rc) return rc;
     } else {
@@ -1744,5 +1753,6 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     const int C = 2 * (D / 2) + 1;
     expert_reduce_kernel<<<dim3((C + 255) / 256, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
     mm::note_launches(1);
+    mm::trace_mark("combine_bwd.expert_reduce", st);
     return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");
 }

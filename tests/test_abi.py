@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_decls():
     h = open(os.path.join(ROOT, "include", "medmoe_b200.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    return re.findall(r"(?:const char\*|int|long long)\s+(mm_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
+    return re.findall(r"(?:const char\*|int|long long|void)\s+(mm_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
 
 
 def test_library_loads_and_exports_every_declared_symbol():
@@ -37,7 +37,7 @@ def test_ctypes_signatures_match_header():
         assert len(params) == len(sig), f"{name}: header has {len(params)} params, ctypes {len(sig)}"
         for p, t in zip(params, sig):
             if "*" in p:
-                assert t is ctypes.c_void_p, f"{name}: {p}"
+                assert t in (ctypes.c_void_p, ctypes.c_char_p), f"{name}: {p}"
             else:
                 base = re.sub(r"\s+\w+$", "", p).replace("const ", "").strip()
                 assert t is kinds[base], f"{name}: {p} vs {t}"

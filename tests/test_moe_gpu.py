@@ -262,3 +262,34 @@ def test_non_integer_scale_ratio_uses_generic_backward():
     moe = _module_from(params, K, hidden, D)
     grads = _check_against(moe, feats, sw, ref_out, ref_grads, cg, cl, labels)
     _check_param_grads(grads, lambda k: pgrads[k], set(ref_out["top_expert"].tolist()), TIGHT)
+
+
+def test_top2_extension_vs_generalised_oracle():
+    """BASELINE config 4 routing: K = 8 experts, top-2 with renormalised gates (extension — parity is
+    against the generalised oracle, not the reference); 384^2 token geometry."""
+    K, hidden, D, Ps, B = 8, [96, 192, 384, 768], 768, [2304, 576, 144, 36], 4
+    params = mo.init_params(K, hidden, D, D, seed=41)
+    params = {k: (v.to(torch.bfloat16).float() if (".proj_convs." in k or ".attn_proj.0." in k) and k.endswith("weight") else v)
+              for k, v in params.items()}
+    torch.manual_seed(42)
+    feats = [torch.randn(B, p, d).to(torch.bfloat16).float() for p, d in zip(Ps, hidden)]
+    sw, cg = torch.randn(B, D), torch.randn(B, D)
+    cl = torch.randn(B, D, 48, 48) / 2304
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    sr = sw.clone().requires_grad_(True)
+    (gf, lf, probs), idx = mo.moe_forward_sparse(pr, fr, sr, topk=2)
+    ((gf * cg).sum() + (lf * cl).sum()).backward()
+
+    moe = _module_from(params, K, hidden, D, topk=2)
+    fg = [f.cuda().requires_grad_(True) for f in feats]
+    sg = sw.cuda().requires_grad_(True)
+    gf2, lf2, probs2 = moe(fg, sg)
+    assert torch.equal(moe.last_top_expert.long().cpu(), idx)
+    assert rel_err(gf2.cpu(), gf) < ACT_TOL and rel_err(lf2.cpu(), lf) < ACT_TOL
+    ((gf2 * cg.cuda()).sum() + (lf2 * cl.cuda()).sum()).backward()
+    for s in range(4):
+        _grad_ok(fg[s].grad.cpu(), fr[s].grad, TIGHT, f"d_feat{s}")
+    # with k > 1 the router is also trained through the gate weights
+    _grad_ok(sg.grad.cpu(), sr.grad, dict(grad=2e-2, cos=0.995), "d_swin_feat")
+    _grad_ok(moe.router[0].weight.grad.cpu(), pr["router.0.weight"].grad, dict(grad=2e-2, cos=0.995), "router.0.weight")

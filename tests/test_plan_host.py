@@ -1,0 +1,58 @@
+"""CPU: host-side dispatch logic (medmoe_b200.plan) — static row layout and the pure-Python
+restatement of mm_dispatch_build that the GPU test compares the kernel against bit for bit."""
+import random
+
+from medmoe_b200 import plan as mmplan
+
+
+def _check(n_items, K, P, seed, topk=1):
+    rnd = random.Random(seed)
+    experts = [rnd.randrange(K) for _ in range(n_items * topk)]
+    lay = mmplan.make_layout(n_items, topk, K, P)
+    ref = mmplan.reference_plan(experts, lay)
+    n = lay.n_items
+    assert sorted(ref["perm"]) == list(range(n)) and all(ref["inv_perm"][ref["perm"][s]] == s for s in range(n))
+    # stable counting sort: slots of one expert keep item order
+    for e in range(K):
+        items = [ref["perm"][s] for s in range(ref["offsets"][e], ref["offsets"][e + 1])]
+        assert items == sorted(items) and all(experts[i] == e for i in items)
+    for s in range(lay.S):
+        assert lay.region_base[s] % 128 == 0 and lay.region_rows[s] % 128 == 0
+        end_prev = lay.region_base[s]
+        for e in range(K):
+            st = ref["seg_start"][s][e]
+            assert st % 128 == 0 and st >= end_prev
+            end_prev = st + ref["counts"][e] * P[s]
+        assert end_prev <= lay.region_base[s] + lay.region_rows[s]
+        # every row of every slot is covered by exactly one owned tile entry with the right expert
+        for slot in range(n):
+            r0 = ref["slot_row"][s][slot]
+            for r in (r0, r0 + P[s] - 1):
+                e, valid = ref["tile_info"][r // 128]
+                assert e == ref["slot_expert"][slot] and r % 128 < valid
+    # wgrad chunks: disjoint, cover every owned tile once, never mix experts
+    covered = {}
+    for (e, first, cnt, s) in ref["chunks"]:
+        for t in range(first, first + cnt):
+            assert t not in covered
+            covered[t] = e
+    owned = {t: e for t, (e, v) in enumerate(ref["tile_info"]) if e >= 0}
+    assert covered == owned
+
+
+def test_reference_plan_invariants():
+    _check(7, 4, [49, 13, 5, 1], 0)
+    _check(64, 6, [196, 49, 16, 4], 1)
+    _check(300, 8, [3, 2, 1, 1], 2)
+    _check(5, 3, [300, 75, 19, 5], 3)
+    _check(16, 8, [64, 16, 4, 1], 4, topk=2)
+    _check(1, 1, [3136, 784, 196, 49], 5)
+
+
+def test_layout_capacity_is_routing_independent():
+    lay = mmplan.make_layout(256, 1, 4, [3136, 784, 196, 49])
+    assert lay.total_rows == sum(lay.region_rows) and lay.total_tiles == lay.total_rows // 128
+    # worst-case skew (everything to one expert) and perfectly balanced routing both fit
+    for experts in ([0] * 256, [i % 4 for i in range(256)]):
+        ref = mmplan.reference_plan(experts, lay)
+        assert len(ref["tile_info"]) == lay.total_tiles and len(ref["chunks"]) == lay.total_chunks
