@@ -255,10 +255,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def stage(msg):
+        if os.environ.get("MEDMOE_BENCH_VERBOSE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     resident = to_device(host, non_blocking=False)
+    stage("eager warm-up")
     for _ in range(args.warmup):
         step(resident)
     barrier()
+    stage("eager warm-up done")
 
     # ---------------- whole-step CUDA graph (routing is resolved on the device, so nothing syncs) ----------------
     graph, graph_loss, graph_err = None, None, None
@@ -272,10 +278,12 @@ def main():
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             launches0 = _lib.call("mm_launch_count")
+            stage("capturing")
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 graph_loss = step(resident)
             launches = _lib.call("mm_launch_count") - launches0
+            stage("captured")
         except Exception as ex:  # noqa: BLE001  (capture is an optimisation; the eager path is always valid)
             graph, graph_err = None, repr(ex)
             torch.cuda.synchronize()
@@ -294,6 +302,7 @@ def main():
     for _ in range(max(args.warmup, 50)):    # same count on every rank: each replay contains collectives
         run_resident()
     barrier()
+    stage("graph warm-up done")
 
     # ---------------- timed region 1: inputs resident in HBM ----------------
     if graph is None:
@@ -306,6 +315,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    stage(f"timed region 1 done: {ms:.3f} ms/step")
     if graph is None:
         launches = (_lib.call("mm_launch_count") - launches0) // args.steps
     clocks = sampler.stop() if rank == 0 else None
@@ -363,8 +373,10 @@ def main():
         torch.cuda.current_stream().synchronize()
         return float(host_loss)
 
+    stage("profiled pass done")
     e2e_loop(max(2, args.warmup))
     barrier()
+    stage("e2e warm-up done")
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = e2e_loop(args.steps)
