@@ -184,6 +184,10 @@ def main():
     if args.impl == "reference":
         return main_reference(args)
 
+    # stdout carries exactly one JSON line: everything libraries print (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch.distributed as dist
     import torch.nn.functional as F
 
@@ -472,9 +476,13 @@ def main():
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # captured NCCL work keeps the communicator busy at teardown: drop the graph first and never hang on exit
+        graph = None
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":
