@@ -100,15 +100,6 @@ int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, 
                          const float* bias, const void* aux, long long ld_aux, const void* gate, long long ld_gate,
                          void* out, long long ld_out, int out_f32, float* colsum, float out_scale, int flags,
                          void* stream);
-/* dY GEMM of the finest scale (region-0 rows == tokens) with its dUT term fused into the epilogue, so that slice of dUT
- * is never materialised:  out = (A W_e^T + beta_0(p) gate_w (dlocal[b,p,:] + dglobal[b,:]/P)) * [gate > 0].
- * seg_start0 [K]: first row of expert e relative to row 0 of A/out; dlocal_bf16 [B*P, N] bf16 or NULL; dglobal [B, N] fp32 or NULL. */
-int mm_grouped_gemm_dy_scale0(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
-                              long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, const void* gate,
-                              long long ld_gate, void* out, long long ld_out, float* colsum, const float* beta,
-                              const int32_t* perm, const int32_t* offsets, const int32_t* seg_start0, const float* item_gate,
-                              const void* dlocal_bf16, long long dlocal_rows, const float* dglobal, int P, int topk,
-                              void* stream);
 /* dW[e][N1, N2] += sum_{rows of expert e} A[row, N1]^T B[row, N2]  (fp32 red.add; caller zeroes dW). */
 int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
                           int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,
@@ -138,10 +129,7 @@ int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2,
                                   const int32_t* seg_start, const int32_t* offsets, const float* gate,
                                   const float* beta, const void* dlocal, int dlocal_f32, const float* dglobal,
                                   float* dlogit, float* dgate, void* dUT, void* dZ, float* part, float* dw2_db1_db2,
-                                  float* mom_u, float* mom_z, int force_generic, int skip_scale0, void* stream);
-/* 1 when the token-centric backward applies (integer scale ratios); skip_scale0 = 1 (finest-scale dUT fused into
- * mm_grouped_gemm_dy_scale0 instead of being written) is only valid then. */
-int mm_combine_bwd_is_token_centric(int P, const int32_t* Ps);
+                                  float* mom_u, float* mom_z, int force_generic, void* stream);
 
 /* ---- (5) global contrastive loss -------------------------------------------------------
  * GLORIA semantics: replaces GLORIAGlobalContrastiveLoss.forward, src/losses.py:766-794.

@@ -35,8 +35,6 @@ SIGNATURES = {
     "mm_transpose_cast_f32_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "mm_grouped_gemm_rows": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                      c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_int, c_vp, c_f, c_int, c_vp]),
-    "mm_grouped_gemm_dy_scale0": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int, c_vp, c_ll,
-                                          c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_vp]),
     "mm_grouped_gemm_wgrad": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                       c_vp, c_vp]),
     "mm_combine_num_token_blocks": (c_int, [c_int]),
@@ -47,8 +45,7 @@ SIGNATURES = {
                                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "mm_interp_softmax_combine_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
-                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
-    "mm_combine_bwd_is_token_centric": (c_int, [c_int, c_vp]),
+                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "mm_gloria_workspace_floats": (c_ll, [c_int]),
     "mm_gloria_global_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_vp, c_vp, c_vp]),
     "mm_gloria_global_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -62,7 +59,7 @@ SIGNATURES = {
 
 # entry points that return a plain value, not an mm_status
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
-                "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_is_token_centric", "mm_gloria_workspace_floats"}
+                "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_gloria_workspace_floats"}
 
 
 def library_path() -> Path:

@@ -213,23 +213,16 @@ extern "C" int mm_trace_collect(char* buf, int len) {
     return off;
 }
 
-struct S0Params {
-    const float* beta; const int32_t* perm; const int32_t* offsets; const int32_t* seg_start; const float* item_gate;
-    const float* dglobal; const void* dlocal; long long dlocal_rows; int P, topk;
-};
-
 // C[rows, N] = epi(A[rows, K] * W[e][N, K]^T) over 128-row tiles; see include/medmoe_b200.h.
-static int rows_gemm_impl(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
-                          long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
-                          const float* bias, const void* aux, long long ld_aux, const void* gate,
-                          long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
-                          float out_scale, int flags, const S0Params* s0, void* stream) {
+extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                                    long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
+                                    const float* bias, const void* aux, long long ld_aux, const void* gate,
+                                    long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
+                                    float out_scale, int flags, void* stream) {
     MM_REQUIRE(A && W && out, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: null operand");
     MM_REQUIRE(K > 0 && K % 8 == 0 && N > 0 && E > 0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: K must be a positive multiple of 8");
-    MM_REQUIRE(s0 || (aux == nullptr) == (gate == nullptr), MM_ERR_UNSUPPORTED,
+    MM_REQUIRE((aux == nullptr) == (gate == nullptr), MM_ERR_UNSUPPORTED,
                "mm_grouped_gemm_rows: aux and gate must be given together");
-    MM_REQUIRE(!s0 || (gate && tile_info && !out_f32 && s0->P % 32 == 0), MM_ERR_UNSUPPORTED,
-               "mm_grouped_gemm_dy_scale0: needs gate, tile_info, bf16 output and P % 32 == 0");
     MM_REQUIRE(!(aux && out_f32), MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: aux/gate need a bf16 output");
     const int BN = pick_bn_rows(N);
     MM_REQUIRE(BN != 0, MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: N must be a multiple of 32");
@@ -255,16 +248,10 @@ static int rows_gemm_impl(const void* A, long long a_rows, int K, long long lda,
                          CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(out)");
         if (rc) return rc;
     }
-    if (aux || s0) {
-        if (s0 && s0->dlocal) {   // aux tiles come from dlocal [B * P, N] in image order
-            rc = encode_tmap(&m.aux, s0->dlocal, static_cast<uint64_t>(N), static_cast<uint64_t>(s0->dlocal_rows),
-                             static_cast<uint64_t>(N), 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_dy_scale0(dlocal)");
-            if (rc) return rc;
-        } else if (aux) {
-            rc = encode_tmap(&m.aux, aux, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_aux), 32, 32,
-                             CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(aux)");
-            if (rc) return rc;
-        }
+    if (aux) {
+        rc = encode_tmap(&m.aux, aux, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_aux), 32, 32,
+                         CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(aux)");
+        if (rc) return rc;
         rc = encode_tmap(&m.gate, gate, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_gate), 32, 32,
                          CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(gate)");
         if (rc) return rc;
@@ -283,19 +270,11 @@ static int rows_gemm_impl(const void* A, long long a_rows, int K, long long lda,
     g.colsum = colsum;
     g.out_scale = out_scale;
     g.flags = flags;
-    g.s0_beta = nullptr; g.s0_perm = nullptr; g.s0_offsets = nullptr; g.s0_seg_start = nullptr; g.s0_item_gate = nullptr;
-    g.s0_dglobal = nullptr; g.s0_P = 1; g.s0_topk = 1; g.s0_has_dlocal = 0;
-    if (s0) {
-        g.s0_beta = s0->beta; g.s0_perm = s0->perm; g.s0_offsets = s0->offsets; g.s0_seg_start = s0->seg_start;
-        g.s0_item_gate = s0->item_gate; g.s0_dglobal = s0->dglobal; g.s0_P = s0->P; g.s0_topk = s0->topk;
-        g.s0_has_dlocal = s0->dlocal != nullptr;
-    }
-    const bool use_aux = aux != nullptr || s0 != nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MM_ROWS_CASE(bn)                                                                          \
     case bn:                                                                                      \
         if (out_f32) return launch_rows<bn, true, false>(m, g, st);                               \
-        return use_aux ? launch_rows<bn, false, true>(m, g, st) : launch_rows<bn, false, false>(m, g, st);
+        return aux ? launch_rows<bn, false, true>(m, g, st) : launch_rows<bn, false, false>(m, g, st);
     switch (BN) {
         MM_ROWS_CASE(256)
         MM_ROWS_CASE(192)
@@ -307,30 +286,6 @@ static int rows_gemm_impl(const void* A, long long a_rows, int K, long long lda,
 #undef MM_ROWS_CASE
     set_error("mm_grouped_gemm_rows: unreachable tile width %d", BN);
     return MM_ERR_UNSUPPORTED;
-}
-
-extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
-                                    long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
-                                    const float* bias, const void* aux, long long ld_aux, const void* gate,
-                                    long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
-                                    float out_scale, int flags, void* stream) {
-    return rows_gemm_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, M, bias, aux, ld_aux, gate,
-                          ld_gate, out, ld_out, out_f32, colsum, out_scale, flags, nullptr, stream);
-}
-
-// dY GEMM of the finest scale with its dUT term fused into the epilogue:
-//   out = (dZ W1 + beta_0(p) * gate_w * (dlocal[b, p, :] + dglobal[b, :] / P)) * [Y > 0]
-// rows of this launch are the region-0 rows (tokens); seg_start0[e] = first row of expert e relative to row 0 of A/out.
-extern "C" int mm_grouped_gemm_dy_scale0(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
-                                         long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
-                                         const void* gate, long long ld_gate, void* out, long long ld_out, float* colsum,
-                                         const float* beta, const int32_t* perm, const int32_t* offsets,
-                                         const int32_t* seg_start0, const float* item_gate, const void* dlocal_bf16,
-                                         long long dlocal_rows, const float* dglobal, int P, int topk, void* stream) {
-    MM_REQUIRE(beta && perm && offsets && seg_start0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_dy_scale0: null table");
-    S0Params s0{beta, perm, offsets, seg_start0, item_gate, dglobal, dlocal_bf16, dlocal_rows, P, topk};
-    return rows_gemm_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, nullptr, nullptr, 0, gate,
-                          ld_gate, out, ld_out, 0, colsum, 1.0f, EPI_ZERO_PAD, &s0, stream);
 }
 
 // dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e.

@@ -71,7 +71,6 @@ struct CombineArgs {
     int cap[4];                     // rows reserved per scale in a stage: ceil(TT * Ps / P) + 2
     int cap_off[4];                 // prefix sums of cap
     int cap_total;
-    int skip_scale0;                // the finest-scale slice of dUT is fused into the dY GEMM epilogue: do not write it
     int dlogit_is_halves;           // dlogit holds two column-half partial dbeta ([.., 2, 4]) instead of finished dlogit
     float* mom_u;                   // [n_items, nruns, 2, D]   zeroth / first moments of beta_s * dF per 32-token run
     float* mom_z;                   // [n_items, nruns, 2, D/2] same for dlogit_s * w2 * gate
@@ -1223,7 +1222,7 @@ combine_bwd_u_kernel(const CombineArgs a) {
         const int idx = p - p_lo;
         const float bt[4] = {lane_pick(bA.x, bB.x, idx), lane_pick(bA.y, bB.y, idx), lane_pick(bA.z, bB.z, idx),
                              lane_pick(bA.w, bB.w, idx)};
-        if (in_run && !a.skip_scale0) {   // scale 0: identity
+        if (in_run) {   // scale 0: identity
             float o[E];
 #pragma unroll
             for (int k = 0; k < E; ++k) o[k] = bt[0] * df[k];
@@ -1669,14 +1668,6 @@ static int classify_scales(CombineArgs& a) {
     return n_moment <= 1;
 }
 
-// 1 when the token-centric backward applies to these token counts (integer scale ratios, see classify_scales)
-extern "C" int mm_combine_bwd_is_token_centric(int P, const int32_t* Ps) {
-    CombineArgs a{};
-    a.P = P;
-    for (int s = 0; s < 4; ++s) a.Ps[s] = Ps[s];
-    return classify_scales(a);
-}
-
 extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
                                              const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,
                                              const int32_t* slot_expert, const int32_t* slot_row, const int32_t* counts,
@@ -1684,7 +1675,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
                                              const float* beta, const void* dlocal, int dlocal_f32, const float* dglobal,
                                              float* dlogit, float* dgate, void* dUT, void* dZ, float* part,
                                              float* dw2_db1_db2, float* mom_u, float* mom_z, int force_generic,
-                                             int skip_scale0, void* stream) {
+                                             void* stream) {
     CombineArgs a{};
     int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_bwd");
     if (rc) return rc;
@@ -1698,11 +1689,6 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     a.nblk = mm_combine_num_token_blocks(P);
     a.nruns = mm_combine_num_runs(P);
     const bool fast = !force_generic && mom_u && mom_z && classify_scales(a);
-    if (skip_scale0 && !fast) {
-        mm::set_error("mm_interp_softmax_combine_bwd: skip_scale0 needs the token-centric path (mm_combine_bwd_is_token_centric)");
-        return MM_ERR_UNSUPPORTED;
-    }
-    a.skip_scale0 = skip_scale0;
     a.nrb = fast ? (a.nruns + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK : mm_combine_num_row_blocks(Ps);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!fast) {

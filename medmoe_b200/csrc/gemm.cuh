@@ -48,29 +48,7 @@ struct RowsGemmArgs {
     float* colsum;           // [E, N] fp32, += column sums of the written tile (bias gradients) or nullptr
     float out_scale;         // multiplies the accumulator before bias (1.0 for the MoE path)
     int flags;
-    // "scale-0 fusion" of the dY GEMM (AUX kernels only, s0_beta != nullptr): the rows of this launch are the
-    // finest-scale tokens, whose dUT is beta_0(p) * gate_w * dF(p) with dF = dlocal[b, p, :] + dglobal[b, :] / P.
-    // The aux tile then comes from `dlocal` (image order, via tmAux) instead of a materialised dUT.
-    const float* s0_beta;        // [n_items, P, 4]
-    const int* s0_perm;          // [n_items] slot -> item
-    const int* s0_offsets;       // [K + 1] first slot of each expert
-    const int* s0_seg_start;     // [K] first row of each expert inside this launch's row space
-    const float* s0_item_gate;   // [n_items] or nullptr
-    const float* s0_dglobal;     // [B, N] fp32 or nullptr
-    int s0_P, s0_topk, s0_has_dlocal;
 };
-
-struct S0Token { int slot, b, p; };
-// token behind row (lt * 128 + r) of expert e's segment in a scale-0 launch
-MM_DEVINL S0Token s0_token(const RowsGemmArgs& a, int e, int lt, int r) {
-    const int seg_row = lt * TILE_M + r - a.s0_seg_start[e];
-    const int j = seg_row / a.s0_P;
-    S0Token t;
-    t.p = seg_row - j * a.s0_P;
-    t.slot = a.s0_offsets[e] + j;
-    t.b = a.s0_perm[t.slot] / a.s0_topk;
-    return t;
-}
 
 struct WgradArgs {
     const int4* chunks;      // [chunk] {expert, first_tile (global), num_tiles, 0}
@@ -212,18 +190,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         auto issue_in = [&](int w, int c, int slot) {   // lane 0 only
             const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
             const int row0 = lt * TILE_M + q * 32, col0 = nt * BN + c * 32;
-            int aux_row = row0;
-            bool load_aux = true;
-            if (a.s0_beta) {   // aux tile = dlocal rows of the warp's 32 tokens (one image: P % 32 == 0, segments 128-aligned)
-                const int2 ti = a.tile_info[a.tile_begin + lt];
-                load_aux = a.s0_has_dlocal && (q * 32 < ti.y);
-                if (load_aux) {
-                    const S0Token t = s0_token(a, ti.x, lt, q * 32);
-                    aux_row = t.b * a.s0_P + t.p;
-                }
-            }
-            mbar_expect_tx(&my_bar[slot], load_aux ? 2 * EPI_SLOT_BYTES : EPI_SLOT_BYTES);
-            if (load_aux) tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES, &tmAux, &my_bar[slot], col0, aux_row);
+            mbar_expect_tx(&my_bar[slot], 2 * EPI_SLOT_BYTES);
+            tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES, &tmAux, &my_bar[slot], col0, row0);
             tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES + EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
         };
 
@@ -245,18 +213,6 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long row = static_cast<long long>(lt) * TILE_M + r_in_tile;
             const bool row_valid = r_in_tile < valid;
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-            float s0_coef = 0.f;            // scale-0 fusion: beta_0(p) * gate weight of this row's token
-            const float* s0_dg = nullptr;   // dglobal row of this row's image
-            bool s0_aux = false;            // the warp's dlocal tile was loaded
-            if (AUX && a.s0_beta) {
-                s0_aux = a.s0_has_dlocal && (q * 32 < valid);
-                if (row_valid) {
-                    const S0Token t = s0_token(a, e, lt, r_in_tile);
-                    const int item = a.s0_perm[t.slot];
-                    s0_coef = a.s0_beta[(static_cast<size_t>(t.slot) * a.s0_P + t.p) * 4] * (a.s0_item_gate ? a.s0_item_gate[item] : 1.0f);
-                    if (a.s0_dglobal) s0_dg = a.s0_dglobal + static_cast<size_t>(t.b) * a.N;
-                }
-            }
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[32];
@@ -287,31 +243,12 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint8_t* gt = ax + EPI_SLOT_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
                         const uint4 g = *reinterpret_cast<const uint4*>(gt + epi_slot_off(lane, j));
-                        if (a.s0_beta) {
-                            // dUT of a finest-scale token, never materialised: beta_0 * gate * (dlocal + dglobal / P)
-                            float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            if (s0_aux) {
-                                const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
-                                d[0] = bf16lo(u.x); d[1] = bf16hi(u.x); d[2] = bf16lo(u.y); d[3] = bf16hi(u.y);
-                                d[4] = bf16lo(u.z); d[5] = bf16hi(u.z); d[6] = bf16lo(u.w); d[7] = bf16hi(u.w);
-                            }
-                            if (s0_dg) {
-                                const float inv_p = 1.0f / static_cast<float>(a.s0_P);
-                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(s0_dg + col0 + 8 * j));
-                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(s0_dg + col0 + 8 * j + 4));
-                                d[0] = fmaf(g0.x, inv_p, d[0]); d[1] = fmaf(g0.y, inv_p, d[1]); d[2] = fmaf(g0.z, inv_p, d[2]); d[3] = fmaf(g0.w, inv_p, d[3]);
-                                d[4] = fmaf(g1.x, inv_p, d[4]); d[5] = fmaf(g1.y, inv_p, d[5]); d[6] = fmaf(g1.z, inv_p, d[6]); d[7] = fmaf(g1.w, inv_p, d[7]);
-                            }
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) f[8 * j + t] = fmaf(s0_coef, d[t], f[8 * j + t]);
-                        } else {
-                            const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
-                            f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
-                            f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);
-                            f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
-                            f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
-                        }
+                        f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
+                        f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);
+                        f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
+                        f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
                         // gate holds ReLU outputs (>= 0): "> 0" is "bits != 0" on the bf16 payload.
                         if ((g.x & 0x0000ffffu) == 0) f[8 * j + 0] = 0.f;
                         if ((g.x & 0xffff0000u) == 0) f[8 * j + 1] = 0.f;

@@ -140,21 +140,13 @@ class _ExpertsFunction(torch.autograd.Function):
             dfused = dfused.contiguous()
         dglobal32 = dglobal.float().contiguous() if dglobal is not None else None
 
-        # the finest-scale slice of dUT (= beta_0 * dF, 75 % of the rows) is folded into the dY GEMM epilogue when the
-        # token-centric backward applies and the incoming gradient is bf16 (or absent)
-        fuse0 = (ops.combine_bwd_is_token_centric(layout) and layout.P[0] % 32 == 0 and
-                 (dfused is None or dfused.dtype == torch.bfloat16))
         dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
-                                                        ctx.gate_needs_grad, skip_scale0=fuse0)
+                                                        ctx.gate_needs_grad)
         # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT; column sums -> conv bias gradients
         W1T = ops.transpose_cast_bf16(W1_32.float()).view(E * D, H)          # [E, D, H]
         dbp = [torch.zeros(E, D, dtype=torch.float32, device=dev) for _ in range(S)]
         for s in range(S):
             r0, nr = layout.region_base[s], layout.region_rows[s]
-            if s == 0 and fuse0:
-                ops.gemm_dy_scale0(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], Y[r0:r0 + nr], dbp[s], plan, beta, gate_flat,
-                                   dfused, dglobal32, tag="dY.s0")
-                continue
             ops.gemm_rows(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
                           tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr], colsum=dbp[s],
                           flags=ops.EPI_ZERO_PAD, tag=f"dY.s{s}")

@@ -118,21 +118,6 @@ def gemm_rows(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, pl
     return out
 
 
-def gemm_dy_scale0(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, gate_rows: torch.Tensor, colsum, plan: DispatchPlan,
-                   beta, item_gate, dlocal, dglobal, tag: str = ""):
-    """Region-0 dY GEMM with the finest-scale dUT fused into the epilogue (see mm_grouped_gemm_dy_scale0)."""
-    lay = plan.layout
-    _need_cuda(A, W, out, gate_rows, beta)
-    E = W.shape[0] // N
-    assert lay.region_base[0] == 0
-    _lib.call("mm_grouped_gemm_dy_scale0", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(W), E, N, W.stride(0),
-              _P(plan.tile_info), lay.tile_base[0], lay.region_tiles[0], _P(gate_rows), gate_rows.stride(0),
-              _P(out), out.stride(0), _P(colsum), _P(beta), _P(plan.perm), _P(plan.offsets), _P(plan.seg_start),
-              _P(item_gate), _P(dlocal), lay.n_images * lay.P[0] if dlocal is not None else 0, _P(dglobal),
-              lay.P[0], lay.topk, _st(), label=f"{tag}:gemm_rows[K={A.shape[1]},N={N}]")
-    return out
-
-
 def gemm_wgrad(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, plan: DispatchPlan, chunk_begin: int,
                chunk_count: int, tile_base: int, tag: str = ""):
     """out[e] (+)= A_e^T B_e over the rows of expert e; out fp32 [E, N1, N2] must be pre-zeroed."""
@@ -160,12 +145,8 @@ def combine_fwd(Y, Z, w2, b2, plan: DispatchPlan, D: int, gate, out_dtype):
     return out, gfeat, beta
 
 
-def combine_bwd_is_token_centric(layout: RowLayout) -> bool:
-    return bool(_lib.call("mm_combine_bwd_is_token_centric", layout.P[0], _lib.host_i32(layout.P))) and not FORCE_GENERIC_COMBINE_BWD
-
-
 def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool,
-                force_generic: bool = False, skip_scale0: bool = False):
+                force_generic: bool = False):
     lay = plan.layout
     _need_cuda(Y, Z, w2, beta, dlocal, dglobal)
     B, P, K = lay.n_images, lay.P[0], lay.num_experts
@@ -186,7 +167,7 @@ def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dgloba
               _P(plan.perm), _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(plan.counts),
               _P(plan.seg_start), _P(plan.offsets), _P(gate), _P(beta), _P(dlocal), int(dl_f32), _P(dglobal),
               _P(dlogit), _P(dgate), _P(dUT), _P(dZ), _P(part), _P(red), _P(mom_u), _P(mom_z),
-              int(force_generic or FORCE_GENERIC_COMBINE_BWD), int(skip_scale0), _st())
+              int(force_generic or FORCE_GENERIC_COMBINE_BWD), _st())
     H = D // 2
     return dUT, dZ, red[:, :H], red[:, H:2 * H], red[:, 2 * H], dgate
 
