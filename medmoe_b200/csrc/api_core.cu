@@ -119,8 +119,8 @@ struct RowsMaps { CUtensorMap a, b, out, aux, gate; };
 
 template <int BN, bool OUT_F32, bool AUX>
 static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
-    // smem: pipeline stages + 16 KB output staging (+ 32 KB aux/gate staging) must fit 227 KB
-    constexpr int STAGES = AUX ? ((BN > 192) ? 3 : (BN > 128 ? 4 : 5)) : ((BN > 192) ? 4 : (BN > 128 ? 5 : 6));
+    // smem: pipeline stages + output staging (32 KB, or 16 KB + 64 KB aux/gate staging) must fit 227 KB
+    constexpr int STAGES = AUX ? ((BN > 128) ? 3 : 4) : ((BN > 192) ? 4 : (BN > 128 ? 4 : 5));
     using S = GemmSmem<BN, STAGES, AUX>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32, AUX>;
@@ -136,7 +136,7 @@ static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t
     const int work = args.tile_count * args.n_tiles;
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
-    kern<<<grid, 256, S::TOTAL, st>>>(m.a, m.b, m.out, m.aux, m.gate, args);
+    kern<<<grid, ROWS_THREADS, S::TOTAL, st>>>(m.a, m.b, m.out, m.aux, m.gate, args);
     note_launches(1);
     return check_launch("gemm_rows");
 }

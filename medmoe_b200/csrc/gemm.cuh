@@ -15,8 +15,10 @@
 //   gemm_wgrad_kernel  dW_e[i, j] = sum_m A[m, i] * B[m, j]             both operands MN-major
 //       reduction over the rows of expert e (split into chunks, fp32 red.add into dW).
 //
-// Roles per CTA (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+// warps 4.. = epilogue (TMEM lane quarter = warp_idx % 4).  gemm_rows runs EIGHT epilogue warps (384 threads):
+// two warps share a lane quarter and take the even / odd 32-column chunks, so every scheduler has two
+// epilogue warps to hide tcgen05.ld / LDS / shuffle latency behind each other.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -60,15 +62,18 @@ struct WgradArgs {
 };
 
 constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
+constexpr int EPI_WARPS = 8;               // epilogue warps of gemm_rows_kernel
+constexpr int ROWS_THREADS = (4 + EPI_WARPS) * 32;
 
 template <int BN, int STAGES, bool AUX = false>
 struct GemmSmem {
     static constexpr int A_BYTES = TILE_M * 64 * 2;                 // 16 KB: 128 rows x 64 bf16 (K-major) or 2 x (64 k-rows x 64 mn)
     static constexpr int B_BYTES = ((BN + 63) / 64) * 64 * 64 * 2;   // BN rounded up to 64-wide chunks
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_OUT_BYTES = 4 * 2 * EPI_SLOT_BYTES;                    // 4 warps x double buffer
-    static constexpr int EPI_IN_BYTES = AUX ? 4 * 2 * 2 * EPI_SLOT_BYTES : 0;       // x {aux, gate}
-    static constexpr int BAR_BYTES = (2 * STAGES + 4 + 8) * 8 + 16;
+    static constexpr int OUT_SLOTS = AUX ? 1 : 2;                                   // output staging slots per epilogue warp
+    static constexpr int EPI_OUT_BYTES = EPI_WARPS * OUT_SLOTS * EPI_SLOT_BYTES;
+    static constexpr int EPI_IN_BYTES = AUX ? EPI_WARPS * 2 * 2 * EPI_SLOT_BYTES : 0;   // double-buffered {aux, gate}
+    static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
 
@@ -80,7 +85,7 @@ MM_DEVINL uint32_t epi_slot_off(int r, int j) { return static_cast<uint32_t>(r *
 // gemm_rows_kernel
 // ------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool OUT_F32, bool AUX>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmGate, const RowsGemmArgs a) {
@@ -97,8 +102,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint64_t* inbar = tempty + 2;          // [4 warps][2 slots]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 8);
+    uint64_t* inbar = tempty + 2;          // [EPI_WARPS][2 slots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 2 * EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -111,8 +116,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
-        for (int s = 0; s < 8; ++s) mbar_init(&inbar[s], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EPI_WARPS); }
+        for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&inbar[s], 1);
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -171,11 +176,14 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp & 3;
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int ew = warp - 4;                // epilogue warp index
+        const int h = ew >> 2;                  // this warp takes chunks h, h + 2, ...
         constexpr int NCH = BN / 32;
-        uint8_t* my_out = sOut + q * 2 * EPI_SLOT_BYTES;
-        uint8_t* my_in = sIn + q * 4 * EPI_SLOT_BYTES;      // slot b: aux at b * 2 * SLOT, gate right after it
-        uint64_t* my_bar = inbar + q * 2;
+        constexpr int CSTEP = EPI_WARPS / 4;
+        uint8_t* my_out = sOut + ew * S::OUT_SLOTS * EPI_SLOT_BYTES;
+        uint8_t* my_in = sIn + ew * 4 * EPI_SLOT_BYTES;      // slot b: aux at b * 2 * SLOT, gate right after it
+        uint64_t* my_bar = inbar + ew * 2;
         int acc = 0; uint32_t acc_phase = 0;
         int oslot = 0;                 // staging slot for the next output chunk
         int islot = 0; uint32_t iphase[2] = {0, 0};
@@ -196,7 +204,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         };
 
         int w = next_valid(blockIdx.x);
-        if (AUX && w < total_work && lane == 0) issue_in(w, 0, 0);
+        if (AUX && w < total_work && lane == 0 && h < NCH) issue_in(w, h, 0);
         while (w < total_work) {
             const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
             int e = 0, valid = TILE_M;
@@ -214,13 +222,13 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool row_valid = r_in_tile < valid;
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
+            for (int c = h; c < NCH; c += CSTEP) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + c * 32, v);
-                if (AUX) {   // prefetch the next chunk's aux/gate into the other slot (its readers finished last iteration)
+                if (AUX) {   // prefetch this warp's next chunk's aux/gate into the other slot (its readers finished last iteration)
                     if (lane == 0) {
-                        if (c + 1 < NCH) issue_in(w, c + 1, islot ^ 1);
-                        else if (w_next < total_work) issue_in(w_next, 0, islot ^ 1);
+                        if (c + CSTEP < NCH) issue_in(w, c + CSTEP, islot ^ 1);
+                        else if (w_next < total_work) issue_in(w_next, h, islot ^ 1);
                     }
                 }
                 tmem_ld_wait();
@@ -277,8 +285,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     }
                 } else {
-                    // staging slot `oslot` is free once the store issued two chunks ago has read it
-                    if (lane == 0) tma_store_wait_read<1>();
+                    // staging slot `oslot` is free once the store that last used it has read it
+                    if (lane == 0) tma_store_wait_read<S::OUT_SLOTS - 1>();
                     __syncwarp();
                     uint8_t* so = my_out + oslot * EPI_SLOT_BYTES;
 #pragma unroll
@@ -296,7 +304,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_store_2d(&tmOut, so, col0, lt * TILE_M + q * 32);
                         tma_store_commit();
                     }
-                    oslot ^= 1;
+                    if (S::OUT_SLOTS == 2) oslot ^= 1;
                 }
                 if (a.colsum) {
                     const float cs = warp_colsum32(f, lane);
