@@ -145,12 +145,13 @@ template <int BN>
 static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const WgradArgs& args, cudaStream_t st) {
     constexpr int STAGES = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
     using S = GemmSmem<BN, STAGES>;
+    static_assert(S::WGRAD_TOTAL <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_wgrad_kernel<BN, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::WGRAD_TOTAL);
         if (e != cudaSuccess) {
-            set_error("gemm_wgrad: cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            set_error("gemm_wgrad: cannot opt in to %d B of shared memory (%s)", S::WGRAD_TOTAL, cudaGetErrorString(e));
             return MM_ERR_CUDA;
         }
         configured = true;
@@ -158,7 +159,7 @@ static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const Wgra
     const int work = args.chunk_count * args.n_i * args.n_j;
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
-    kern<<<grid, 256, S::TOTAL, st>>>(tA, tB, args);
+    kern<<<grid, 256, S::WGRAD_TOTAL, st>>>(tA, tB, args);
     note_launches(1);
     return check_launch("gemm_wgrad");
 }

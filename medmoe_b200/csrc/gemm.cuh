@@ -75,6 +75,7 @@ struct GemmSmem {
     static constexpr int EPI_IN_BYTES = AUX ? EPI_WARPS * 2 * 2 * EPI_SLOT_BYTES : 0;   // double-buffered {aux, gate}
     static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;   // + alignment slack
+    static constexpr int WGRAD_TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;      // the wgrad kernel has no staging slots
 };
 
 // 16-byte chunk j (0..3) of row r inside a 32-row x 64-byte staging slot written/read by TMA with
