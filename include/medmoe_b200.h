@@ -114,6 +114,7 @@ int mm_combine_num_token_blocks(int P);
 int mm_combine_num_row_blocks(const int32_t* Ps);
 int mm_combine_num_runs(int P);
 int mm_combine_num_part_blocks(int P, const int32_t* Ps);
+long long mm_combine_bwd_z_scratch_floats(int P, const int32_t* Ps, int D);   /* floats per item of `mom_z` */
 int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk, int P,
                                   const int32_t* Ps, int D, const int32_t* inv_perm, const int32_t* slot_expert,
                                   const int32_t* slot_row, const float* gate, float* beta, void* out, int out_f32,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "mm_combine_num_row_blocks": (c_int, [c_vp]),
     "mm_combine_num_runs": (c_int, [c_int]),
     "mm_combine_num_part_blocks": (c_int, [c_int, c_vp]),
+    "mm_combine_bwd_z_scratch_floats": (c_ll, [c_int, c_vp, c_int]),
     "mm_interp_softmax_combine_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "mm_interp_softmax_combine_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
@@ -59,7 +60,7 @@ SIGNATURES = {
 
 # entry points that return a plain value, not an mm_status
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
-                "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_gloria_workspace_floats"}
+                "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats"}
 
 
 def library_path() -> Path:

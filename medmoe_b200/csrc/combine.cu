@@ -71,6 +71,8 @@ struct CombineArgs {
     int cap[4];                     // rows reserved per scale in a stage: ceil(TT * Ps / P) + 2
     int cap_off[4];                 // prefix sums of cap
     int cap_total;
+    float* zscr;                    // scratch of the interval-prefix dZ path (combine_bwd_z.cuh), aliases mom_z
+    int z_rows_path;                // dZ comes from the interval-prefix kernels: finalize only writes dUT
     int dlogit_is_halves;           // dlogit holds two column-half partial dbeta ([.., 2, 4]) instead of finished dlogit
     float* mom_u;                   // [n_items, nruns, 2, D]   zeroth / first moments of beta_s * dF per 32-token run
     float* mom_z;                   // [n_items, nruns, 2, D/2] same for dlogit_s * w2 * gate
@@ -1430,6 +1432,10 @@ combine_bwd_z_kernel(const CombineArgs a) {
     }
 }
 
+}  // namespace mm
+#include "combine_bwd_z.cuh"
+namespace mm {
+
 // MOMENT scale: combine the runs of each native row's window.  grid = (ceil(Ps[s] / 8), n_items); warp = native row.
 template <int D>
 __global__ void __launch_bounds__(256)
@@ -1468,14 +1474,16 @@ combine_bwd_finalize_kernel(const CombineArgs a, int s) {
         load_row_x8<N, float>(mu + D, lane, m1);
 #pragma unroll
         for (int k = 0; k < N * 8; ++k) u[k] = fmaf(wa, m0[k], fmaf(slope, m1[k], u[k]));
-        float n0[NE * 4], n1[NE * 4];
-        load_row_f32x4<NE>(mz, lane, n0);
-        load_row_f32x4<NE>(mz + H, lane, n1);
+        if (!a.z_rows_path) {
+            float n0[NE * 4], n1[NE * 4];
+            load_row_f32x4<NE>(mz, lane, n0);
+            load_row_f32x4<NE>(mz + H, lane, n1);
 #pragma unroll
-        for (int k = 0; k < NE * 4; ++k) z[k] = fmaf(wa, n0[k], fmaf(slope, n1[k], z[k]));
+            for (int k = 0; k < NE * 4; ++k) z[k] = fmaf(wa, n0[k], fmaf(slope, n1[k], z[k]));
+        }
     }
     store_row_x8<N, __nv_bfloat16>(a.dUT + (base + i) * D, lane, u);
-    store_slab_bf16<NE>(a.dZ + (base + i) * H, lane, z);
+    if (!a.z_rows_path) store_slab_bf16<NE>(a.dZ + (base + i) * H, lane, z);
 }
 
 // out[e, c] = sum over the slots of expert e and their nrb blocks of part[slot, blk, c]; grid = (ceil(C/256), K)
@@ -1638,9 +1646,23 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
 extern "C" int mm_combine_num_runs(int P) { return (P + RUN_TOKENS - 1) / RUN_TOKENS; }
 // number of per-slot partial blocks `part` must hold (max over the two backward paths)
 extern "C" int mm_combine_num_part_blocks(int P, const int32_t* Ps) {
-    const int fast = (mm_combine_num_runs(P) + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
+    int fast = (mm_combine_num_runs(P) + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK;
+    fast += ((Ps[1] + ZR_ROWS_PER_WARP - 1) / ZR_ROWS_PER_WARP + (Ps[2] + ZR_ROWS_PER_WARP - 1) / ZR_ROWS_PER_WARP +
+             (Ps[3] + ZR_ROWS_PER_WARP - 1) / ZR_ROWS_PER_WARP + ZR_WARPS - 1) / ZR_WARPS;      // interval-prefix dZ path
     const int generic = mm_combine_num_row_blocks(Ps);
     return fast > generic ? fast : generic;
+}
+// floats of scratch per item that `mom_z` must provide (max of the moment layout and the interval-prefix layout)
+extern "C" long long mm_combine_bwd_z_scratch_floats(int P, const int32_t* Ps, int D) {
+    long long need = static_cast<long long>(mm_combine_num_runs(P)) * 2 * (D / 2);
+    bool ok = Ps[0] == P;
+    for (int s = 1; s < 4 && ok; ++s) ok = Ps[s] > 0 && P % Ps[s] == 0;
+    if (ok) {
+        int ps[4] = {Ps[0], Ps[1], Ps[2], Ps[3]};
+        const long long z = z_scratch_layout(P, ps).per_slot;
+        if (z > need) need = z;
+    }
+    return need;
 }
 
 // classify the scale ratios for the token-centric backward; returns 1 when it applies
@@ -1690,6 +1712,9 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     a.nruns = mm_combine_num_runs(P);
     const bool fast = !force_generic && mom_u && mom_z && classify_scales(a);
     a.nrb = fast ? (a.nruns + RUNS_PER_BLOCK - 1) / RUNS_PER_BLOCK : mm_combine_num_row_blocks(Ps);
+    a.zscr = mom_z;
+    a.z_rows_path = fast && z_rows_path_ok(a) && !(force_generic & 2);
+    if (a.z_rows_path) a.nrb = z_ident_blocks(a) + z_rows_blocks(a);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!fast) {
         dim3 grid(a.nblk, B);
@@ -1720,15 +1745,25 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
             mm::note_launches(1);
             mm::trace_mark("combine_bwd.dUT", st);
         }
-        dim3 gridz(a.nrb, a.n_items + K);
-        switch (D) {
-            case 256: combine_bwd_z_kernel<256><<<gridz, 256, 0, st>>>(a); break;
-            case 512: combine_bwd_z_kernel<512><<<gridz, 256, 0, st>>>(a); break;
-            case 768: combine_bwd_z_kernel<768><<<gridz, 256, 0, st>>>(a); break;
-            case 1024: combine_bwd_z_kernel<1024><<<gridz, 256, 0, st>>>(a); break;
+        if (a.z_rows_path) {   // interval prefix sums: O(rows) instead of O(tokens x scales)
+            switch (D) {
+                case 256: rc = launch_bwd_z_rows_path<256>(a, st); break;
+                case 512: rc = launch_bwd_z_rows_path<512>(a, st); break;
+                case 768: rc = launch_bwd_z_rows_path<768>(a, st); break;
+                case 1024: rc = launch_bwd_z_rows_path<1024>(a, st); break;
+            }
+            if (rc) return rc;
+        } else {
+            dim3 gridz(a.nrb, a.n_items + K);
+            switch (D) {
+                case 256: combine_bwd_z_kernel<256><<<gridz, 256, 0, st>>>(a); break;
+                case 512: combine_bwd_z_kernel<512><<<gridz, 256, 0, st>>>(a); break;
+                case 768: combine_bwd_z_kernel<768><<<gridz, 256, 0, st>>>(a); break;
+                case 1024: combine_bwd_z_kernel<1024><<<gridz, 256, 0, st>>>(a); break;
+            }
+            mm::note_launches(1);
+            mm::trace_mark("combine_bwd.dZ", st);
         }
-        mm::note_launches(1);
-        mm::trace_mark("combine_bwd.dZ", st);
         for (int s = 1; s < 4; ++s) {
             if (a.mode[s] != SCALE_MOMENT) continue;
             dim3 gridf((a.Ps[s] + 7) / 8, a.n_items);

@@ -1,0 +1,336 @@
+// medmoe_b200 — dZ (gradient w.r.t. the native-resolution attention hidden Z) by interval prefix sums.
+// Included by combine.cu after CombineArgs, the row helpers and token_dlogit().
+//
+//   dZ_s[i, k] = w2[k] * sum_p w_i(p) dl_s(p) [interp(Z_s)(p, k) > 0]          (autograd of swin.py:63-68)
+//
+// For an integer scale ratio r the tokens between two adjacent native rows (a = Z_s[m], b = Z_s[m+1]) form an
+// interval j = 0..r-1 with lambda_j = (j + 0.5) / r, and h_j = a + lambda_j (b - a) changes sign at most once.
+// So the set of tokens whose ReLU gate is open is a prefix or a suffix of the interval, and per element
+//   A-side (to row m)   = sum_open (1 - lambda_j) dl_j = S0 - S1
+//   B-side (to row m+1) = sum_open lambda_j dl_j       = S1
+//   dw2[k]             += sum_open dl_j h_j            = a S0 + (b - a) S1
+// with S0 / S1 read from exclusive prefix sums of dl_j and lambda_j dl_j over the interval: O(1) per
+// (row, element) instead of O(r).  The r/2 clamped tokens before the first and after the last native row
+// ("head" / "tail") see h = Z_s[0] resp. Z_s[P_s - 1] with their whole weight on that row.
+//
+// Kernels (all deterministic, no atomics):
+//   bwd_z_dlogit_kernel : dlogit[slot, p, 0..3] from beta and the two column-half partial dbeta (+ gate gradient)
+//   bwd_z_prefix_kernel : per (slot, coarse scale, interval) the r+1 exclusive prefix sums, head / tail sums
+//   bwd_z_ident_kernel  : finest scale (r = 1): dZ_0[p] = dl_0(p) w2 [Z_0[p] > 0]  (+ dw2, db1, db2 partials)
+//   bwd_z_rows_kernel   : coarse scales, a warp walks 8 consecutive native rows (+ dw2, db1 partials)
+#pragma once
+
+namespace mm {
+
+constexpr int ZR_ROWS_PER_WARP = 8;
+constexpr int ZR_WARPS = 8;
+
+// scratch layout per slot (floats): dlog [P][4] | for s = 1..3: PA0 [(Ps-1)(r+1)], PA1 [(Ps-1)(r+1)] | HT [3][2]
+struct ZScratch {
+    long long per_slot;
+    long long pa_off[4];       // offset of PA0 of scale s (PA1 follows PA0)
+    long long pa_len[4];
+    long long ht_off;
+};
+__host__ __device__ inline ZScratch z_scratch_layout(int P, const int* Ps) {
+    ZScratch z{};
+    long long off = 4LL * P;
+    for (int s = 1; s < 4; ++s) {
+        const int r = P / Ps[s];
+        z.pa_len[s] = static_cast<long long>(Ps[s] - 1 > 0 ? Ps[s] - 1 : 0) * (r + 1);
+        z.pa_off[s] = off;
+        off += 2 * z.pa_len[s];
+    }
+    z.ht_off = off;
+    off += 8;
+    z.per_slot = off;
+    return z;
+}
+
+// grid = (ceil(P / 256), n_items)
+__global__ void __launch_bounds__(256)
+bwd_z_dlogit_kernel(const CombineArgs a, const ZScratch zs) {
+    const int slot = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const int item = a.perm[slot];
+    const float g = a.gate ? a.gate[item] : 1.0f;
+    float dot = 0.f;
+    if (p < a.P) {
+        const float4 dl = token_dlogit(a, slot, p, g, dot);
+        *reinterpret_cast<float4*>(a.zscr + slot * zs.per_slot + 4LL * p) = dl;
+    }
+    if (a.dgate) {   // top-k extension: d gate = sum_p <beta, dbeta>
+        __shared__ float sm[8];
+        dot = warp_sum(p < a.P ? dot : 0.f);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += sm[w];
+            atomicAdd(a.dgate + item, t);
+        }
+    }
+}
+
+// grid = (ceil(max_s (Ps - 1) / 256), n_items, 3); thread = interval m of scale s = blockIdx.z + 1
+__global__ void __launch_bounds__(256)
+bwd_z_prefix_kernel(const CombineArgs a, const ZScratch zs) {
+    const int slot = blockIdx.y;
+    const int s = blockIdx.z + 1;
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    const int Ps = a.Ps[s], r = a.ratio[s];
+    float* base = a.zscr + slot * zs.per_slot;
+    const float* dlog = base;
+    if (m < Ps - 1) {
+        float* pa0 = base + zs.pa_off[s] + static_cast<long long>(m) * (r + 1);
+        float* pa1 = pa0 + zs.pa_len[s];
+        const int p0 = r * m + (r >> 1);
+        const float inv_r = 1.0f / static_cast<float>(r);
+        float run0 = 0.f, run1 = 0.f;
+        for (int j = 0; j < r; ++j) {
+            pa0[j] = run0; pa1[j] = run1;
+            const float dl = dlog[4LL * (p0 + j) + s];
+            run0 += dl;
+            run1 = fmaf((static_cast<float>(j) + 0.5f) * inv_r, dl, run1);
+        }
+        pa0[r] = run0; pa1[r] = run1;
+    }
+    if (m == 0) {   // clamped tokens: head [0, r/2) -> row 0, tail [P - r/2, P) -> row Ps - 1
+        float hs = 0.f, ts = 0.f;
+        for (int p = 0; p < (r >> 1); ++p) hs += dlog[4LL * p + s];
+        for (int p = a.P - (r >> 1); p < a.P; ++p) ts += dlog[4LL * p + s];
+        base[zs.ht_off + (s - 1) * 2 + 0] = hs;
+        base[zs.ht_off + (s - 1) * 2 + 1] = ts;
+    }
+}
+
+// per-CTA partials [dw2 (H) | db1 (H) | db2] -> a.part[(slot * nrb + blk) * PART ...]
+template <int D, int NWARPS>
+MM_DEVINL void z_write_partials(const CombineArgs& a, int slot, int blk, float (*s_part)[2 * (D / 2) + 1], int warp, int lane,
+                                const float (&dw2)[(D / 256) * 4], const float (&db1)[(D / 256) * 4], float db2) {
+    constexpr int NE = D / 256;
+    constexpr int H = D / 2;
+    constexpr int PART = 2 * H + 1;
+#pragma unroll
+    for (int t = 0; t < NE; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s_part[warp][4 * (lane + 32 * t) + k] = dw2[4 * t + k];
+            s_part[warp][H + 4 * (lane + 32 * t) + k] = db1[4 * t + k];
+        }
+    if (lane == 0) s_part[warp][2 * H] = db2;
+    __syncthreads();
+    float* dst = a.part + (static_cast<size_t>(slot) * a.nrb + blk) * PART;
+    for (int cc = threadIdx.x; cc < PART; cc += blockDim.x) {
+        float accv = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) accv += s_part[w][cc];
+        dst[cc] = accv;
+    }
+}
+
+// finest scale; grid = (ceil(nruns / 8), n_items + K); warp = run of 32 tokens; blocks y >= n_items zero dZ's padding
+template <int D>
+__global__ void __launch_bounds__(256)
+bwd_z_ident_kernel(const CombineArgs a, const ZScratch zs) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    __shared__ float s_part[8][2 * H + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.y >= a.n_items) {
+        const int e = blockIdx.y - a.n_items;
+        for (int s = 0; s < 4; ++s) {
+            const long long rows = static_cast<long long>(a.counts[e]) * a.Ps[s];
+            const long long pad = (rows + TILE_M - 1) / TILE_M * TILE_M - rows;
+            __nv_bfloat16* dz = a.dZ + (static_cast<long long>(a.seg_start[s * a.K + e]) + rows) * H;
+            for (long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 4; i < pad * H;
+                 i += static_cast<long long>(gridDim.x) * 256 * 4)
+                *reinterpret_cast<uint2*>(dz + i) = make_uint2(0, 0);
+        }
+        return;
+    }
+    const int slot = blockIdx.y;
+    const int c = blockIdx.x * 8 + warp;
+    const int t0 = c * RUN_TOKENS;
+    float dw2[E], db1[E], db2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < E; ++k) { dw2[k] = 0.f; db1[k] = 0.f; }
+    if (c < a.nruns) {
+        const int e = a.slot_expert[slot];
+        float w2[E];
+        load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+        const long long base = a.slot_row[slot];                 // scale 0
+        const float* dlog = a.zscr + slot * zs.per_slot;
+        const int n_tok = min(RUN_TOKENS, a.P - t0);
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < n_tok) mine = *reinterpret_cast<const float4*>(dlog + 4LL * (t0 + lane));
+        db2 = mine.x + mine.y + mine.z + mine.w;                 // summed over lanes by the partial reduction below
+        float z[E];
+        load_row_bf16x4<NE>(a.Z + (base + t0) * H, lane, z);
+        for (int t = 0; t < n_tok; ++t) {
+            float zn[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) zn[k] = 0.f;
+            if (t + 1 < n_tok) load_row_bf16x4<NE>(a.Z + (base + t0 + t + 1) * H, lane, zn);
+            const float dl = __shfl_sync(0xffffffffu, mine.x, t);
+            float gk[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                const bool open = z[k] > 0.f;
+                gk[k] = open ? dl * w2[k] : 0.f;
+                if (open) dw2[k] = fmaf(dl, z[k], dw2[k]);
+                db1[k] += gk[k];
+            }
+            store_slab_bf16<NE>(a.dZ + (base + t0 + t) * H, lane, gk);
+#pragma unroll
+            for (int k = 0; k < E; ++k) z[k] = zn[k];
+        }
+        db2 = warp_sum(db2);
+    }
+    z_write_partials<D, 8>(a, slot, blockIdx.x, s_part, warp, lane, dw2, db1, lane == 0 ? db2 : 0.f);
+}
+
+// S0 / S1 of the open-gate token set of interval m for one element with end values (za, zb)
+MM_DEVINL void z_open_sums(float za, float zb, int r, const float* pa0, const float* pa1, float& S0, float& S1) {
+    S0 = 0.f; S1 = 0.f;
+    const bool pa = za > 0.f, pb = zb > 0.f;
+    if (!pa && !pb) return;
+    if (pa && pb) { S0 = pa0[r]; S1 = pa1[r]; return; }
+    const float t = za / (za - zb);                       // crossing point, in (0, 1]
+    const float x = t * static_cast<float>(r) - 0.5f;
+    if (pa) {                                             // open for lambda_j < t: prefix j < x
+        const int n = min(max(static_cast<int>(ceilf(x)), 0), r);
+        S0 = pa0[n]; S1 = pa1[n];
+    } else {                                              // open for lambda_j > t: suffix j > x
+        const int n = min(max(static_cast<int>(floorf(x)) + 1, 0), r);
+        S0 = pa0[r] - pa0[n]; S1 = pa1[r] - pa1[n];
+    }
+}
+
+// coarse scales; grid = (ceil(chunks / 8), n_items); warp = 8 consecutive native rows of one scale
+template <int D>
+__global__ void __launch_bounds__(ZR_WARPS * 32)
+bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunks2, int chunks3, int blk_base) {
+    constexpr int NE = D / 256;
+    constexpr int E = NE * 4;
+    constexpr int H = D / 2;
+    __shared__ float s_part[ZR_WARPS][2 * H + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.y;
+    int ch = blockIdx.x * ZR_WARPS + warp;
+    float dw2[E], db1[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) { dw2[k] = 0.f; db1[k] = 0.f; }
+    int s = 0;
+    if (ch < chunks1) s = 1;
+    else if ((ch -= chunks1) < chunks2) s = 2;
+    else if ((ch -= chunks2) < chunks3) s = 3;
+    if (s != 0) {
+        const int Ps = a.Ps[s], r = a.ratio[s];
+        const int e = a.slot_expert[slot];
+        float w2[E];
+        load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
+        const long long base = a.slot_row[s * a.n_items + slot];
+        const float* sbase = a.zscr + slot * zs.per_slot;
+        const float* PA0 = sbase + zs.pa_off[s];
+        const float* PA1 = PA0 + zs.pa_len[s];
+        const float hs = sbase[zs.ht_off + (s - 1) * 2 + 0], ts = sbase[zs.ht_off + (s - 1) * 2 + 1];
+        const int i_a = ch * ZR_ROWS_PER_WARP, i_b = min(Ps, i_a + ZR_ROWS_PER_WARP);
+        float za[E], zb[E], carry[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) carry[k] = 0.f;
+        load_row_bf16x4<NE>(a.Z + (base + i_a) * H, lane, zb);              // zb = Z[i_a]
+        if (i_a >= 1) {   // B-side of the interval that ends in the first row of this chunk
+            load_row_bf16x4<NE>(a.Z + (base + i_a - 1) * H, lane, za);
+            const float* pa0 = PA0 + static_cast<long long>(i_a - 1) * (r + 1);
+            const float* pa1 = PA1 + static_cast<long long>(i_a - 1) * (r + 1);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+                float S0, S1;
+                z_open_sums(za[k], zb[k], r, pa0, pa1, S0, S1);
+                carry[k] = S1;
+            }
+        }
+        for (int i = i_a; i < i_b; ++i) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) za[k] = zb[k];                        // za = Z[i]
+            float row[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) row[k] = carry[k];
+            if (i == 0) {
+#pragma unroll
+                for (int k = 0; k < E; ++k)
+                    if (za[k] > 0.f) { row[k] += hs; dw2[k] = fmaf(hs, za[k], dw2[k]); }
+            }
+            if (i == Ps - 1) {
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    if (za[k] > 0.f) { row[k] += ts; dw2[k] = fmaf(ts, za[k], dw2[k]); }
+                    carry[k] = 0.f;
+                }
+            } else {
+                load_row_bf16x4<NE>(a.Z + (base + i + 1) * H, lane, zb);    // zb = Z[i + 1]
+                const float* pa0 = PA0 + static_cast<long long>(i) * (r + 1);
+                const float* pa1 = PA1 + static_cast<long long>(i) * (r + 1);
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    float S0, S1;
+                    z_open_sums(za[k], zb[k], r, pa0, pa1, S0, S1);
+                    row[k] += S0 - S1;
+                    carry[k] = S1;
+                    dw2[k] += za[k] * S0 + (zb[k] - za[k]) * S1;
+                }
+            }
+            float o[E];
+#pragma unroll
+            for (int k = 0; k < E; ++k) { o[k] = w2[k] * row[k]; db1[k] += o[k]; }
+            store_slab_bf16<NE>(a.dZ + (base + i) * H, lane, o);
+        }
+    }
+    z_write_partials<D, ZR_WARPS>(a, slot, blk_base + blockIdx.x, s_part, warp, lane, dw2, db1, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+// the interval formulation needs the finest scale at full resolution and even integer ratios for the others
+static inline bool z_rows_path_ok(const CombineArgs& a) {
+    if (a.Ps[0] != a.P) return false;
+    for (int s = 1; s < 4; ++s) {
+        if (a.Ps[s] <= 0 || a.P % a.Ps[s] != 0) return false;
+        const int r = a.P / a.Ps[s];
+        if (r < 2 || (r & 1)) return false;
+    }
+    return true;
+}
+static inline int z_ident_blocks(const CombineArgs& a) { return (a.nruns + 7) / 8; }
+static inline int z_row_chunks(const CombineArgs& a, int s) { return (a.Ps[s] + ZR_ROWS_PER_WARP - 1) / ZR_ROWS_PER_WARP; }
+static inline int z_rows_blocks(const CombineArgs& a) {
+    return (z_row_chunks(a, 1) + z_row_chunks(a, 2) + z_row_chunks(a, 3) + ZR_WARPS - 1) / ZR_WARPS;
+}
+
+// launches the four kernels; a.nrb must be z_ident_blocks + z_rows_blocks, a.ratio[] filled
+template <int D>
+static int launch_bwd_z_rows_path(const CombineArgs& a, cudaStream_t st) {
+    int Ps[4] = {a.Ps[0], a.Ps[1], a.Ps[2], a.Ps[3]};
+    const ZScratch zs = z_scratch_layout(a.P, Ps);
+    bwd_z_dlogit_kernel<<<dim3((a.P + 255) / 256, a.n_items), 256, 0, st>>>(a, zs);
+    note_launches(1);
+    trace_mark("combine_bwd.dZ.dlogit", st);
+    int max_iv = 1;
+    for (int s = 1; s < 4; ++s) max_iv = a.Ps[s] - 1 > max_iv ? a.Ps[s] - 1 : max_iv;
+    bwd_z_prefix_kernel<<<dim3((max_iv + 255) / 256, a.n_items, 3), 256, 0, st>>>(a, zs);
+    note_launches(1);
+    trace_mark("combine_bwd.dZ.prefix", st);
+    bwd_z_ident_kernel<D><<<dim3(z_ident_blocks(a), a.n_items + a.K), 256, 0, st>>>(a, zs);
+    note_launches(1);
+    trace_mark("combine_bwd.dZ.ident", st);
+    bwd_z_rows_kernel<D><<<dim3(z_rows_blocks(a), a.n_items), ZR_WARPS * 32, 0, st>>>(
+        a, zs, z_row_chunks(a, 1), z_row_chunks(a, 2), z_row_chunks(a, 3), z_ident_blocks(a));
+    note_launches(1);
+    trace_mark("combine_bwd.dZ.rows", st);
+    return check_launch("combine_bwd(dZ interval path)");
+}
+
+}  // namespace mm

@@ -155,7 +155,7 @@ def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dgloba
     nrb = _lib.call("mm_combine_num_part_blocks", P, _lib.host_i32(lay.P))
     nruns = _lib.call("mm_combine_num_runs", P)
     mom_u = torch.empty(lay.n_items, nruns, 2, D, **f32)
-    mom_z = torch.empty(lay.n_items, nruns, 2, D // 2, **f32)
+    mom_z = torch.empty(lay.n_items, _lib.call("mm_combine_bwd_z_scratch_floats", P, _lib.host_i32(lay.P), D), **f32)
     dlogit = torch.empty(lay.n_items, P, 8, **f32)   # dlogit [.., 4] (generic path) or the two dbeta halves [.., 2, 4]
     dgate = torch.zeros(lay.n_items, **f32) if need_dgate else None
     dUT = torch.empty(lay.total_rows, D, dtype=torch.bfloat16, device=dev)
