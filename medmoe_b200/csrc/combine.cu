@@ -1486,16 +1486,28 @@ combine_bwd_finalize_kernel(const CombineArgs a, int s) {
     if (!a.z_rows_path) store_slab_bf16<NE>(a.dZ + (base + i) * H, lane, z);
 }
 
-// out[e, c] = sum over the slots of expert e and their nrb blocks of part[slot, blk, c]; grid = (ceil(C/256), K)
+// out[e, c] = sum over the slots of expert e and their nrb blocks of part[slot, blk, c].
+// grid = (ceil(C / 32), K); block = 32 columns x 8 row groups, fixed summation order (deterministic).
 __global__ void __launch_bounds__(256)
 expert_reduce_kernel(const float* __restrict__ part, const int* __restrict__ offsets, int nrb, int C, float* __restrict__ out) {
+    __shared__ float sm[8][33];
     const int e = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     const long long lo = static_cast<long long>(offsets[e]) * nrb, hi = static_cast<long long>(offsets[e + 1]) * nrb;
     float acc = 0.f;
-    for (long long r = lo; r < hi; ++r) acc += part[r * C + c];
-    out[static_cast<size_t>(e) * C + c] = acc;
+    if (c < C) {
+#pragma unroll 8
+        for (long long r = lo + grp; r < hi; r += 8) acc += part[r * C + c];
+    }
+    sm[grp][cl] = acc;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += sm[g][cl];
+        out[static_cast<size_t>(e) * C + c] = t;
+    }
 }
 
 }  // namespace mm
@@ -1786,7 +1798,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
         if (rc) return rc;
     }
     const int C = 2 * (D / 2) + 1;
-    expert_reduce_kernel<<<dim3((C + 255) / 256, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
+    expert_reduce_kernel<<<dim3((C + 31) / 32, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
     mm::note_launches(1);
     mm::trace_mark("combine_bwd.expert_reduce", st);
     return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");

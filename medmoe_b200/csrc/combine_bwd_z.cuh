@@ -43,7 +43,7 @@ __host__ __device__ inline ZScratch z_scratch_layout(int P, const int* Ps) {
     }
     z.ht_off = off;
     off += 8;
-    z.per_slot = off;
+    z.per_slot = (off + 3) / 4 * 4;      // dlog is accessed as float4: keep every slot 16-byte aligned
     return z;
 }
 
