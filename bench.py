@@ -339,6 +339,7 @@ def main():
         kern.pop("mm_interp_softmax_combine_fwd", None)
     if any(k.startswith("combine_bwd.") for k in sub):
         kern.pop("mm_interp_softmax_combine_bwd", None)
+        kern.pop("mm_interp_softmax_combine_bwd_global", None)
     kern.update(sub)
 
     # ---------------- timed region 2: end to end from pinned host buffers ----------------
@@ -435,6 +436,9 @@ def main():
                 "combine_bwd.dbeta": sum(Ps) * D * 2 + P0 * (16 + 32) + dloc,
                 "combine_bwd.dUT": sum(Ps) * D * 2 + P0 * 16 + dloc,
                 "combine_bwd.dZ": sum(Ps) * H * 2 * 2 + P0 * (16 + 32),
+                "combine_bwd.rowdot": sum(Ps) * D * 2 + sum(Ps) * 8,
+                "combine_bwd.dZ.rows": (sum(Ps) - P0) * H * 2 * 2,
+                "combine_bwd.dZ.ident": P0 * H * 2 * 2 + P0 * 16,
                 "mm_dispatch_rows": 2 * sum(p * d for p, d in zip(Ps, HIDDEN)) * 2,
                 "mm_undispatch_rows": 2 * sum(p * d for p, d in zip(Ps, HIDDEN)) * 2,
             }.get(top_label)

@@ -117,7 +117,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 // ---------------------------------------------------------------------------------------
 struct RowsMaps { CUtensorMap a, b, out, aux, gate; };
 
-template <int BN, bool OUT_F32, bool AUX>
+template <int BN, bool OUT_F32, int AUX>
 static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
     // smem: pipeline stages + output staging (32 KB, or 16 KB + 64 KB aux/gate staging) must fit 227 KB
     constexpr int STAGES = AUX ? ((BN > 128) ? 3 : 4) : ((BN > 192) ? 4 : (BN > 128 ? 4 : 5));
@@ -215,16 +215,23 @@ extern "C" int mm_trace_collect(char* buf, int len) {
 }
 
 // C[rows, N] = epi(A[rows, K] * W[e][N, K]^T) over 128-row tiles; see include/medmoe_b200.h.
-extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
-                                    long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
-                                    const float* bias, const void* aux, long long ld_aux, const void* gate,
-                                    long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
-                                    float out_scale, int flags, void* stream) {
+struct Rank1Aux { const float* row_coef; const int32_t* row_vec; const float* vecs; long long ld_vecs; };
+
+static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                          long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
+                          const float* bias, const void* aux, long long ld_aux, const Rank1Aux* r1, const void* gate,
+                          long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
+                          float out_scale, int flags, void* stream) {
     MM_REQUIRE(A && W && out, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: null operand");
     MM_REQUIRE(K > 0 && K % 8 == 0 && N > 0 && E > 0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: K must be a positive multiple of 8");
-    MM_REQUIRE((aux == nullptr) == (gate == nullptr), MM_ERR_UNSUPPORTED,
+    MM_REQUIRE(((aux != nullptr) || (r1 != nullptr)) == (gate != nullptr), MM_ERR_UNSUPPORTED,
                "mm_grouped_gemm_rows: aux and gate must be given together");
-    MM_REQUIRE(!(aux && out_f32), MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: aux/gate need a bf16 output");
+    MM_REQUIRE(!(gate && out_f32), MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: aux/gate need a bf16 output");
+    if (r1) {
+        MM_REQUIRE(!aux && r1->row_coef && r1->row_vec && r1->vecs && r1->ld_vecs >= N && r1->ld_vecs % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(r1->vecs) & 15) == 0,
+                   MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows_rank1: row_coef / row_vec / vecs (16-byte aligned rows) required");
+    }
     const int BN = pick_bn_rows(N);
     MM_REQUIRE(BN != 0, MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: N must be a multiple of 32");
     if (!tile_info) {
@@ -253,6 +260,8 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
         rc = encode_tmap(&m.aux, aux, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_aux), 32, 32,
                          CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(aux)");
         if (rc) return rc;
+    }
+    if (gate) {
         rc = encode_tmap(&m.gate, gate, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_gate), 32, 32,
                          CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(gate)");
         if (rc) return rc;
@@ -271,11 +280,16 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
     g.colsum = colsum;
     g.out_scale = out_scale;
     g.flags = flags;
+    g.row_coef = r1 ? r1->row_coef : nullptr;
+    g.row_vec = r1 ? r1->row_vec : nullptr;
+    g.vecs = r1 ? r1->vecs : nullptr;
+    g.ld_vecs = r1 ? r1->ld_vecs : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MM_ROWS_CASE(bn)                                                                          \
     case bn:                                                                                      \
-        if (out_f32) return launch_rows<bn, true, false>(m, g, st);                               \
-        return aux ? launch_rows<bn, false, true>(m, g, st) : launch_rows<bn, false, false>(m, g, st);
+        if (out_f32) return launch_rows<bn, true, 0>(m, g, st);                                   \
+        if (r1) return launch_rows<bn, false, 2>(m, g, st);                                       \
+        return aux ? launch_rows<bn, false, 1>(m, g, st) : launch_rows<bn, false, 0>(m, g, st);
     switch (BN) {
         MM_ROWS_CASE(256)
         MM_ROWS_CASE(192)
@@ -287,6 +301,28 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
 #undef MM_ROWS_CASE
     set_error("mm_grouped_gemm_rows: unreachable tile width %d", BN);
     return MM_ERR_UNSUPPORTED;
+}
+
+extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                                    long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
+                                    const float* bias, const void* aux, long long ld_aux, const void* gate,
+                                    long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
+                                    float out_scale, int flags, void* stream) {
+    return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, M, bias, aux, ld_aux, nullptr,
+                          gate, ld_gate, out, ld_out, out_f32, colsum, out_scale, flags, stream);
+}
+
+// out = (A W_e^T + row_coef[row] * vecs[row_vec[row], :]) * [gate > 0]: the dY GEMM when only global_feat has a
+// cotangent, so that the combine's gradient w.r.t. Y is rank-1 per image and never materialised.
+extern "C" int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                                          long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
+                                          const float* row_coef, const int32_t* row_vec, const float* vecs,
+                                          long long ld_vecs, const void* gate, long long ld_gate, void* out,
+                                          long long ld_out, float* colsum, void* stream) {
+    MM_REQUIRE(tile_info, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows_rank1: tile_info required");
+    const Rank1Aux r1{row_coef, row_vec, vecs, ld_vecs};
+    return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, nullptr, nullptr, 0, &r1,
+                          gate, ld_gate, out, ld_out, 0, colsum, 1.0f, 0, stream);
 }
 
 // dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e.

@@ -74,6 +74,7 @@ struct CombineArgs {
     float* zscr;                    // scratch of the interval-prefix dZ path (combine_bwd_z.cuh), aliases mom_z
     int z_rows_path;                // dZ comes from the interval-prefix kernels: finalize only writes dUT
     int dlogit_is_halves;           // dlogit holds two column-half partial dbeta ([.., 2, 4]) instead of finished dlogit
+    const float* row_dot;           // [rows] <dglobal[b], Y[row]> / P: dbeta is its lerp (rank-1 path, combine_rank1.cuh) or nullptr
     float* mom_u;                   // [n_items, nruns, 2, D]   zeroth / first moments of beta_s * dF per 32-token run
     float* mom_z;                   // [n_items, nruns, 2, D/2] same for dlogit_s * w2 * gate
 };
@@ -1140,6 +1141,19 @@ MM_DEVINL float4 token_dlogit(const CombineArgs& a, int slot, int p, float g, fl
     dot_out = 0.f;
     if (p < 0 || p >= a.P) return make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t tok = static_cast<size_t>(slot) * a.P + p;
+    if (a.row_dot) {             // dF is constant per image: dbeta_s(p) = interp(G_s)(p)
+        const float4 bt = *reinterpret_cast<const float4*>(a.beta + tok * 4);
+        float d[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+            const float* G = a.row_dot + a.slot_row[s * a.n_items + slot];
+            d[s] = (1.0f - L.lam) * G[L.i0] + L.lam * G[L.i1];
+        }
+        const float dot = bt.x * d[0] + bt.y * d[1] + bt.z * d[2] + bt.w * d[3];
+        dot_out = dot;
+        return make_float4(g * bt.x * (d[0] - dot), g * bt.y * (d[1] - dot), g * bt.z * (d[2] - dot), g * bt.w * (d[3] - dot));
+    }
     if (!a.dlogit_is_halves)     // finished dlogit (gate already applied) written by combine_bwd_logit_staged_kernel
         return *reinterpret_cast<const float4*>(a.dlogit + tok * 4);
     const float4 bt = *reinterpret_cast<const float4*>(a.beta + tok * 4);
@@ -1434,6 +1448,7 @@ combine_bwd_z_kernel(const CombineArgs a) {
 
 }  // namespace mm
 #include "combine_bwd_z.cuh"
+#include "combine_rank1.cuh"
 namespace mm {
 
 // MOMENT scale: combine the runs of each native row's window.  grid = (ceil(Ps[s] / 8), n_items); warp = native row.
@@ -1802,4 +1817,76 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     mm::note_launches(1);
     mm::trace_mark("combine_bwd.expert_reduce", st);
     return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");
+}
+
+// ---- backward when only global_feat has a cotangent (dlocal == NULL): rank-1 path, see combine_rank1.cuh ----
+extern "C" int mm_combine_bwd_global_supported(int P, const int32_t* Ps, int D) {
+    if (!(D == 256 || D == 512 || D == 768 || D == 1024)) return 0;
+    CombineArgs a{};
+    a.P = P;
+    for (int s = 0; s < 4; ++s) a.Ps[s] = Ps[s];
+    return z_rows_path_ok(a) ? 1 : 0;
+}
+
+extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
+                                                    const int32_t* Ps, int D, int K, const int32_t* perm,
+                                                    const int32_t* inv_perm, const int32_t* slot_expert,
+                                                    const int32_t* slot_row, const int32_t* counts, const int32_t* seg_start,
+                                                    const int32_t* offsets, const float* gate, const float* beta,
+                                                    const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
+                                                    float* dgate, void* dZ, float* part, float* dw2_db1_db2, float* zscr,
+                                                    void* stream) {
+    CombineArgs a{};
+    int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_bwd_global");
+    if (rc) return rc;
+    if (!(Y && Z && w2 && beta && dglobal && row_dot && row_coef && row_img && dZ && part && dw2_db1_db2 && zscr)) {
+        mm::set_error("mm_interp_softmax_combine_bwd_global: null operand");
+        return MM_ERR_BAD_SHAPE;
+    }
+    a.perm = perm; a.inv_perm = inv_perm; a.slot_expert = slot_expert; a.slot_row = slot_row; a.gate = gate;
+    a.counts = counts; a.seg_start = seg_start; a.K = K;
+    a.Y = static_cast<const __nv_bfloat16*>(Y); a.Z = static_cast<const __nv_bfloat16*>(Z);
+    a.w2 = w2; a.beta = const_cast<float*>(beta);
+    a.dglobal = dglobal; a.dgate = dgate; a.dZ = static_cast<__nv_bfloat16*>(dZ);
+    a.part = part; a.zscr = zscr; a.mom_z = zscr; a.row_dot = row_dot;
+    a.nblk = mm_combine_num_token_blocks(P);
+    a.nruns = mm_combine_num_runs(P);
+    if (!z_rows_path_ok(a)) {
+        mm::set_error("mm_interp_softmax_combine_bwd_global: needs Ps[0] == P and even integer scale ratios (use mm_interp_softmax_combine_bwd)");
+        return MM_ERR_UNSUPPORTED;
+    }
+    for (int s = 0; s < 4; ++s) a.ratio[s] = P / Ps[s];
+    a.z_rows_path = 1;
+    a.nrb = z_ident_blocks(a) + z_rows_blocks(a);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int total = Ps[0] + Ps[1] + Ps[2] + Ps[3];
+    mm::trace_mark("begin", st);
+    {
+        dim3 grid((total + R1_WARPS * R1_ROWS_PER_WARP - 1) / (R1_WARPS * R1_ROWS_PER_WARP), a.n_items);
+        switch (D) {
+            case 256: rank1_rowdot_kernel<256><<<grid, R1_WARPS * 32, 0, st>>>(a, row_dot, row_img); break;
+            case 512: rank1_rowdot_kernel<512><<<grid, R1_WARPS * 32, 0, st>>>(a, row_dot, row_img); break;
+            case 768: rank1_rowdot_kernel<768><<<grid, R1_WARPS * 32, 0, st>>>(a, row_dot, row_img); break;
+            case 1024: rank1_rowdot_kernel<1024><<<grid, R1_WARPS * 32, 0, st>>>(a, row_dot, row_img); break;
+        }
+        mm::note_launches(1);
+        mm::trace_mark("combine_bwd.rowdot", st);
+    }
+    rank1_coef_kernel<<<dim3((total + 255) / 256, a.n_items), 256, 0, st>>>(a, row_coef);
+    mm::note_launches(1);
+    mm::trace_mark("combine_bwd.coef", st);
+    rc = mm_check_launch("mm_interp_softmax_combine_bwd_global(rank-1)");
+    if (rc) return rc;
+    switch (D) {
+        case 256: rc = launch_bwd_z_rows_path<256>(a, st); break;
+        case 512: rc = launch_bwd_z_rows_path<512>(a, st); break;
+        case 768: rc = launch_bwd_z_rows_path<768>(a, st); break;
+        case 1024: rc = launch_bwd_z_rows_path<1024>(a, st); break;
+    }
+    if (rc) return rc;
+    const int C = 2 * (D / 2) + 1;
+    expert_reduce_kernel<<<dim3((C + 31) / 32, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
+    mm::note_launches(1);
+    mm::trace_mark("combine_bwd.expert_reduce", st);
+    return mm_check_launch("mm_interp_softmax_combine_bwd_global(reduce)");
 }

@@ -50,6 +50,11 @@ struct RowsGemmArgs {
     float* colsum;           // [E, N] fp32, += column sums of the written tile (bias gradients) or nullptr
     float out_scale;         // multiplies the accumulator before bias (1.0 for the MoE path)
     int flags;
+    // AUX == 2 ("rank-1 aux"): aux[row, col] = row_coef[row] * vecs[row_vec[row], col], never materialised
+    const float* row_coef;   // [rows] fp32
+    const int* row_vec;      // [rows] index of the row's vector
+    const float* vecs;       // [n_vecs, ld_vecs] fp32
+    long long ld_vecs;
 };
 
 struct WgradArgs {
@@ -65,7 +70,9 @@ constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
 constexpr int EPI_WARPS = 8;               // epilogue warps of gemm_rows_kernel
 constexpr int ROWS_THREADS = (4 + EPI_WARPS) * 32;
 
-template <int BN, int STAGES, bool AUX = false>
+// AUX: 0 = plain epilogue, 1 = out = (acc + aux) * [gate > 0] with aux/gate tiles TMA-prefetched,
+//      2 = same with aux given as a rank-1 product (only the gate tile is loaded)
+template <int BN, int STAGES, int AUX = 0>
 struct GemmSmem {
     static constexpr int A_BYTES = TILE_M * 64 * 2;                 // 16 KB: 128 rows x 64 bf16 (K-major) or 2 x (64 k-rows x 64 mn)
     static constexpr int B_BYTES = ((BN + 63) / 64) * 64 * 64 * 2;   // BN rounded up to 64-wide chunks
@@ -85,7 +92,7 @@ MM_DEVINL uint32_t epi_slot_off(int r, int j) { return static_cast<uint32_t>(r *
 // ------------------------------------------------------------------------------------
 // gemm_rows_kernel
 // ------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool OUT_F32, bool AUX>
+template <int BN, int STAGES, bool OUT_F32, int AUX>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
@@ -113,7 +120,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (!OUT_F32) tma_prefetch_desc(&tmOut);
-        if (AUX) { tma_prefetch_desc(&tmAux); tma_prefetch_desc(&tmGate); }
+        if (AUX == 1) tma_prefetch_desc(&tmAux);
+        if (AUX) tma_prefetch_desc(&tmGate);
     }
     if (threadIdx.x == 32) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -199,8 +207,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         auto issue_in = [&](int w, int c, int slot) {   // lane 0 only
             const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
             const int row0 = lt * TILE_M + q * 32, col0 = nt * BN + c * 32;
-            mbar_expect_tx(&my_bar[slot], 2 * EPI_SLOT_BYTES);
-            tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES, &tmAux, &my_bar[slot], col0, row0);
+            mbar_expect_tx(&my_bar[slot], (AUX == 1 ? 2 : 1) * EPI_SLOT_BYTES);
+            if (AUX == 1) tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES, &tmAux, &my_bar[slot], col0, row0);
             tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES + EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
         };
 
@@ -222,6 +230,12 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long long row = static_cast<long long>(lt) * TILE_M + r_in_tile;
             const bool row_valid = r_in_tile < valid;
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+            float r1_coef = 0.f;
+            const float* r1_vec = a.vecs;
+            if (AUX == 2 && row_valid) {
+                r1_coef = __ldg(a.row_coef + row);
+                r1_vec = a.vecs + static_cast<long long>(__ldg(a.row_vec + row)) * a.ld_vecs;
+            }
 #pragma unroll 1
             for (int c = h; c < NCH; c += CSTEP) {
                 uint32_t v[32];
@@ -250,14 +264,25 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     iphase[islot] ^= 1;
                     const uint8_t* ax = my_in + islot * 2 * EPI_SLOT_BYTES;
                     const uint8_t* gt = ax + EPI_SLOT_BYTES;
+                    if (AUX == 2) {
+                        const float4* vp = reinterpret_cast<const float4*>(r1_vec + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 x = __ldg(vp + j);
+                            f[4 * j + 0] = fmaf(r1_coef, x.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(r1_coef, x.y, f[4 * j + 1]);
+                            f[4 * j + 2] = fmaf(r1_coef, x.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(r1_coef, x.w, f[4 * j + 3]);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
                         const uint4 g = *reinterpret_cast<const uint4*>(gt + epi_slot_off(lane, j));
-                        f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
-                        f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);
-                        f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
-                        f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
+                        if (AUX == 1) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
+                            f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
+                            f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);
+                            f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
+                            f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
+                        }
                         // gate holds ReLU outputs (>= 0): "> 0" is "bits != 0" on the bf16 payload.
                         if ((g.x & 0x0000ffffu) == 0) f[8 * j + 0] = 0.f;
                         if ((g.x & 0xffff0000u) == 0) f[8 * j + 1] = 0.f;

@@ -140,17 +140,28 @@ class _ExpertsFunction(torch.autograd.Function):
             dfused = dfused.contiguous()
         dglobal32 = dglobal.float().contiguous() if dglobal is not None else None
 
-        dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
-                                                        ctx.gate_needs_grad)
-        # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT; column sums -> conv bias gradients
         W1T = ops.transpose_cast_bf16(W1_32.float()).view(E * D, H)          # [E, D, H]
         dbp = [torch.zeros(E, D, dtype=torch.float32, device=dev) for _ in range(S)]
-        for s in range(S):
-            r0, nr = layout.region_base[s], layout.region_rows[s]
-            ops.gemm_rows(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
-                          tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr], colsum=dbp[s],
-                          flags=ops.EPI_ZERO_PAD, tag=f"dY.s{s}")
-        dPre = dUT
+        if dfused is None and not ops.FORCE_GENERIC_COMBINE_BWD and ops.combine_bwd_global_supported(plan, D):
+            # only global_feat has a cotangent: d fused / d Y is rank-1 per image and is rebuilt in the dY epilogue
+            row_coef, row_img, dZ, dw2, db1, db2, dgate = ops.combine_bwd_global(Y, Z, w2, plan, D, gate_flat, beta, dglobal32,
+                                                                                ctx.gate_needs_grad)
+            dPre = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
+            for s in range(S):
+                r0, nr = layout.region_base[s], layout.region_rows[s]
+                ops.gemm_rows_rank1(dZ[r0:r0 + nr], W1T, D, dPre[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
+                                    tile_count=layout.region_tiles[s], row_coef=row_coef[r0:r0 + nr], row_vec=row_img[r0:r0 + nr],
+                                    vecs=dglobal32, gate=Y[r0:r0 + nr], colsum=dbp[s], tag=f"dY.s{s}")
+        else:
+            dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
+                                                            ctx.gate_needs_grad)
+            # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT; column sums -> conv bias gradients
+            for s in range(S):
+                r0, nr = layout.region_base[s], layout.region_rows[s]
+                ops.gemm_rows(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
+                              tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr], colsum=dbp[s],
+                              flags=ops.EPI_ZERO_PAD, tag=f"dY.s{s}")
+            dPre = dUT
 
         grads_feats: List = [None] * S
         if any(ctx.feat_needs_grad):

@@ -293,3 +293,44 @@ def test_top2_extension_vs_generalised_oracle():
     # with k > 1 the router is also trained through the gate weights
     _grad_ok(sg.grad.cpu(), sr.grad, dict(grad=2e-2, cos=0.995), "d_swin_feat")
     _grad_ok(moe.router[0].weight.grad.cpu(), pr["router.0.weight"].grad, dict(grad=2e-2, cos=0.995), "router.0.weight")
+
+
+@pytest.mark.parametrize("topk,Ps", [(1, [3136, 784, 196, 49]), (2, [2304, 576, 144, 36])])
+def test_global_only_cotangent_rank1_path(topk, Ps):
+    """Only global_feat has a cotangent (BASELINE config 2: the contrastive loss consumes global_feat alone): the backward
+    takes the rank-1 path (mm_interp_softmax_combine_bwd_global + mm_grouped_gemm_rows_rank1).  It must agree with the
+    oracle and with the general path fed an explicit all-zero local cotangent."""
+    K, hidden, D, B = 4, [96, 192, 384, 768], 768, 5
+    params = mo.init_params(K, hidden, D, D, seed=51)
+    params = {k: (v.to(torch.bfloat16).float() if (".proj_convs." in k or ".attn_proj.0." in k) and k.endswith("weight") else v)
+              for k, v in params.items()}
+    torch.manual_seed(52)
+    feats = [torch.randn(B, p, d).to(torch.bfloat16).float() for p, d in zip(Ps, hidden)]
+    sw, cg = torch.randn(B, D), torch.randn(B, D)
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    (gf, lf, probs), idx = mo.moe_forward_sparse(pr, fr, sw.clone(), topk=topk)
+    (gf * cg).sum().backward()
+
+    moe = _module_from(params, K, hidden, D, topk=topk)
+    launches = []
+    for zero_local in (False, True):
+        moe.zero_grad()
+        fg = [f.cuda().requires_grad_(True) for f in feats]
+        gf2, lf2, _ = moe(fg, sw.cuda())
+        obj = (gf2 * cg.cuda()).sum()
+        if zero_local:
+            obj = obj + (lf2 * 0.0).sum()
+        n0 = medmoe_b200._lib.load().mm_launch_count()
+        obj.backward()
+        launches.append(medmoe_b200._lib.load().mm_launch_count() - n0)
+        got_f = [f.grad.clone() for f in fg]
+        got_p = {k: p.grad.clone() for k, p in moe.named_parameters() if p.grad is not None}
+        for s in range(4):
+            _grad_ok(got_f[s].cpu(), fr[s].grad, TIGHT, f"d_feat{s} (zero_local={zero_local})")
+        used = set(idx.flatten().tolist())
+        for k, gr in got_p.items():
+            if not k.startswith("experts.") or int(k.split(".")[1]) not in used or k.endswith("attn_proj.2.bias"):
+                continue
+            _grad_ok(gr.cpu(), pr[k].grad, TIGHT, k, key="attn0" if ".attn_proj.0." in k else "grad")
+    assert launches[0] < launches[1]      # the rank-1 path really ran (fewer kernels: no dbeta / dUT / finalize passes)
