@@ -124,10 +124,16 @@ int mm_combine_num_row_blocks(const int32_t* Ps);
 int mm_combine_num_runs(int P);
 int mm_combine_num_part_blocks(int P, const int32_t* Ps);
 long long mm_combine_bwd_z_scratch_floats(int P, const int32_t* Ps, int D);   /* floats per item of `mom_z` */
+/* perm / seg_start / offsets / tile_info0 (the n_tiles0 tile_info entries of the finest-scale region, whose first
+ * row-space row is region0_row) / K / total_rows (rows of Y) come from mm_dispatch_build; they enable the
+ * tensor-core combine (out = C * Yrows with a sparse coefficient matrix, tcgen05).  tile_info0 == NULL or
+ * flags & 1 selects the CUDA-core kernel. */
 int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk, int P,
                                   const int32_t* Ps, int D, const int32_t* inv_perm, const int32_t* slot_expert,
                                   const int32_t* slot_row, const float* gate, float* beta, void* out, int out_f32,
-                                  float* gpart, float* global_feat, void* stream);
+                                  float* gpart, float* global_feat, const int32_t* perm, const int32_t* seg_start,
+                                  const int32_t* offsets, const int32_t* tile_info0, int n_tiles0, int region0_row, int K,
+                                  long long total_rows, int flags, void* stream);
 /* backward: dlocal [B, P, D] (bf16/fp32, may be NULL), dglobal [B, D] fp32 (may be NULL) ->
  * dlogit [n_items, P, 8] scratch (dlogit, or the two column-half partial dbeta of the token-centric path), dgate [n_items] (+=, may be NULL), dUT [rows, D] bf16, dZ [rows, D/2] bf16,
  * part [n_items, mm_combine_num_part_blocks, D + 1] scratch, dw2_db1_db2 [K, D + 1] = per expert

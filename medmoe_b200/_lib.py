@@ -45,7 +45,8 @@ SIGNATURES = {
     "mm_combine_num_part_blocks": (c_int, [c_int, c_vp]),
     "mm_combine_bwd_z_scratch_floats": (c_ll, [c_int, c_vp, c_int]),
     "mm_interp_softmax_combine_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp,
-                                              c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+                                              c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int,
+                                              c_int, c_int, c_ll, c_int, c_vp]),
     "mm_interp_softmax_combine_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),

@@ -112,6 +112,15 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
     return encode_tmap(out, base, inner, rows, row_stride, box_inner, box_rows, CU_TENSOR_MAP_SWIZZLE_128B, what);
 }
 
+int encode_tmap_bf16_swz(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                         uint32_t box_inner, uint32_t box_rows, int swizzle_bytes, const char* what) {
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+    return encode_tmap(out, base, inner, rows, row_stride, box_inner, box_rows, swz, what);
+}
+
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------

@@ -14,6 +14,9 @@ int check_launch(const char* what);
 // row_stride = elements between rows, box = {box_inner (<= 64), box_rows (<= 256)}.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
                      uint32_t box_inner, uint32_t box_rows, const char* what);
+// same with a selectable swizzle (0 / 32 / 64 / 128 bytes)
+int encode_tmap_bf16_swz(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
+                         uint32_t box_inner, uint32_t box_rows, int swizzle_bytes, const char* what);
 int sm_count();
 // number of kernels launched through the C-ABI since load (bench.py's gpu_launches evidence)
 void note_launches(int n);

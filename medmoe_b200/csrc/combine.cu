@@ -1449,6 +1449,7 @@ combine_bwd_z_kernel(const CombineArgs a) {
 }  // namespace mm
 #include "combine_bwd_z.cuh"
 #include "combine_rank1.cuh"
+#include "combine_mma.cuh"
 namespace mm {
 
 // MOMENT scale: combine the runs of each native row's window.  grid = (ceil(Ps[s] / 8), n_items); warp = native row.
@@ -1624,11 +1625,48 @@ extern "C" int mm_combine_num_row_blocks(const int32_t* Ps) {
     return (Ps[0] + Ps[1] + Ps[2] + Ps[3] + CB_ROWS_PER_BLOCK - 1) / CB_ROWS_PER_BLOCK;
 }
 
+// tensor-core forward combine (combine_mma.cuh): 0 = launched, 1 = does not apply (caller falls back), < 0 = error
+static int cm_launch_out(CombineArgs& a, CmArgs& c, int D, long long total_rows, int out_f32, cudaStream_t st) {
+    if (!c.tile_info || !c.seg_start || !c.offsets || !a.perm || !cm_geometry(a, D, c)) return 1;
+    for (int s = 0; s < 4; ++s) a.ratio[s] = a.P / a.Ps[s];
+    c.D = D;
+    c.n_pass = D / CM_BN;
+    c.out_f32 = out_f32;
+    const size_t smem = cm_smem_bytes(c, out_f32 != 0);
+    if (smem > 227 * 1024) return 1;
+    CUtensorMap tmY[4], tmOut;
+    for (int s = 0; s < 4; ++s) {
+        int rc = mm::encode_tmap_bf16(&tmY[s], a.Y, static_cast<uint64_t>(D), static_cast<uint64_t>(total_rows),
+                                      static_cast<uint64_t>(D), 64, static_cast<uint32_t>(c.cap[s]), "combine_out(Y)");
+        if (rc) return rc;
+    }
+    tmOut = tmY[0];
+    if (!out_f32) {
+        int rc = mm::encode_tmap_bf16_swz(&tmOut, a.out, static_cast<uint64_t>(D), static_cast<uint64_t>(a.B) * a.P,
+                                          static_cast<uint64_t>(D), 32, 32, 64, "combine_out(out)");
+        if (rc) return rc;
+    }
+    const int grid = c.n_tiles < mm::sm_count() ? c.n_tiles : mm::sm_count();
+    if (out_f32) {
+        auto kern = cm_out_kernel<true>;
+        if (int rc = opt_in_smem(kern, smem, "combine_out(mma)")) return rc;
+        kern<<<grid, CM_THREADS, smem, st>>>(tmY[0], tmY[1], tmY[2], tmY[3], tmOut, a, c);
+    } else {
+        auto kern = cm_out_kernel<false>;
+        if (int rc = opt_in_smem(kern, smem, "combine_out(mma)")) return rc;
+        kern<<<grid, CM_THREADS, smem, st>>>(tmY[0], tmY[1], tmY[2], tmY[3], tmOut, a, c);
+    }
+    mm::note_launches(1);
+    return MM_OK;
+}
+
 extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk,
                                              int P, const int32_t* Ps, int D, const int32_t* inv_perm,
                                              const int32_t* slot_expert, const int32_t* slot_row, const float* gate,
                                              float* beta, void* out, int out_f32, float* gpart, float* global_feat,
-                                             void* stream) {
+                                             const int32_t* perm, const int32_t* seg_start, const int32_t* offsets,
+                                             const int32_t* tile_info0, int n_tiles0, int region0_row, int K,
+                                             long long total_rows, int flags, void* stream) {
     CombineArgs a{};
     int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_fwd");
     if (rc) return rc;
@@ -1651,10 +1689,24 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     if (staged < 0) return staged;
     if (staged == 0) {
         mm::trace_mark("combine_fwd.logits", st);
-        a.nblk = a.tiles_per_img;
-        MM_STAGED_D(D, out_f32, sg_launch_out, a, st, staged)
-        if (staged < 0) return staged;
-        if (staged == 0) mm::trace_mark("combine_fwd.out", st);
+        // out = C Yrows on the tensor cores when the geometry allows it, else the CUDA-core staged kernel
+        CmArgs c{};
+        c.n_tiles = n_tiles0;
+        c.tile_info = reinterpret_cast<const int2*>(tile_info0);
+        c.region_row[0] = region0_row;
+        c.seg_start = seg_start; c.offsets = offsets; c.K = K;
+        a.perm = perm;
+        a.nblk = mm_combine_num_token_blocks(P);
+        int mma = (flags & 1) ? 1 : cm_launch_out(a, c, D, total_rows, out_f32, st);
+        if (mma < 0) return mma;
+        if (mma == 0) {
+            mm::trace_mark("combine_fwd.out", st);
+        } else {
+            a.nblk = a.tiles_per_img;
+            MM_STAGED_D(D, out_f32, sg_launch_out, a, st, staged)
+            if (staged < 0) return staged;
+            if (staged == 0) mm::trace_mark("combine_fwd.out", st);
+        }
     }
     if (staged != 0) {
         a.nblk = (P + CB_TOKENS_PER_BLOCK - 1) / CB_TOKENS_PER_BLOCK;

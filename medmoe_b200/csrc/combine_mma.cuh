@@ -1,0 +1,312 @@
+// medmoe_b200 — forward combine on the tensor cores (tcgen05 / TMEM / TMA).
+// Included by combine.cu after CombineArgs.
+//
+//   fused[p, :] = sum_s beta_s(p) interp(Y_s)(p, :)        (reference swin.py:42,78-80)
+//
+// is a sparse matrix product: for a tile of 128 consecutive tokens (= 128 consecutive rows of the finest scale
+// in the expert-sorted row space) every output row is a combination of 7 native rows
+//   out[128, D] = C[128, KT] * Yrows[KT, D],   KT = 128 (scale 0, diagonal beta_0) + sum_{s>0} (128 / r_s + 2 -> mult. of 8)
+// The native rows a tile touches are ONE contiguous row range per scale (items of an expert are contiguous in
+// every region), so TMA stages them as the MN-major B operand (channels contiguous), the coefficient matrix C is
+// built in shared memory as the K-major A operand (7 non-zeros per row at fixed positions, everything else stays
+// zero), and tcgen05.mma does all the multiply-adds.  CUDA cores only compute 7 coefficients per token and run the
+// epilogue (TMEM -> bf16 -> swizzled staging -> TMA store, plus the per-32-token column sums for global_feat).
+// HBM traffic = Y once + out once: the kernel is bound by HBM, not by instruction issue like its CUDA-core predecessor.
+//
+// Roles (512 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 coefficient
+// builders (thread = token), warps 8-15 epilogue (two per TMEM lane quarter).
+// Requirements (host falls back to the CUDA-core kernel otherwise): topk == 1, Ps[0] == P, P % 32 == 0, every
+// ratio r_s = P / Ps[s] a power of two <= 128, D % 128 == 0.
+#pragma once
+#include "gemm.cuh"
+
+namespace mm {
+
+constexpr int CM_BN = 128;              // output columns per accumulator pass
+constexpr int CM_STAGES = 3;
+constexpr int CM_ACC = 4;               // TMEM ring: 4 accumulators x 128 columns
+constexpr int CM_EPI_WARPS = 8;
+constexpr int CM_COEF_WARPS = 4;
+constexpr int CM_THREADS = (4 + CM_COEF_WARPS + CM_EPI_WARPS) * 32;
+
+struct CmArgs {
+    int n_tiles;                 // 128-row tiles of the finest-scale region
+    const int2* tile_info;       // [n_tiles] {expert | -1, valid rows} of those tiles
+    int region_row[4];           // first row-space row of region s
+    const int* seg_start;        // [4, K]
+    const int* offsets;          // [K + 1] first slot of expert e
+    int K;
+    int cap[4], koff[4], ktot;   // rows staged per scale, their first k index, total (multiple of 16)
+    int D, n_pass;               // D / CM_BN
+    int out_f32;
+};
+
+MM_DEVINL int cm_floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// byte offset of element (m, k) of the K-major SWIZZLE_128B coefficient matrix (blocks of 64 k = 16 KB)
+MM_DEVINL uint32_t cm_a_off(int m, int k) {
+    const int kb = k >> 6, kin = k & 63;
+    return static_cast<uint32_t>(kb * 16384 + m * 128 + ((((kin >> 3) ^ (m & 7))) << 4) + (kin & 7) * 2);
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(CM_THREADS, 1)
+cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ CUtensorMap tmY1,
+              const __grid_constant__ CUtensorMap tmY2, const __grid_constant__ CUtensorMap tmY3,
+              const __grid_constant__ CUtensorMap tmOut, const CombineArgs a, const CmArgs c) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = ((c.ktot + 63) / 64) * 16384;
+    const int stage_bytes = c.ktot * 256;                       // 2 column chunks x ktot rows x 128 B
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + a_bytes;
+    uint8_t* sOut = sB + CM_STAGES * stage_bytes;               // [CM_EPI_WARPS][2 slots] (bf16 output only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (OUT_F32 ? 0 : CM_EPI_WARPS * 2 * EPI_SLOT_BYTES));
+    uint64_t* empty = full + CM_STAGES;
+    uint64_t* tfull = empty + CM_STAGES;
+    uint64_t* tempty = tfull + CM_ACC;
+    uint64_t* a_full = tempty + CM_ACC;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmY0); tma_prefetch_desc(&tmY1); tma_prefetch_desc(&tmY2); tma_prefetch_desc(&tmY3);
+        if (!OUT_F32) tma_prefetch_desc(&tmOut);
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < CM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CM_ACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CM_EPI_WARPS); }
+        mbar_init(a_full, CM_COEF_WARPS);
+        mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    // the coefficient matrix starts as all zeros; only the 7 fixed positions of every row are ever rewritten
+    for (int i = threadIdx.x * 16; i < a_bytes; i += CM_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nk = c.ktot >> 4;
+
+    if (threadIdx.x == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int e = c.tile_info[t].x;
+            if (e < 0) continue;
+            const int row0 = c.region_row[0] + t * TILE_M;
+            const int rel0 = row0 - c.seg_start[e];                 // multiple of 128
+            int row_s[4];
+            row_s[0] = row0;
+#pragma unroll
+            for (int s = 1; s < 4; ++s) row_s[s] = c.seg_start[s * c.K + e] + rel0 / a.ratio[s] - 1;
+            for (int n = 0; n < c.n_pass; ++n) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], static_cast<uint32_t>(stage_bytes));
+                uint8_t* dst = sB + stage * stage_bytes;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint8_t* d = dst + ch * (c.ktot * 128);
+                    const int col = n * CM_BN + ch * 64;
+                    tma_load_2d(d + c.koff[0] * 128, &tmY0, &full[stage], col, row_s[0]);
+                    tma_load_2d(d + c.koff[1] * 128, &tmY1, &full[stage], col, row_s[1]);
+                    tma_load_2d(d + c.koff[2] * 128, &tmY2, &full[stage], col, row_s[2]);
+                    tma_load_2d(d + c.koff[3] * 128, &tmY3, &full[stage], col, row_s[3]);
+                }
+                if (++stage == CM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(TILE_M, CM_BN, 0, 1);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t a_phase = 0;
+        const uint32_t a_addr = smem_u32(sA);
+        const uint32_t lbo = static_cast<uint32_t>(c.ktot) * 128u;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            if (c.tile_info[t].x < 0) continue;
+            mbar_wait(a_full, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+            for (int n = 0; n < c.n_pass; ++n) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * CM_BN;
+                const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
+                for (int j = 0; j < nk; ++j) {
+                    const uint64_t da = make_smem_desc(a_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024);
+                    const uint64_t db = make_smem_desc(b_addr + j * 2048, lbo, 1024);
+                    umma_bf16(d_tmem, da, db, idesc, j != 0);
+                }
+                umma_commit(&empty[stage]);
+                umma_commit(&tfull[acc]);
+                if (++stage == CM_STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == CM_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+            umma_commit(a_empty);       // every MMA that reads this tile's coefficients has retired
+        }
+    } else if (warp >= 4 && warp < 4 + CM_COEF_WARPS) {
+        // ===================== coefficient builders: thread = token m of the tile =====================
+        const int m = (warp - 4) * 32 + lane;
+        uint32_t a_phase = 0;
+        // fixed positions of this token's non-zeros: k = m (scale 0) and koff[s] + j0 + 1, + 2 (coarse scales)
+        uint32_t off0 = cm_a_off(m, c.koff[0] + m), offa[4], offb[4];
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const int r = a.ratio[s];
+            const int j0 = cm_floor_div(2 * m + 1 - r, 2 * r);
+            offa[s] = cm_a_off(m, c.koff[s] + j0 + 1);
+            offb[s] = cm_a_off(m, c.koff[s] + j0 + 2);
+        }
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int2 ti = c.tile_info[t];
+            const int e = ti.x;
+            if (e < 0) continue;
+            float v0 = 0.f, va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m < ti.y) {
+                const int rel0 = c.region_row[0] + t * TILE_M - c.seg_start[e];
+                const int rel = rel0 + m;
+                const int j = rel / a.P, p = rel - j * a.P;
+                const int slot = c.offsets[e] + j;
+                const float g = a.gate ? a.gate[a.perm[slot]] : 1.0f;
+                const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+                const float bs[4] = {bt.x * g, bt.y * g, bt.z * g, bt.w * g};
+                v0 = bs[0];
+#pragma unroll
+                for (int s = 1; s < 4; ++s) {
+                    const int r = a.ratio[s];
+                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                    const int fs = c.seg_start[s * c.K + e] + rel0 / r - 1;
+                    const int base = a.slot_row[s * a.n_items + slot];
+                    const int qa = base + L.i0 - fs, qb = base + L.i1 - fs;
+                    const int q0 = cm_floor_div(2 * m + 1 - r, 2 * r) + 1;
+                    va[s] = bs[s] * ((qa == q0 ? 1.0f - L.lam : 0.f) + (qb == q0 ? L.lam : 0.f));
+                    vb[s] = bs[s] * ((qa == q0 + 1 ? 1.0f - L.lam : 0.f) + (qb == q0 + 1 ? L.lam : 0.f));
+                }
+            }
+            mbar_wait(a_empty, a_phase ^ 1);
+            a_phase ^= 1;
+            *reinterpret_cast<__nv_bfloat16*>(sA + off0) = __float2bfloat16_rn(v0);
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+                *reinterpret_cast<__nv_bfloat16*>(sA + offa[s]) = __float2bfloat16_rn(va[s]);
+                *reinterpret_cast<__nv_bfloat16*>(sA + offb[s]) = __float2bfloat16_rn(vb[s]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    } else if (warp >= 4 + CM_COEF_WARPS) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                      // TMEM lane quarter (== warp index % 4)
+        const int ew = warp - 4 - CM_COEF_WARPS;
+        const int h = ew >> 2;                       // this warp takes the 32-column chunks h and h + 2 of every pass
+        uint8_t* my_out = sOut + ew * 2 * EPI_SLOT_BYTES;
+        int acc = 0; uint32_t acc_phase = 0;
+        int oslot = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int2 ti = c.tile_info[t];
+            const int e = ti.x;
+            if (e < 0) continue;
+            const int m0 = q * 32;
+            const bool valid = m0 < ti.y;            // P % 32 == 0: a warp's 32 tokens are all valid or all padding
+            long long orow = 0;
+            int blk = 0, b = 0;
+            if (valid) {
+                const int rel = c.region_row[0] + t * TILE_M - c.seg_start[e] + m0;
+                const int j = rel / a.P, p0 = rel - j * a.P;
+                b = a.perm[c.offsets[e] + j] / a.topk;
+                orow = static_cast<long long>(b) * a.P + p0;
+                blk = p0 >> 5;
+            }
+            for (int n = 0; n < c.n_pass; ++n) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                if (valid) {
+                    const uint32_t t_row = tmem_base + acc * CM_BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+                    for (int cc = h; cc < CM_BN / 32; cc += 2) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_row + cc * 32, v);
+                        tmem_ld_wait();
+                        const int col0 = n * CM_BN + cc * 32;
+                        float f[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+                        if constexpr (OUT_F32) {
+                            float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + (orow + lane) * c.D + col0);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) op[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+                        } else {
+                            if (lane == 0) tma_store_wait_read<1>();
+                            __syncwarp();
+                            uint8_t* so = my_out + oslot * EPI_SLOT_BYTES;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint4 u;
+                                u.x = pack_bf16x2(f[8 * k + 0], f[8 * k + 1]);
+                                u.y = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
+                                u.z = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]);
+                                u.w = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
+                                *reinterpret_cast<uint4*>(so + epi_slot_off(lane, k)) = u;
+                            }
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmOut, so, col0, static_cast<int>(orow));
+                                tma_store_commit();
+                            }
+                            oslot ^= 1;
+                        }
+                        // deterministic partial of global_feat: column sums over this warp's 32 tokens
+                        const float cs = warp_colsum32(f, lane);
+                        a.gpart[(static_cast<size_t>(b) * a.nblk + blk) * c.D + col0 + lane] = cs;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == CM_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        if (!OUT_F32 && lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static inline bool cm_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// fills the K layout; false when the tensor-core path does not apply
+static inline bool cm_geometry(const CombineArgs& a, int D, CmArgs& c) {
+    if (a.topk != 1 || a.Ps[0] != a.P || a.P % 32 != 0 || D % CM_BN != 0) return false;
+    int off = 0;
+    for (int s = 0; s < 4; ++s) {
+        if (a.Ps[s] <= 0 || a.P % a.Ps[s] != 0) return false;
+        const int r = a.P / a.Ps[s];
+        if (!cm_pow2(r) || r > TILE_M || (s > 0 && r < 2)) return false;
+        c.cap[s] = (s == 0) ? TILE_M : ((TILE_M / r + 2 + 7) / 8) * 8;
+        c.koff[s] = off;
+        off += c.cap[s];
+    }
+    c.ktot = off;        // every staged row comes from a TMA box: no uninitialised k rows
+    return off % 16 == 0 && off <= 256;
+}
+
+static inline size_t cm_smem_bytes(const CmArgs& c, bool out_f32) {
+    return static_cast<size_t>((c.ktot + 63) / 64) * 16384 + static_cast<size_t>(CM_STAGES) * c.ktot * 256 +
+           (out_f32 ? 0 : CM_EPI_WARPS * 2 * EPI_SLOT_BYTES) + (2 * CM_STAGES + 2 * CM_ACC + 2) * 8 + 16 + 1024;
+}
+
+}  // namespace mm

@@ -183,6 +183,20 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_commit(&tfull[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+    } else if (warp == 3) {
+        // ===================== tiles no expert owns =====================
+        // The capacity slack behind a region's last segment gets defined contents (zeros), so that consumers which
+        // stage whole row ranges with TMA (combine_mma.cuh) never multiply uninitialised memory by a zero coefficient.
+        if (!OUT_F32 && a.tile_info) {
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
+                if (a.tile_info[a.tile_begin + lt].x >= 0) continue;
+                __nv_bfloat16* base = static_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(lt) * TILE_M * a.ld_out + nt * BN;
+                for (int r = 0; r < TILE_M; ++r)
+                    for (int cidx = lane * 8; cidx < BN; cidx += 256)
+                        stg_v4(base + r * a.ld_out + cidx, make_uint4(0, 0, 0, 0));
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;                 // TMEM lane quarter

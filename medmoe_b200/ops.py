@@ -17,6 +17,8 @@ EPI_RELU, EPI_ZERO_PAD = 1, 2
 _P = _lib.ptr
 # test hook: run the generic (any scale ratio) backward-combine kernel instead of the token-centric one
 FORCE_GENERIC_COMBINE_BWD = False
+# test hook: run the CUDA-core forward combine instead of the tensor-core one (combine_mma.cuh)
+FORCE_CUDA_CORE_COMBINE_FWD = False
 
 
 def _need_cuda(*tensors):
@@ -152,9 +154,12 @@ def combine_fwd(Y, Z, w2, b2, plan: DispatchPlan, D: int, gate, out_dtype):
     out = torch.empty(B, P, D, dtype=out_dtype, device=dev)
     gpart = torch.empty(B, nblk, D, dtype=torch.float32, device=dev)
     gfeat = torch.empty(B, D, dtype=torch.float32, device=dev)
+    tile0 = plan.tile_info[lay.tile_base[0]:lay.tile_base[0] + lay.region_tiles[0]]
     _lib.call("mm_interp_softmax_combine_fwd", _P(Y), _P(Z), _P(w2), _P(b2), B, lay.topk, P, _lib.host_i32(lay.P), D,
               _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(gate), _P(beta), _P(out),
-              int(out_dtype == torch.float32), _P(gpart), _P(gfeat), _st())
+              int(out_dtype == torch.float32), _P(gpart), _P(gfeat), _P(plan.perm), _P(plan.seg_start), _P(plan.offsets),
+              _P(tile0), lay.region_tiles[0], lay.region_base[0], lay.num_experts, Y.shape[0],
+              int(FORCE_CUDA_CORE_COMBINE_FWD), _st())
     return out, gfeat, beta
 
 

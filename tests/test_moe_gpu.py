@@ -334,3 +334,28 @@ def test_global_only_cotangent_rank1_path(topk, Ps):
                 continue
             _grad_ok(gr.cpu(), pr[k].grad, TIGHT, k, key="attn0" if ".attn_proj.0." in k else "grad")
     assert launches[0] < launches[1]      # the rank-1 path really ran (fewer kernels: no dbeta / dUT / finalize passes)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_tensor_core_and_cuda_core_forward_combine_agree(dtype):
+    """The tcgen05 forward combine (out = C * Yrows, bf16 coefficients) against the CUDA-core kernel (fp32 coefficients):
+    same beta, same Y; they differ by the bf16 rounding of the 7 coefficients per token (<= 2^-9 relative each)."""
+    K, hidden, D, Ps, B = 3, [96, 192, 384, 768], 768, [3136, 784, 196, 49], 7
+    params = mo.init_params(K, hidden, D, D, seed=61)
+    moe = _module_from(params, K, hidden, D)
+    torch.manual_seed(62)
+    feats = [torch.randn(B, p, d, device="cuda", dtype=dtype) for p, d in zip(Ps, hidden)]
+    sw = torch.randn(B, D, device="cuda")
+    outs = []
+    for force in (False, True):
+        ops.FORCE_CUDA_CORE_COMBINE_FWD = force
+        try:
+            with torch.no_grad():
+                gf, lf, _ = moe(feats, sw)
+            outs.append((gf.float().clone(), lf.float().clone()))
+        finally:
+            ops.FORCE_CUDA_CORE_COMBINE_FWD = False
+    (g_t, l_t), (g_c, l_c) = outs
+    assert torch.isfinite(l_t).all()
+    assert rel_err(l_t, l_c) < 4e-3 and rel_err(g_t, g_c) < 2e-3
+    assert not torch.equal(l_t, l_c)          # the two paths really are different kernels
