@@ -22,13 +22,13 @@
 
 namespace mm {
 
-constexpr int ZR_ROWS_PER_WARP = 8;
+constexpr int ZR_ROWS_PER_WARP = 16;
 constexpr int ZR_WARPS = 8;
 
-// scratch layout per slot (floats): dlog [P][4] | for s = 1..3: PA0 [(Ps-1)(r+1)], PA1 [(Ps-1)(r+1)] | HT [3][2]
+// scratch layout per slot (floats): dlog [P][4] | for s = 1..3: PA [(Ps-1)(r+1)] x {PA0, PA1} interleaved | HT [3][2]
 struct ZScratch {
     long long per_slot;
-    long long pa_off[4];       // offset of PA0 of scale s (PA1 follows PA0)
+    long long pa_off[4];       // offset of the {PA0, PA1} pairs of scale s (8-byte aligned)
     long long pa_len[4];
     long long ht_off;
 };
@@ -82,18 +82,17 @@ bwd_z_prefix_kernel(const CombineArgs a, const ZScratch zs) {
     float* base = a.zscr + slot * zs.per_slot;
     const float* dlog = base;
     if (m < Ps - 1) {
-        float* pa0 = base + zs.pa_off[s] + static_cast<long long>(m) * (r + 1);
-        float* pa1 = pa0 + zs.pa_len[s];
+        float2* pa = reinterpret_cast<float2*>(base + zs.pa_off[s]) + static_cast<long long>(m) * (r + 1);
         const int p0 = r * m + (r >> 1);
         const float inv_r = 1.0f / static_cast<float>(r);
         float run0 = 0.f, run1 = 0.f;
         for (int j = 0; j < r; ++j) {
-            pa0[j] = run0; pa1[j] = run1;
+            pa[j] = make_float2(run0, run1);
             const float dl = dlog[4LL * (p0 + j) + s];
             run0 += dl;
             run1 = fmaf((static_cast<float>(j) + 0.5f) * inv_r, dl, run1);
         }
-        pa0[r] = run0; pa1[r] = run1;
+        pa[r] = make_float2(run0, run1);
     }
     if (m == 0) {   // clamped tokens: head [0, r/2) -> row 0, tail [P - r/2, P) -> row Ps - 1
         float hs = 0.f, ts = 0.f;
@@ -191,21 +190,20 @@ bwd_z_ident_kernel(const CombineArgs a, const ZScratch zs) {
     z_write_partials<D, 8>(a, slot, blockIdx.x, s_part, warp, lane, dw2, db1, lane == 0 ? db2 : 0.f);
 }
 
-// S0 / S1 of the open-gate token set of interval m for one element with end values (za, zb)
-MM_DEVINL void z_open_sums(float za, float zb, int r, const float* pa0, const float* pa1, float& S0, float& S1) {
-    S0 = 0.f; S1 = 0.f;
-    const bool pa = za > 0.f, pb = zb > 0.f;
-    if (!pa && !pb) return;
-    if (pa && pb) { S0 = pa0[r]; S1 = pa1[r]; return; }
-    const float t = za / (za - zb);                       // crossing point, in (0, 1]
-    const float x = t * static_cast<float>(r) - 0.5f;
-    if (pa) {                                             // open for lambda_j < t: prefix j < x
-        const int n = min(max(static_cast<int>(ceilf(x)), 0), r);
-        S0 = pa0[n]; S1 = pa1[n];
-    } else {                                              // open for lambda_j > t: suffix j > x
-        const int n = min(max(static_cast<int>(floorf(x)) + 1, 0), r);
-        S0 = pa0[r] - pa0[n]; S1 = pa1[r] - pa1[n];
-    }
+// S0 / S1 of the open-gate token set of interval m for one element with end values (za, zb): the open set is the
+// token range [lo, hi) of the interval (a prefix, a suffix, everything or nothing), read from the prefix sums.
+// Branch-free: lanes of a warp see all four cases.  The crossing point uses the fast division: a gate can only
+// differ from the forward's when interp(Z) is within ~1e-6 relative of zero, far below the bf16 storage noise of Z.
+MM_DEVINL void z_open_sums(float za, float zb, int r, const float2* __restrict__ pa, float& S0, float& S1) {
+    const bool oa = za > 0.f, ob = zb > 0.f;
+    const float x = __fdividef(za, za - zb) * static_cast<float>(r) - 0.5f;     // crossing, in token units
+    const int n_pre = min(max(static_cast<int>(ceilf(x)), 0), r);               // open for lambda_j < t: tokens j < x
+    const int n_suf = min(max(static_cast<int>(floorf(x)) + 1, 0), r);          // open for lambda_j > t: tokens j > x
+    const int hi = oa ? (ob ? r : n_pre) : (ob ? r : 0);
+    const int lo = (ob && !oa) ? n_suf : 0;
+    const float2 h = __ldg(pa + hi), l = __ldg(pa + lo);
+    S0 = h.x - l.x;
+    S1 = h.y - l.y;
 }
 
 // coarse scales; grid = (ceil(chunks / 8), n_items); warp = 8 consecutive native rows of one scale
@@ -233,28 +231,28 @@ bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunk
         load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
         const long long base = a.slot_row[s * a.n_items + slot];
         const float* sbase = a.zscr + slot * zs.per_slot;
-        const float* PA0 = sbase + zs.pa_off[s];
-        const float* PA1 = PA0 + zs.pa_len[s];
+        const float2* PA = reinterpret_cast<const float2*>(sbase + zs.pa_off[s]);
         const float hs = sbase[zs.ht_off + (s - 1) * 2 + 0], ts = sbase[zs.ht_off + (s - 1) * 2 + 1];
         const int i_a = ch * ZR_ROWS_PER_WARP, i_b = min(Ps, i_a + ZR_ROWS_PER_WARP);
-        float za[E], zb[E], carry[E];
+        float za[E], zb[E], zn[E], carry[E];
 #pragma unroll
-        for (int k = 0; k < E; ++k) carry[k] = 0.f;
+        for (int k = 0; k < E; ++k) { carry[k] = 0.f; zn[k] = 0.f; }
         load_row_bf16x4<NE>(a.Z + (base + i_a) * H, lane, zb);              // zb = Z[i_a]
+        if (i_a + 1 < Ps) load_row_bf16x4<NE>(a.Z + (base + i_a + 1) * H, lane, zn);
         if (i_a >= 1) {   // B-side of the interval that ends in the first row of this chunk
             load_row_bf16x4<NE>(a.Z + (base + i_a - 1) * H, lane, za);
-            const float* pa0 = PA0 + static_cast<long long>(i_a - 1) * (r + 1);
-            const float* pa1 = PA1 + static_cast<long long>(i_a - 1) * (r + 1);
+            const float2* pa = PA + static_cast<long long>(i_a - 1) * (r + 1);
 #pragma unroll
             for (int k = 0; k < E; ++k) {
                 float S0, S1;
-                z_open_sums(za[k], zb[k], r, pa0, pa1, S0, S1);
+                z_open_sums(za[k], zb[k], r, pa, S0, S1);
                 carry[k] = S1;
             }
         }
         for (int i = i_a; i < i_b; ++i) {
 #pragma unroll
-            for (int k = 0; k < E; ++k) za[k] = zb[k];                        // za = Z[i]
+            for (int k = 0; k < E; ++k) { za[k] = zb[k]; zb[k] = zn[k]; }     // za = Z[i], zb = Z[i + 1]
+            if (i + 2 < Ps && i + 1 < i_b) load_row_bf16x4<NE>(a.Z + (base + i + 2) * H, lane, zn);   // prefetch Z[i + 2]
             float row[E];
 #pragma unroll
             for (int k = 0; k < E; ++k) row[k] = carry[k];
@@ -270,13 +268,11 @@ bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunk
                     carry[k] = 0.f;
                 }
             } else {
-                load_row_bf16x4<NE>(a.Z + (base + i + 1) * H, lane, zb);    // zb = Z[i + 1]
-                const float* pa0 = PA0 + static_cast<long long>(i) * (r + 1);
-                const float* pa1 = PA1 + static_cast<long long>(i) * (r + 1);
+                const float2* pa = PA + static_cast<long long>(i) * (r + 1);
 #pragma unroll
                 for (int k = 0; k < E; ++k) {
                     float S0, S1;
-                    z_open_sums(za[k], zb[k], r, pa0, pa1, S0, S1);
+                    z_open_sums(za[k], zb[k], r, pa, S0, S1);
                     row[k] += S0 - S1;
                     carry[k] = S1;
                     dw2[k] += za[k] * S0 + (zb[k] - za[k]) * S1;

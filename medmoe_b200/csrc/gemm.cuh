@@ -85,6 +85,11 @@ struct GemmSmem {
     static constexpr int WGRAD_TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;      // the wgrad kernel has no staging slots
 };
 
+// 0xffff in every 16-bit half of `w` (two bf16) that is > 0
+MM_DEVINL uint32_t bf16x2_pos_mask(uint32_t w) {
+    return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w), __float2bfloat162_rn(0.0f));
+}
+
 // 16-byte chunk j (0..3) of row r inside a 32-row x 64-byte staging slot written/read by TMA with
 // CU_TENSOR_MAP_SWIZZLE_64B (address bits [4,6) ^= bits [7,9)).
 MM_DEVINL uint32_t epi_slot_off(int r, int j) { return static_cast<uint32_t>(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
@@ -238,18 +243,18 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 valid = min(TILE_M, a.M - lt * TILE_M);
             }
             const int w_next = next_valid(w + gridDim.x);
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
             const int r_in_tile = q * 32 + lane;
             const long long row = static_cast<long long>(lt) * TILE_M + r_in_tile;
             const bool row_valid = r_in_tile < valid;
-            const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
             float r1_coef = 0.f;
             const float* r1_vec = a.vecs;
-            if (AUX == 2 && row_valid) {
+            if (AUX == 2 && row_valid) {     // issued before the accumulator wait: the two dependent loads hide behind it
                 r1_coef = __ldg(a.row_coef + row);
                 r1_vec = a.vecs + static_cast<long long>(__ldg(a.row_vec + row)) * a.ld_vecs;
             }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = h; c < NCH; c += CSTEP) {
                 uint32_t v[32];
@@ -260,11 +265,21 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         else if (w_next < total_work) issue_in(w_next, h, islot ^ 1);
                     }
                 }
-                tmem_ld_wait();
                 const int col0 = nt * BN + c * 32;
+                float4 xv[8];
+                if (AUX == 2) {      // rank-1 aux vector: issued before the TMEM wait so that both latencies overlap
+                    const float4* vp = reinterpret_cast<const float4*>(r1_vec + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] = __ldg(vp + j);
+                }
+                tmem_ld_wait();
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * a.out_scale;
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (a.out_scale != 1.0f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] *= a.out_scale;
+                }
                 if (a.bias) {
                     const float4* bp = reinterpret_cast<const float4*>(a.bias + static_cast<size_t>(e) * a.N + col0);
 #pragma unroll
@@ -273,18 +288,17 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
                     }
                 }
+                uint32_t gmask[16];      // AUX: 0xffff per bf16 half whose gate (a ReLU output, >= 0) is > 0
                 if (AUX) {
                     mbar_wait(&my_bar[islot], iphase[islot]);
                     iphase[islot] ^= 1;
                     const uint8_t* ax = my_in + islot * 2 * EPI_SLOT_BYTES;
                     const uint8_t* gt = ax + EPI_SLOT_BYTES;
                     if (AUX == 2) {
-                        const float4* vp = reinterpret_cast<const float4*>(r1_vec + col0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 x = __ldg(vp + j);
-                            f[4 * j + 0] = fmaf(r1_coef, x.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(r1_coef, x.y, f[4 * j + 1]);
-                            f[4 * j + 2] = fmaf(r1_coef, x.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(r1_coef, x.w, f[4 * j + 3]);
+                            f[4 * j + 0] = fmaf(r1_coef, xv[j].x, f[4 * j + 0]); f[4 * j + 1] = fmaf(r1_coef, xv[j].y, f[4 * j + 1]);
+                            f[4 * j + 2] = fmaf(r1_coef, xv[j].z, f[4 * j + 2]); f[4 * j + 3] = fmaf(r1_coef, xv[j].w, f[4 * j + 3]);
                         }
                     }
 #pragma unroll
@@ -297,15 +311,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             f[8 * j + 4] += bf16lo(u.z); f[8 * j + 5] += bf16hi(u.z);
                             f[8 * j + 6] += bf16lo(u.w); f[8 * j + 7] += bf16hi(u.w);
                         }
-                        // gate holds ReLU outputs (>= 0): "> 0" is "bits != 0" on the bf16 payload.
-                        if ((g.x & 0x0000ffffu) == 0) f[8 * j + 0] = 0.f;
-                        if ((g.x & 0xffff0000u) == 0) f[8 * j + 1] = 0.f;
-                        if ((g.y & 0x0000ffffu) == 0) f[8 * j + 2] = 0.f;
-                        if ((g.y & 0xffff0000u) == 0) f[8 * j + 3] = 0.f;
-                        if ((g.z & 0x0000ffffu) == 0) f[8 * j + 4] = 0.f;
-                        if ((g.z & 0xffff0000u) == 0) f[8 * j + 5] = 0.f;
-                        if ((g.w & 0x0000ffffu) == 0) f[8 * j + 6] = 0.f;
-                        if ((g.w & 0xffff0000u) == 0) f[8 * j + 7] = 0.f;
+                        gmask[4 * j + 0] = bf16x2_pos_mask(g.x); gmask[4 * j + 1] = bf16x2_pos_mask(g.y);
+                        gmask[4 * j + 2] = bf16x2_pos_mask(g.z); gmask[4 * j + 3] = bf16x2_pos_mask(g.w);
                     }
                     __syncwarp();       // every lane is done with slot `islot` before lane 0 refills it next iteration
                     islot ^= 1;
@@ -314,7 +321,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
                 }
-                if (!row_valid) {
+                if (valid < TILE_M && !row_valid) {      // only a segment's last tile has padding rows
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = 0.f;
                 }
@@ -325,19 +332,19 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     }
                 } else {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                        if (AUX) pk[j] &= gmask[j];      // the ReLU gate, applied to the packed pair
+                    }
                     // staging slot `oslot` is free once the store that last used it has read it
                     if (lane == 0) tma_store_wait_read<S::OUT_SLOTS - 1>();
                     __syncwarp();
                     uint8_t* so = my_out + oslot * EPI_SLOT_BYTES;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                        u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                        u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                        u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(so + epi_slot_off(lane, j)) = u;
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(so + epi_slot_off(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
@@ -345,6 +352,10 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_store_commit();
                     }
                     if (S::OUT_SLOTS == 2) oslot ^= 1;
+                    if (AUX && a.colsum) {               // column sums of what was written (gated, bf16-rounded)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { f[2 * j] = bf16lo(pk[j]); f[2 * j + 1] = bf16hi(pk[j]); }
+                    }
                 }
                 if (a.colsum) {
                     const float cs = warp_colsum32(f, lane);
