@@ -113,6 +113,11 @@ int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K, long long
 int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
                           int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,
                           int tile_base, float* out, void* stream);
+/* same, plus colsum[e][i] += sum over the rows of expert e of A[row, i] (fp32 [E, N1], caller zeroes it): the bias
+ * gradient that belongs to the weight gradient, from the same MMAs (a constant ones block appended to B). */
+int mm_grouped_gemm_wgrad_colsum(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
+                                 int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,
+                                 int tile_base, float* out, float* colsum, void* stream);
 
 /* ---- (4) interpolate + scale-softmax + weighted combine / scatter-back ------------------
  * replaces swin.py:42-80 (F.interpolate, stack/permute, attn_proj[1:], softmax over scales,

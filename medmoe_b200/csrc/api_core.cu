@@ -150,17 +150,18 @@ static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t
     return check_launch("gemm_rows");
 }
 
-template <int BN>
+template <int BN, bool COLSUM>
 static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const WgradArgs& args, cudaStream_t st) {
-    constexpr int STAGES = (BN > 192) ? 4 : (BN > 128 ? 5 : 6);
+    constexpr int STAGES = COLSUM ? ((BN > 128) ? 4 : (BN > 64 ? 5 : 6)) : ((BN > 192) ? 4 : (BN > 128 ? 5 : 6));
     using S = GemmSmem<BN, STAGES>;
-    static_assert(S::WGRAD_TOTAL <= 227 * 1024, "shared memory budget exceeded");
-    auto kern = gemm_wgrad_kernel<BN, STAGES>;
+    constexpr int SMEM = S::WGRAD_TOTAL + (COLSUM ? STAGES * 8192 : 0);
+    static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_wgrad_kernel<BN, STAGES, COLSUM>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::WGRAD_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) {
-            set_error("gemm_wgrad: cannot opt in to %d B of shared memory (%s)", S::WGRAD_TOTAL, cudaGetErrorString(e));
+            set_error("gemm_wgrad: cannot opt in to %d B of shared memory (%s)", SMEM, cudaGetErrorString(e));
             return MM_ERR_CUDA;
         }
         configured = true;
@@ -168,7 +169,7 @@ static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const Wgra
     const int work = args.chunk_count * args.n_i * args.n_j;
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
-    kern<<<grid, 256, S::WGRAD_TOTAL, st>>>(tA, tB, args);
+    kern<<<grid, 256, SMEM, st>>>(tA, tB, args);
     note_launches(1);
     return check_launch("gemm_wgrad");
 }
@@ -334,20 +335,20 @@ extern "C" int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K
                           gate, ld_gate, out, ld_out, 0, colsum, 1.0f, 0, stream);
 }
 
-// dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e.
-extern "C" int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B,
-                                     long long b_rows, int N2, long long ldb, const int32_t* chunks, int chunk_begin,
-                                     int chunk_count, int tile_base, float* out, void* stream) {
+// dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e (+ optional column sums of A).
+static int gemm_wgrad_impl(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows, int N2,
+                           long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count, int tile_base,
+                           float* out, float* colsum, void* stream) {
     MM_REQUIRE(A && B && out && chunks, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_wgrad: null operand");
     MM_REQUIRE(N1 > 0 && N1 % 8 == 0 && N2 > 0 && N2 % 8 == 0, MM_ERR_BAD_SHAPE,
                "mm_grouped_gemm_wgrad: N1, N2 must be positive multiples of 8");
     if (chunk_count <= 0) return MM_OK;
     int BN;
-    if (N2 % 256 == 0) BN = 256;
+    if (N2 % 256 == 0 && !colsum) BN = 256;
     else if (N2 % 192 == 0) BN = 192;
     else if (N2 <= 64) BN = 64;
     else if (N2 <= 128) BN = 128;
-    else if (N2 <= 192) BN = 192;
+    else if (N2 <= 192 || colsum) BN = 192;
     else BN = 256;
     CUtensorMap tA, tB;
     int rc = encode_tmap_bf16(&tA, A, static_cast<uint64_t>(N1), static_cast<uint64_t>(a_rows), static_cast<uint64_t>(lda), 64, 64,
@@ -366,13 +367,39 @@ extern "C" int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, lo
     g.n_i = (N1 + TILE_M - 1) / TILE_M;
     g.n_j = (N2 + BN - 1) / BN;
     g.out = out;
+    g.colsum = colsum;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (BN) {
-        case 256: return launch_wgrad<256>(tA, tB, g, st);
-        case 192: return launch_wgrad<192>(tA, tB, g, st);
-        case 128: return launch_wgrad<128>(tA, tB, g, st);
-        case 64: return launch_wgrad<64>(tA, tB, g, st);
+    if (colsum) {
+        switch (BN) {
+            case 192: return launch_wgrad<192, true>(tA, tB, g, st);
+            case 128: return launch_wgrad<128, true>(tA, tB, g, st);
+            case 64: return launch_wgrad<64, true>(tA, tB, g, st);
+        }
+    } else {
+        switch (BN) {
+            case 256: return launch_wgrad<256, false>(tA, tB, g, st);
+            case 192: return launch_wgrad<192, false>(tA, tB, g, st);
+            case 128: return launch_wgrad<128, false>(tA, tB, g, st);
+            case 64: return launch_wgrad<64, false>(tA, tB, g, st);
+        }
     }
     set_error("mm_grouped_gemm_wgrad: unreachable tile width %d", BN);
     return MM_ERR_UNSUPPORTED;
+}
+
+extern "C" int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B,
+                                     long long b_rows, int N2, long long ldb, const int32_t* chunks, int chunk_begin,
+                                     int chunk_count, int tile_base, float* out, void* stream) {
+    return gemm_wgrad_impl(A, a_rows, N1, lda, B, b_rows, N2, ldb, chunks, chunk_begin, chunk_count, tile_base, out, nullptr,
+                           stream);
+}
+
+// same, and colsum[e][i] += sum over the rows of expert e of A[row, i]: the bias gradient that goes with a weight
+// gradient, produced by the same MMAs through a constant ones block appended to B.
+extern "C" int mm_grouped_gemm_wgrad_colsum(const void* A, long long a_rows, int N1, long long lda, const void* B,
+                                            long long b_rows, int N2, long long ldb, const int32_t* chunks, int chunk_begin,
+                                            int chunk_count, int tile_base, float* out, float* colsum, void* stream) {
+    MM_REQUIRE(colsum, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_wgrad_colsum: colsum is NULL");
+    return gemm_wgrad_impl(A, a_rows, N1, lda, B, b_rows, N2, ldb, chunks, chunk_begin, chunk_count, tile_base, out, colsum,
+                           stream);
 }

@@ -64,6 +64,7 @@ struct WgradArgs {
     int N1, N2;              // dW is [E, N1, N2]; A is [rows, N1], B is [rows, N2]
     int n_i, n_j;            // tiles along N1 (128 each) and N2 (BN each)
     float* out;              // [E, N1, N2] fp32, accumulated with red.add
+    float* colsum;           // COLSUM only: [E, N1] fp32, += sum over rows of A[row, i] (column sums of A on the tensor cores)
 };
 
 constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
@@ -379,18 +380,24 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------
 // gemm_wgrad_kernel: dW[e][i][j] += sum over rows m of chunk: A[m][i] * B[m][j]
 // ------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// COLSUM: the B tile gets one more 64-column chunk that holds the constant 1.0 (written once, never touched by TMA) and
+// the j == 0 work items run their MMAs 16 columns wider, so accumulator column BN of row i is sum_m A[m][i]: the
+// column sums of A (the conv-bias gradients, A = dPre) come out of the tensor cores for free instead of a
+// 31-shuffle transpose-reduction per 32x32 chunk in the epilogue of the GEMM that produced A.
+template <int BN, int STAGES, bool COLSUM = false>
 __global__ void __launch_bounds__(256, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const WgradArgs a) {
     using S = GemmSmem<BN, STAGES>;
     static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 (MN-major SW128 chunks)");
+    static_assert(!COLSUM || BN <= 192, "the ones chunk needs 16 accumulator columns behind BN");
     constexpr int NB_CHUNKS = BN / 64;
+    constexpr int B_STAGE = (NB_CHUNKS + (COLSUM ? 1 : 0)) * 8192;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * S::A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (S::A_BYTES + B_STAGE));
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -409,6 +416,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (COLSUM) {   // bf16 1.0 in the extra chunk of every stage
+        for (int st = 0; st < STAGES; ++st) {
+            uint8_t* ones = sB + st * B_STAGE + NB_CHUNKS * 8192;
+            for (int i = threadIdx.x * 16; i < 8192; i += 256 * 16)
+                *reinterpret_cast<uint4*>(ones + i) = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        }
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -430,7 +445,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], S::A_BYTES + NB_CHUNKS * 8192);
                 uint8_t* dA = sA + stage * S::A_BYTES;
-                uint8_t* dB = sB + stage * S::B_BYTES;
+                uint8_t* dB = sB + stage * B_STAGE;
                 const int r = row0 + kb * 64;
                 tma_load_2d(dA, &tmA, &full[stage], it * 128, r);
                 tma_load_2d(dA + 8192, &tmA, &full[stage], it * 128 + 64, r);
@@ -441,7 +456,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     } else if (threadIdx.x == 32) {
-        constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, 1, 1);
+        constexpr uint32_t idesc_plain = make_idesc_bf16(TILE_M, BN, 1, 1);
+        constexpr uint32_t idesc_wide = make_idesc_bf16(TILE_M, BN + 16, 1, 1);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -449,6 +465,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int4 ch = a.chunks[a.chunk_begin + c];
             if (ch.z <= 0) continue;
             const int num_kb = ch.z * 2;
+            const uint32_t idesc = (COLSUM && (w - c * per_chunk) % a.n_j == 0) ? idesc_wide : idesc_plain;
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 256;
@@ -456,7 +473,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + stage * S::B_BYTES);
+                const uint32_t b_addr = smem_u32(sB + stage * B_STAGE);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // 16 k-rows per MMA = 2048 B; 64-element MN chunks are 8192 B apart (LBO),
@@ -503,6 +520,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                 }
+            }
+            if (COLSUM && jt == 0) {      // accumulator column BN = sum over the chunk's rows of A[row, i]
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + BN, v);
+                tmem_ld_wait();
+                if (i < a.N1) atomicAdd(a.colsum + static_cast<size_t>(ch.x) * a.N1 + i, __uint_as_float(v[0]));
             }
             tc_fence_before();
             __syncwarp();

@@ -141,6 +141,7 @@ class _ExpertsFunction(torch.autograd.Function):
         dglobal32 = dglobal.float().contiguous() if dglobal is not None else None
 
         W1T = ops.transpose_cast_bf16(W1_32.float()).view(E * D, H)          # [E, D, H]
+        # conv bias gradients = column sums of dPre: they come out of the dWp weight-gradient MMAs (ones block)
         dbp = [torch.zeros(E, D, dtype=torch.float32, device=dev) for _ in range(S)]
         if dfused is None and not ops.FORCE_GENERIC_COMBINE_BWD and ops.combine_bwd_global_supported(plan, D):
             # only global_feat has a cotangent: d fused / d Y is rank-1 per image and is rebuilt in the dY epilogue
@@ -151,15 +152,15 @@ class _ExpertsFunction(torch.autograd.Function):
                 r0, nr = layout.region_base[s], layout.region_rows[s]
                 ops.gemm_rows_rank1(dZ[r0:r0 + nr], W1T, D, dPre[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
                                     tile_count=layout.region_tiles[s], row_coef=row_coef[r0:r0 + nr], row_vec=row_img[r0:r0 + nr],
-                                    vecs=dglobal32, gate=Y[r0:r0 + nr], colsum=dbp[s], tag=f"dY.s{s}")
+                                    vecs=dglobal32, gate=Y[r0:r0 + nr], tag=f"dY.s{s}")
         else:
             dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
                                                             ctx.gate_needs_grad)
-            # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT; column sums -> conv bias gradients
+            # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT
             for s in range(S):
                 r0, nr = layout.region_base[s], layout.region_rows[s]
                 ops.gemm_rows(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
-                              tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr], colsum=dbp[s],
+                              tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr],
                               flags=ops.EPI_ZERO_PAD, tag=f"dY.s{s}")
             dPre = dUT
 
@@ -185,7 +186,7 @@ class _ExpertsFunction(torch.autograd.Function):
                 r0, nr = layout.region_base[s], layout.region_rows[s]
                 g = torch.zeros(E, D, widths[s], dtype=torch.float32, device=dev)
                 ops.gemm_wgrad(dPre[r0:r0 + nr], fs[s], g, plan, layout.chunk_base[s], layout.chunk_cap[s],
-                               layout.tile_base[s], tag=f"dWp.s{s}")
+                               layout.tile_base[s], tag=f"dWp.s{s}", colsum=dbp[s])
                 dWp.append(g)
             for e in range(E):
                 for s in range(S):

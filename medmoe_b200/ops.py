@@ -134,12 +134,18 @@ def gemm_rows_rank1(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor,
 
 
 def gemm_wgrad(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, plan: DispatchPlan, chunk_begin: int,
-               chunk_count: int, tile_base: int, tag: str = ""):
-    """out[e] (+)= A_e^T B_e over the rows of expert e; out fp32 [E, N1, N2] must be pre-zeroed."""
-    _need_cuda(A, Bm, out)
-    _lib.call("mm_grouped_gemm_wgrad", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(Bm), Bm.shape[0], Bm.shape[1],
-              Bm.stride(0), _P(plan.chunks), chunk_begin, chunk_count, tile_base, _P(out), _st(),
-              label=f"{tag}:gemm_wgrad[N1={A.shape[1]},N2={Bm.shape[1]}]")
+               chunk_count: int, tile_base: int, tag: str = "", colsum: Optional[torch.Tensor] = None):
+    """out[e] (+)= A_e^T B_e over the rows of expert e; out fp32 [E, N1, N2] must be pre-zeroed.
+    colsum (fp32 [E, N1], pre-zeroed): also accumulate the column sums of A per expert (bias gradient)."""
+    _need_cuda(A, Bm, out, colsum)
+    if colsum is None:
+        _lib.call("mm_grouped_gemm_wgrad", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(Bm), Bm.shape[0], Bm.shape[1],
+                  Bm.stride(0), _P(plan.chunks), chunk_begin, chunk_count, tile_base, _P(out), _st(),
+                  label=f"{tag}:gemm_wgrad[N1={A.shape[1]},N2={Bm.shape[1]}]")
+    else:
+        _lib.call("mm_grouped_gemm_wgrad_colsum", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(Bm), Bm.shape[0],
+                  Bm.shape[1], Bm.stride(0), _P(plan.chunks), chunk_begin, chunk_count, tile_base, _P(out), _P(colsum), _st(),
+                  label=f"{tag}:gemm_wgrad[N1={A.shape[1]},N2={Bm.shape[1]}]")
     return out
 
 
