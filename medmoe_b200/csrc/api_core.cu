@@ -12,6 +12,10 @@
 #include <string>
 #include <vector>
 
+#ifndef MM_EPI_WARPS_PLAIN
+#define MM_EPI_WARPS_PLAIN 16
+#endif
+
 namespace mm {
 
 static thread_local char g_err[512] = "";
@@ -128,11 +132,15 @@ struct RowsMaps { CUtensorMap a, b, out, aux, gate; };
 
 template <int BN, bool OUT_F32, int AUX>
 static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
+    // plain bf16 epilogues are bound by the latency of their TMEM -> registers -> staging -> TMA-store chain: sixteen
+    // epilogue warps (four per scheduler, one staging slot each) hide it; aux/gate epilogues keep eight (their prefetch
+    // slots take the shared memory) as does the fp32-output path.
+    constexpr int EW = (AUX == 0 && !OUT_F32 && BN >= 128) ? MM_EPI_WARPS_PLAIN : 8;
     // smem: pipeline stages + output staging (32 KB, or 16 KB + 64 KB aux/gate staging) must fit 227 KB
     constexpr int STAGES = AUX ? ((BN > 128) ? 3 : 4) : ((BN > 192) ? 4 : (BN > 128 ? 4 : 5));
-    using S = GemmSmem<BN, STAGES, AUX>;
+    using S = GemmSmem<BN, STAGES, AUX, EW>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
-    auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32, AUX>;
+    auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32, AUX, EW>;
     static bool configured = false;   // benign race: attribute set is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -145,7 +153,7 @@ static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t
     const int work = args.tile_count * args.n_tiles;
     const int grid = work < sm_count() ? work : sm_count();
     if (grid <= 0) return MM_OK;
-    kern<<<grid, ROWS_THREADS, S::TOTAL, st>>>(m.a, m.b, m.out, m.aux, m.gate, args);
+    kern<<<grid, rows_threads(EW), S::TOTAL, st>>>(m.a, m.b, m.out, m.aux, m.gate, args);
     note_launches(1);
     return check_launch("gemm_rows");
 }

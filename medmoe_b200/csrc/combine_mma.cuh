@@ -309,4 +309,313 @@ static inline size_t cm_smem_bytes(const CmArgs& c, bool out_f32) {
            (out_f32 ? 0 : CM_EPI_WARPS * 2 * EPI_SLOT_BYTES) + (2 * CM_STAGES + 2 * CM_ACC + 2) * 8 + 16 + 1024;
 }
 
+
+// =======================================================================================
+// Forward pass 1 on the tensor cores: logits over scales + softmax -> beta.
+//
+//   logit_s(p) = w2 . ReLU(interp(Z_s)(p)) + b2,   beta = softmax_s(logit)      (reference swin.py:63-68, with the
+//   first Linear already applied at native resolution: Z = Y W1^T + b1)
+//
+// The lerp is a matrix product again: U_s[128 tokens, H] = L_s[128, cap_s] * Zrows_s[cap_s, H] with L_s the pure
+// lerp-weight matrix (2 non-zeros per row, k / 128 values: exact in bf16; identity for the finest scale).  The scales
+// must stay separate (the ReLU sits between the lerp and the dot with w2), so a tile runs 4 MMAs groups per column
+// pass into separate TMEM accumulators and the epilogue reduces each accumulator row with max/fma against w2:
+// 2 CUDA-core instructions per interpolated element instead of ~6 (unpack, 2 lerp FMAs, max, fma + shuffles).
+//
+// Roles (512 threads) as in cm_out_kernel.  Stages alternate {finest-scale rows} / {coarse rows of the 3 other scales}
+// of one column pass.  Requirements: those of cm_geometry plus H = D / 2 a multiple of 128 or 192.
+// =======================================================================================
+constexpr int CL_STAGES = 3;
+constexpr int CL_ACC_COLS = 256;       // TMEM columns per accumulator slot (2 slots)
+
+struct ClArgs {
+    int n_tiles;
+    const int2* tile_info;
+    int region_row0;
+    const int* seg_start;
+    const int* offsets;
+    int K;
+    int H, HB, n_half;           // hidden width, columns per pass (<= 192), passes per scale
+    int cap[4], koff[4], kc;     // coarse scales 1..3: rows staged (multiple of 16), first k, total
+};
+
+MM_DEVINL float4 cl_softmax4(float l0, float l1, float l2, float l3) {
+    const float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx), e3 = expf(l3 - mx);
+    const float inv = 1.0f / (e0 + e1 + e2 + e3);
+    return make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
+}
+
+__global__ void __launch_bounds__(CM_THREADS, 1)
+cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant__ CUtensorMap tmZ1,
+                 const __grid_constant__ CUtensorMap tmZ2, const __grid_constant__ CUtensorMap tmZ3,
+                 const CombineArgs a, const ClArgs c) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = c.HB * 256;                          // 128 rows x HB columns of bf16
+    const int ac_bytes = ((c.kc + 63) / 64) * 16384;
+    uint8_t* sAi = smem;                                         // identity, 128 x 128 (two 64-wide k blocks)
+    uint8_t* sAc = sAi + 32768;                                  // coarse lerp weights, 128 x kc
+    uint8_t* sB = sAc + ac_bytes;
+    float* s_w2 = reinterpret_cast<float*>(sB + CL_STAGES * stage_bytes);          // [H] of the current expert
+    float4* s_x = reinterpret_cast<float4*>(s_w2 + c.H);                           // [2 tile parities][128 tokens]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * TILE_M);
+    uint64_t* empty = full + CL_STAGES;
+    uint64_t* tfull = empty + CL_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* a_full = tempty + 2;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { tma_prefetch_desc(&tmZ0); tma_prefetch_desc(&tmZ1); tma_prefetch_desc(&tmZ2); tma_prefetch_desc(&tmZ3); }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CM_EPI_WARPS); }
+        mbar_init(a_full, CM_COEF_WARPS);
+        mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    for (int i = threadIdx.x * 16; i < 32768 + ac_bytes; i += CM_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < TILE_M) *reinterpret_cast<__nv_bfloat16*>(sAi + cm_a_off(threadIdx.x, threadIdx.x)) = __float2bfloat16_rn(1.0f);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_chunk64 = c.HB / 64;
+
+    if (threadIdx.x == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int e = c.tile_info[t].x;
+            if (e < 0) continue;
+            const int row0 = c.region_row0 + t * TILE_M;
+            const int rel0 = row0 - c.seg_start[e];
+            int row_s[4];
+            row_s[0] = row0;
+#pragma unroll
+            for (int s = 1; s < 4; ++s) row_s[s] = c.seg_start[s * c.K + e] + rel0 / a.ratio[s] - 1;
+            for (int h = 0; h < c.n_half; ++h) {
+                // finest scale: 128 rows x HB columns
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], static_cast<uint32_t>(TILE_M * c.HB * 2));
+                uint8_t* dst = sB + stage * stage_bytes;
+                for (int ch = 0; ch < n_chunk64; ++ch)
+                    tma_load_2d(dst + ch * (TILE_M * 128), &tmZ0, &full[stage], h * c.HB + ch * 64, row_s[0]);
+                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                // coarse scales: kc rows x HB columns
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], static_cast<uint32_t>(c.kc * c.HB * 2));
+                dst = sB + stage * stage_bytes;
+                for (int ch = 0; ch < n_chunk64; ++ch) {
+                    uint8_t* d = dst + ch * (c.kc * 128);
+                    const int col = h * c.HB + ch * 64;
+                    tma_load_2d(d + c.koff[1] * 128, &tmZ1, &full[stage], col, row_s[1]);
+                    tma_load_2d(d + c.koff[2] * 128, &tmZ2, &full[stage], col, row_s[2]);
+                    tma_load_2d(d + c.koff[3] * 128, &tmZ3, &full[stage], col, row_s[3]);
+                }
+                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_bf16(TILE_M, c.HB, 0, 1);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t a_phase = 0;
+        const uint32_t ai_addr = smem_u32(sAi), ac_addr = smem_u32(sAc);
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            if (c.tile_info[t].x < 0) continue;
+            mbar_wait(a_full, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+            for (int h = 0; h < c.n_half; ++h) {
+                // ---- finest scale: identity x Z_0 tile ----
+                mbar_wait(&full[stage], phase);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                {
+                    const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
+                    const uint32_t d_tmem = tmem_base + acc * CL_ACC_COLS;
+                    for (int j = 0; j < TILE_M / 16; ++j)
+                        umma_bf16(d_tmem, make_smem_desc(ai_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
+                                  make_smem_desc(b_addr + j * 2048, TILE_M * 128, 1024), idesc, j != 0);
+                    umma_commit(&empty[stage]);
+                    umma_commit(&tfull[acc]);
+                }
+                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                // ---- coarse scales ----
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
+                for (int s = 1; s < 4; ++s) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * CL_ACC_COLS;
+                    const int j0 = c.koff[s] >> 4, j1 = (c.koff[s] + c.cap[s]) >> 4;
+                    for (int j = j0; j < j1; ++j)
+                        umma_bf16(d_tmem, make_smem_desc(ac_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
+                                  make_smem_desc(b_addr + j * 2048, static_cast<uint32_t>(c.kc) * 128u, 1024), idesc, j != j0);
+                    if (s == 3) umma_commit(&empty[stage]);
+                    umma_commit(&tfull[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(a_empty);
+        }
+    } else if (warp >= 4 && warp < 4 + CM_COEF_WARPS) {
+        // ===================== lerp-weight builders: thread = token m of the tile =====================
+        const int m = (warp - 4) * 32 + lane;
+        uint32_t a_phase = 0;
+        uint32_t offa[4], offb[4];
+        int q0[4];
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const int r = a.ratio[s];
+            q0[s] = cm_floor_div(2 * m + 1 - r, 2 * r) + 1;
+            offa[s] = cm_a_off(m, c.koff[s] + q0[s]);
+            offb[s] = cm_a_off(m, c.koff[s] + q0[s] + 1);
+        }
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int2 ti = c.tile_info[t];
+            const int e = ti.x;
+            if (e < 0) continue;
+            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m < ti.y) {
+                const int rel0 = c.region_row0 + t * TILE_M - c.seg_start[e];
+                const int rel = rel0 + m;
+                const int j = rel / a.P, p = rel - j * a.P;
+                const int slot = c.offsets[e] + j;
+#pragma unroll
+                for (int s = 1; s < 4; ++s) {
+                    const int r = a.ratio[s];
+                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                    const int fs = c.seg_start[s * c.K + e] + rel0 / r - 1;
+                    const int base = a.slot_row[s * a.n_items + slot];
+                    const int qa = base + L.i0 - fs, qb = base + L.i1 - fs;
+                    va[s] = (qa == q0[s] ? 1.0f - L.lam : 0.f) + (qb == q0[s] ? L.lam : 0.f);
+                    vb[s] = (qa == q0[s] + 1 ? 1.0f - L.lam : 0.f) + (qb == q0[s] + 1 ? L.lam : 0.f);
+                }
+            }
+            mbar_wait(a_empty, a_phase ^ 1);
+            a_phase ^= 1;
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+                *reinterpret_cast<__nv_bfloat16*>(sAc + offa[s]) = __float2bfloat16_rn(va[s]);
+                *reinterpret_cast<__nv_bfloat16*>(sAc + offb[s]) = __float2bfloat16_rn(vb[s]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    } else if (warp >= 4 + CM_COEF_WARPS) {
+        // ===================== epilogue: row-wise w2 . ReLU(.) over the accumulator, then the softmax over scales =====================
+        const int q = warp & 3;
+        const int ew = warp - 4 - CM_COEF_WARPS;
+        const int hsel = ew >> 2;                    // column chunks hsel, hsel + 2, ... of every pass
+        const int n_ch = c.HB / 32;
+        const int epi_tid = threadIdx.x - (4 + CM_COEF_WARPS) * 32;
+        int acc = 0; uint32_t acc_phase = 0;
+        int cur_e = -1;
+        uint32_t parity = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int2 ti = c.tile_info[t];
+            const int e = ti.x;
+            if (e < 0) continue;
+            if (e != cur_e) {        // (re)load this expert's w2: every epilogue warp sees the same tile sequence
+                named_bar_sync(1, CM_EPI_WARPS * 32);
+                for (int i = epi_tid; i < c.H; i += CM_EPI_WARPS * 32) s_w2[i] = a.w2[static_cast<size_t>(e) * c.H + i];
+                named_bar_sync(1, CM_EPI_WARPS * 32);
+                cur_e = e;
+            }
+            float lg[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int h = 0; h < c.n_half; ++h) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    mbar_wait(&tfull[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t t_row = tmem_base + acc * CL_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+                    float part = 0.f;
+#pragma unroll 1
+                    for (int cc = hsel; cc < n_ch; cc += 2) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_row + cc * 32, v);
+                        const float4* wp = reinterpret_cast<const float4*>(s_w2 + h * c.HB + cc * 32);
+                        float4 w[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) w[k] = wp[k];
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 0]), 0.f), w[k].x, part);
+                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 1]), 0.f), w[k].y, part);
+                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 2]), 0.f), w[k].z, part);
+                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 3]), 0.f), w[k].w, part);
+                        }
+                    }
+                    lg[s] += part;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+            // the two warps of a lane quarter hold the two column halves of the same 32 tokens
+            float4* xs = s_x + parity * TILE_M + q * 32 + lane;
+            if (hsel == 1) *xs = make_float4(lg[0], lg[1], lg[2], lg[3]);
+            named_bar_sync(1, CM_EPI_WARPS * 32);
+            if (hsel == 0) {
+                const int m = q * 32 + lane;
+                if (m < ti.y) {
+                    const float4 o = *xs;
+                    const float b2 = a.b2[e];
+                    const int rel = c.region_row0 + t * TILE_M - c.seg_start[e] + m;
+                    const int j = rel / a.P, p = rel - j * a.P;
+                    const int slot = c.offsets[e] + j;
+                    *reinterpret_cast<float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4) =
+                        cl_softmax4(lg[0] + o.x + b2, lg[1] + o.y + b2, lg[2] + o.z + b2, lg[3] + o.w + b2);
+                }
+            }
+            parity ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// K layout of the coarse scales; false when the tensor-core logits kernel does not apply
+static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
+    CmArgs tmp{};
+    if (!cm_geometry(a, D, tmp)) return false;
+    const int H = D / 2;
+    c.H = H;
+    if (H % 192 == 0) c.HB = 192;
+    else if (H % 128 == 0) c.HB = 128;
+    else return false;
+    c.n_half = H / c.HB;
+    int off = 0;
+    c.cap[0] = TILE_M; c.koff[0] = 0;
+    for (int s = 1; s < 4; ++s) {
+        const int r = a.P / a.Ps[s];
+        c.cap[s] = ((TILE_M / r + 2 + 15) / 16) * 16;
+        c.koff[s] = off;
+        off += c.cap[s];
+    }
+    c.kc = off;
+    return off <= TILE_M;       // the coarse rows share a stage sized for 128 rows
+}
+
+static inline size_t cl_smem_bytes(const ClArgs& c) {
+    return 32768 + static_cast<size_t>((c.kc + 63) / 64) * 16384 + static_cast<size_t>(CL_STAGES) * c.HB * 256 +
+           static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 4 + 2) * 8 + 16 + 1024;
+}
+
 }  // namespace mm

@@ -68,17 +68,16 @@ struct WgradArgs {
 };
 
 constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
-constexpr int EPI_WARPS = 8;               // epilogue warps of gemm_rows_kernel
-constexpr int ROWS_THREADS = (4 + EPI_WARPS) * 32;
+constexpr int rows_threads(int epi_warps) { return (4 + epi_warps) * 32; }   // gemm_rows_kernel: 4 role warps + epilogue warps
 
 // AUX: 0 = plain epilogue, 1 = out = (acc + aux) * [gate > 0] with aux/gate tiles TMA-prefetched,
 //      2 = same with aux given as a rank-1 product (only the gate tile is loaded)
-template <int BN, int STAGES, int AUX = 0>
+template <int BN, int STAGES, int AUX = 0, int EPI_WARPS = 8>
 struct GemmSmem {
     static constexpr int A_BYTES = TILE_M * 64 * 2;                 // 16 KB: 128 rows x 64 bf16 (K-major) or 2 x (64 k-rows x 64 mn)
     static constexpr int B_BYTES = ((BN + 63) / 64) * 64 * 64 * 2;   // BN rounded up to 64-wide chunks
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int OUT_SLOTS = AUX ? 1 : 2;                                   // output staging slots per epilogue warp
+    static constexpr int OUT_SLOTS = (AUX || EPI_WARPS > 8) ? 1 : 2;                // output staging slots per epilogue warp
     static constexpr int EPI_OUT_BYTES = EPI_WARPS * OUT_SLOTS * EPI_SLOT_BYTES;
     static constexpr int EPI_IN_BYTES = AUX ? EPI_WARPS * 2 * 2 * EPI_SLOT_BYTES : 0;   // double-buffered {aux, gate}
     static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
@@ -98,12 +97,13 @@ MM_DEVINL uint32_t epi_slot_off(int r, int j) { return static_cast<uint32_t>(r *
 // ------------------------------------------------------------------------------------
 // gemm_rows_kernel
 // ------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool OUT_F32, int AUX>
-__global__ void __launch_bounds__(ROWS_THREADS, 1)
+template <int BN, int STAGES, bool OUT_F32, int AUX, int EPI_WARPS>
+__global__ void __launch_bounds__(rows_threads(EPI_WARPS), 1)
 gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                  const __grid_constant__ CUtensorMap tmGate, const RowsGemmArgs a) {
-    using S = GemmSmem<BN, STAGES, AUX>;
+    using S = GemmSmem<BN, STAGES, AUX, EPI_WARPS>;
+    static_assert(EPI_WARPS % 4 == 0, "epilogue warps come in groups of four (one per TMEM lane quarter)");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 in [32, 256]");
     static_assert(BN % 16 == 0, "UMMA N constraint for M = 128");
     extern __shared__ uint8_t smem_raw[];
