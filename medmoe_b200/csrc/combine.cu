@@ -1660,6 +1660,26 @@ static int cm_launch_out(CombineArgs& a, CmArgs& c, int D, long long total_rows,
     return MM_OK;
 }
 
+// tensor-core logits + softmax (combine_mma.cuh): 0 = launched, 1 = does not apply, < 0 = error
+static int cm_launch_logits(CombineArgs& a, ClArgs& c, int D, long long total_rows, cudaStream_t st) {
+    if (!c.tile_info || !c.seg_start || !c.offsets || !cl_geometry(a, D, c)) return 1;
+    for (int s = 0; s < 4; ++s) a.ratio[s] = a.P / a.Ps[s];
+    const size_t smem = cl_smem_bytes(c);
+    if (smem > 227 * 1024) return 1;
+    CUtensorMap tmZ[4];
+    for (int s = 0; s < 4; ++s) {
+        int rc = mm::encode_tmap_bf16(&tmZ[s], a.Z, static_cast<uint64_t>(c.H), static_cast<uint64_t>(total_rows),
+                                      static_cast<uint64_t>(c.H), 64, static_cast<uint32_t>(c.cap[s]), "combine_logits(Z)");
+        if (rc) return rc;
+    }
+    auto kern = cm_logits_kernel;
+    if (int rc = opt_in_smem(kern, smem, "combine_logits(mma)")) return rc;
+    const int grid = c.n_tiles < mm::sm_count() ? c.n_tiles : mm::sm_count();
+    kern<<<grid, CM_THREADS, smem, st>>>(tmZ[0], tmZ[1], tmZ[2], tmZ[3], a, c);
+    mm::note_launches(1);
+    return MM_OK;
+}
+
 extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const float* w2, const float* b2, int B, int topk,
                                              int P, const int32_t* Ps, int D, const int32_t* inv_perm,
                                              const int32_t* slot_expert, const int32_t* slot_row, const float* gate,
@@ -1680,7 +1700,17 @@ extern "C" int mm_interp_softmax_combine_fwd(const void* Y, const void* Z, const
     sg_setup_tiles(a, 32);
     mm::trace_mark("begin", st);
     int staged = 1;
-    switch (D) {
+    {   // logits + softmax on the tensor cores when the geometry allows it
+        ClArgs cl{};
+        cl.n_tiles = n_tiles0;
+        cl.tile_info = reinterpret_cast<const int2*>(tile_info0);
+        cl.region_row0 = region0_row;
+        cl.seg_start = seg_start; cl.offsets = offsets; cl.K = K;
+        const int mma = (flags & 1) ? 1 : cm_launch_logits(a, cl, D, total_rows, st);
+        if (mma < 0) return mma;
+        if (mma == 0) staged = 0;
+    }
+    if (staged != 0) switch (D) {
         case 256: staged = sg_launch_logits<256>(a, st); break;
         case 512: staged = sg_launch_logits<512>(a, st); break;
         case 768: staged = sg_launch_logits<768>(a, st); break;

@@ -594,7 +594,9 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
 // K layout of the coarse scales; false when the tensor-core logits kernel does not apply
 static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
     CmArgs tmp{};
-    if (!cm_geometry(a, D, tmp)) return false;
+    CombineArgs one = a;
+    one.topk = 1;                 // beta is per (image, choice) slot: the logits kernel does not care about top-k
+    if (!cm_geometry(one, D, tmp)) return false;
     const int H = D / 2;
     c.H = H;
     if (H % 192 == 0) c.HB = 192;
