@@ -23,6 +23,20 @@ void note_launches(int n);
 // optional per-kernel timing inside composite entry points: one CUDA event per mark; the time between two
 // consecutive marks on a stream is attributed to the later mark's name ("begin" restarts the chain)
 void trace_mark(const char* name, cudaStream_t st);
+// generic strided fp32 GEMM used by the loss and router kernels (loss.cu):
+//   C[m, n] = alpha * den(m, n) * sum_k A(m, k) B(k, n) + rs[m] * X[m, n]
+//   A(m, k) = A[m * sam + k * sak],  B(k, n) = B[k * sbk + n * sbn];  den = 1 / max(na[m] nb[n], eps) when na != nullptr
+struct SgemmArgs {
+    const float* A; long long sam, sak;
+    const float* B; long long sbk, sbn;
+    float* C; long long ldc;
+    int M, N, K;
+    float alpha;
+    const float* alpha_dev;  // optional device scalar multiplied into alpha (exp(logit_scale))
+    const float* na; const float* nb; float eps;
+    const float* rs; const float* X; long long ldx;
+};
+int run_sgemm(const SgemmArgs& a, cudaStream_t st, const char* what);
 }  // namespace mm
 
 #define MM_REQUIRE(cond, code, msg)        \

@@ -19,63 +19,55 @@ namespace mm {
 //   den(m, n) = 1 / max(na[m] * nb[n], eps) when na != nullptr, else 1
 // 64x64x16 tiles, 256 threads, 4x4 outputs per thread.
 // ------------------------------------------------------------------------------------
-struct SgemmArgs {
-    const float* A; long long sam, sak;
-    const float* B; long long sbk, sbn;
-    float* C; long long ldc;
-    int M, N, K;
-    float alpha;
-    const float* alpha_dev;  // optional device scalar multiplied into alpha (exp(logit_scale))
-    const float* na; const float* nb; float eps;
-    const float* rs; const float* X; long long ldx;
-};
-
+// T x T outputs per thread, 16 x 16 threads: tile = 16 T (64 x 64 for T = 4; 32 x 32 for T = 2, used when the
+// 64-wide grid would leave most of the 148 SMs idle, e.g. the 256 x 256 single-rank logits).
+template <int T>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
-    __shared__ float As[16][68];
-    __shared__ float Bs[16][68];
+    constexpr int TILE = 16 * T;
+    __shared__ __align__(16) float As[16][TILE + 4];
+    __shared__ __align__(16) float Bs[16][TILE + 4];
     const int t = threadIdx.x;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
     const int ty = t >> 4, tx = t & 15;
-    float acc[4][4];
+    float acc[T][T];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < T; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
 
     for (int k0 = 0; k0 < a.K; k0 += 16) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < T; ++j) {
             int m, k;
-            if (a.sak == 1) { k = t & 15; m = (t >> 4) + 16 * j; } else { m = t & 63; k = (t >> 6) + 4 * j; }
+            if (a.sak == 1) { k = t & 15; m = (t >> 4) + 16 * j; } else { m = t % TILE; k = t / TILE + (256 / TILE) * j; }
             const int gm = m0 + m, gk = k0 + k;
             As[k][m] = (gm < a.M && gk < a.K) ? a.A[gm * a.sam + gk * a.sak] : 0.f;
             int n, kb;
-            if (a.sbk == 1) { kb = t & 15; n = (t >> 4) + 16 * j; } else { n = t & 63; kb = (t >> 6) + 4 * j; }
+            if (a.sbk == 1) { kb = t & 15; n = (t >> 4) + 16 * j; } else { n = t % TILE; kb = t / TILE + (256 / TILE) * j; }
             const int gn = n0 + n, gkb = k0 + kb;
             Bs[kb][n] = (gn < a.N && gkb < a.K) ? a.B[gkb * a.sbk + gn * a.sbn] : 0.f;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float ar[4] = {av.x, av.y, av.z, av.w};
-            const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+            float ar[T], br[T];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < T; ++i) { ar[i] = As[k][ty * T + i]; br[i] = Bs[k][tx * T + i]; }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
         __syncthreads();
     }
     const float alpha = a.alpha * (a.alpha_dev ? *a.alpha_dev : 1.0f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < T; ++i) {
+        const int m = m0 + ty * T + i;
         if (m >= a.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
+        for (int j = 0; j < T; ++j) {
+            const int n = n0 + tx * T + j;
             if (n >= a.N) continue;
             float v = acc[i][j];
             if (a.na) v = v / fmaxf(a.na[m] * a.nb[n], a.eps);
@@ -142,8 +134,10 @@ __global__ void __launch_bounds__(256) lse_cols_kernel(const float* __restrict__
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float mx = -INFINITY;
+#pragma unroll 8
     for (int r = 0; r < R; ++r) mx = fmaxf(mx, L[r * ld + c]);
     float s = 0.f;
+#pragma unroll 8
     for (int r = 0; r < R; ++r) s += expf(L[r * ld + c] - mx);
     lse[c] = mx + logf(s);
 }
@@ -267,10 +261,14 @@ zeroshot_kernel(const float* __restrict__ I, const float* __restrict__ T, int M,
     if (lane == 0) pred[m] = best_c;
 }
 
-static int run_sgemm(const SgemmArgs& a, cudaStream_t st, const char* what) {
+int run_sgemm(const SgemmArgs& a, cudaStream_t st, const char* what) {
     if (a.M <= 0 || a.N <= 0) return MM_OK;
-    dim3 grid((a.N + 63) / 64, (a.M + 63) / 64);
-    sgemm_kernel<<<grid, 256, 0, st>>>(a);
+    const int blocks64 = ((a.N + 63) / 64) * ((a.M + 63) / 64);
+    if (blocks64 >= 96) {
+        sgemm_kernel<4><<<dim3((a.N + 63) / 64, (a.M + 63) / 64), 256, 0, st>>>(a);
+    } else {      // small problem: quarter-size tiles put four times as many SMs to work
+        sgemm_kernel<2><<<dim3((a.N + 31) / 32, (a.M + 31) / 32), 256, 0, st>>>(a);
+    }
     mm::note_launches(1);
     return check_launch(what);
 }

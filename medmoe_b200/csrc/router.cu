@@ -31,15 +31,24 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
     for (int i = threadIdx.x; i < D; i += blockDim.x) sx[i] = x[static_cast<size_t>(b) * D + i];
     __syncthreads();
     // hidden: each warp owns 32 outputs; lanes stride the 768-long dot (coalesced W1 reads).
-    for (int o = warp * 32; o < warp * 32 + 32; ++o) {
+    // Four outputs at a time: four independent load -> FMA chains per lane keep the L2 latency of W1 covered.
+    for (int o = warp * 32; o < warp * 32 + 32; o += 4) {
         const float* w = W1 + static_cast<size_t>(o) * D;
-        float acc = 0.f;
-        for (int i = lane; i < D; i += 32) acc = fmaf(w[i], sx[i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float h = fmaxf(acc + b1[o], 0.f);
-            sh[o] = h;
-            hidden[static_cast<size_t>(b) * ROUTER_HID + o] = h;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int i = lane; i < D; i += 32) {
+            const float xv = sx[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(w[static_cast<size_t>(u) * D + i], xv, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float v = warp_sum(acc[u]);
+            if (lane == 0) {
+                const float h = fmaxf(v + b1[o + u], 0.f);
+                sh[o + u] = h;
+                hidden[static_cast<size_t>(b) * ROUTER_HID + o + u] = h;
+            }
         }
     }
     __syncthreads();
@@ -78,12 +87,12 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
     }
 }
 
-// Per image: dlogit = p * (dp - <p, dp>); dh = (dlogit W2) * [h > 0]; dx = dh W1.
+// Per image: dlogit = p * (dp - <p, dp>); dh = (dlogit W2) * [h > 0]   (dx = dh W1 and dW1 = dh^T x are sgemms).
 __global__ void __launch_bounds__(128)
 router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restrict__ probs,
                          const float* __restrict__ hidden, const float* __restrict__ W1,
                          const float* __restrict__ W2, int D, int K, float* __restrict__ dlogit,
-                         float* __restrict__ dhidden, float* __restrict__ dx) {
+                         float* __restrict__ dhidden) {
     __shared__ float sdl[ROUTER_MAX_K];
     __shared__ float sdh[ROUTER_HID];
     const int b = blockIdx.x;
@@ -105,15 +114,6 @@ router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restri
         sdh[o] = dh;
         dhidden[static_cast<size_t>(b) * ROUTER_HID + o] = dh;
     }
-    __syncthreads();
-    if (dx) {
-        for (int i = threadIdx.x; i < D; i += blockDim.x) {
-            float acc = 0.f;
-#pragma unroll 8
-            for (int o = 0; o < ROUTER_HID; ++o) acc = fmaf(sdh[o], W1[static_cast<size_t>(o) * D + i], acc);
-            dx[static_cast<size_t>(b) * D + i] = acc;
-        }
-    }
 }
 
 // out[r, c] = sum_b L[b, r] * R[b, c]   (dW = dOut^T * In, batch reduction, deterministic order)
@@ -124,6 +124,7 @@ batch_outer_kernel(const float* __restrict__ L, int ldl, const float* __restrict
     const int r = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     float acc = 0.f, accb = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b) {
         const float l = L[static_cast<size_t>(b) * ldl + r];
         accb += l;
@@ -155,10 +156,22 @@ extern "C" int mm_router_bwd(const float* dprobs, const float* probs, const floa
                              float* dx, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
     MM_REQUIRE(B > 0 && D > 0 && K > 0 && K <= ROUTER_MAX_K, MM_ERR_BAD_SHAPE, "mm_router_bwd: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    router_bwd_sample_kernel<<<B, 128, 0, st>>>(dprobs, probs, hidden, W1, W2, D, K, dlogit, dhidden, dx);
+    router_bwd_sample_kernel<<<B, 128, 0, st>>>(dprobs, probs, hidden, W1, W2, D, K, dlogit, dhidden);
     mm::note_launches(1);
-    // dW1[128, D] = dh^T x ; db1 = sum_b dh
-    batch_outer_kernel<<<dim3((D + 255) / 256, ROUTER_HID), 256, 0, st>>>(dhidden, ROUTER_HID, x, D, B, D, dW1, db1);
+    if (dx) {   // dx[B, D] = dh[B, 128] W1[128, D]
+        SgemmArgs g{};
+        g.A = dhidden; g.sam = ROUTER_HID; g.sak = 1; g.B = W1; g.sbk = D; g.sbn = 1; g.C = dx; g.ldc = D;
+        g.M = B; g.N = D; g.K = ROUTER_HID; g.alpha = 1.f;
+        if (int rc = run_sgemm(g, st, "mm_router_bwd(dx)")) return rc;
+    }
+    {           // dW1[128, D] = dh^T x   (batch reduction in a fixed order)
+        SgemmArgs g{};
+        g.A = dhidden; g.sam = 1; g.sak = ROUTER_HID; g.B = x; g.sbk = D; g.sbn = 1; g.C = dW1; g.ldc = D;
+        g.M = ROUTER_HID; g.N = D; g.K = B; g.alpha = 1.f;
+        if (int rc = run_sgemm(g, st, "mm_router_bwd(dW1)")) return rc;
+    }
+    // db1 = sum_b dh (C = 0: only the bias column of the batch reduction)
+    batch_outer_kernel<<<dim3(1, ROUTER_HID), 32, 0, st>>>(dhidden, ROUTER_HID, x, D, B, 0, dW1, db1);
     mm::note_launches(1);
     // dW2[K, 128] = dlogit^T h ; db2 = sum_b dlogit
     batch_outer_kernel<<<dim3(1, K), 256, 0, st>>>(dlogit, K, hidden, ROUTER_HID, B, ROUTER_HID, dW2, db2);

@@ -58,8 +58,11 @@ def make_layout(n_images: int, topk: int, num_experts: int, P: Sequence[int], ta
     for p in P:
         rows = _round_up(n_items * p, TILE_M) + num_experts * TILE_M
         tiles = rows // TILE_M
+        # wgrad chunks: enough of them to fill the SMs, few enough that the fp32 red.add traffic of their partial
+        # results stays small (small regions get proportionally fewer chunks)
+        want = target_chunks if tiles >= 1024 else max(8, target_chunks // 4)
         g = 1
-        while g * 2 <= max(1, tiles // target_chunks) and g < 64:
+        while g * 2 <= max(1, tiles // want) and g < 64:
             g *= 2
         cap = (tiles + g - 1) // g + num_experts
         region_rows.append(rows); region_base.append(row); region_tiles.append(tiles); tile_base.append(tile)
