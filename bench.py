@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256, help="pairs per GPU")
     ap.add_argument("--experts", type=int, default=4)
     ap.add_argument("--img", type=int, default=224)
+    ap.add_argument("--topk", type=int, default=1, help="experts per image (1 = the reference; 2 = BASELINE config 4 extension)")
     ap.add_argument("--loss", default="flava", choices=["flava", "gloria"])
     ap.add_argument("--local-grad", action="store_true", help="also feed a dense synthetic cotangent into local_feat")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
@@ -153,9 +154,10 @@ def run_cpu_baseline(args, steps, warmup):
 
 
 def config_dict(args, world):
-    return {"workload": f"cfg2: MoE block + global InfoNCE fwd/bwd, batch {args.batch}/GPU, {args.experts} experts top-1, "
+    name = "cfg2" if (args.experts == 4 and args.topk == 1 and args.img == 224) else "cfg4-like" if args.topk > 1 else "custom"
+    return {"workload": f"{name}: MoE block + global InfoNCE fwd/bwd, batch {args.batch}/GPU, {args.experts} experts top-{args.topk}, "
                         f"Swin-T stage features of a {args.img}^2 image ({'/'.join(map(str, token_counts(args.img)))} tokens), bf16",
-            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "experts": args.experts, "img": args.img,
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "experts": args.experts, "topk": args.topk, "img": args.img,
             "loss": args.loss, "local_cotangent": bool(args.local_grad),
             "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": "inputs+intermediates per step (> 5 GB) exceed the 126 MB L2; no explicit flush"}
@@ -207,7 +209,7 @@ def main():
     B, K = args.batch, args.experts
     Ps = token_counts(args.img)
     torch.manual_seed(0)
-    moe = medmoe_b200.MoE(num_experts=K).to(dev)
+    moe = medmoe_b200.MoE(num_experts=K, topk=args.topk).to(dev)
     loss_mod = (medmoe_b200.FLAVAGlobalContrastiveLoss() if args.loss == "flava" else medmoe_b200.GLORIAGlobalContrastiveLoss()).to(dev)
     params = [p for p in list(moe.parameters()) + list(loss_mod.parameters())]
 
@@ -397,7 +399,8 @@ def main():
 
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
-        R = B * sum(Ps)
+        Bi = B * args.topk                # (image, expert choice) items: the row space holds one set of rows per item
+        R = Bi * sum(Ps)
         H = D // 2
         P0 = Ps[0]
         peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -407,10 +410,10 @@ def main():
         flops, nbytes = {}, {}
         for s, (p, d_s) in enumerate(zip(Ps, HIDDEN)):
             for tag in ("E1", "dX", "dWp"):
-                flops[f"{tag}.s{s}"] = 2.0 * B * p * d_s * D
-                nbytes[f"{tag}.s{s}"] = B * p * (d_s + D) * 2
-            flops[f"dY.s{s}"] = 2.0 * B * p * H * D
-            nbytes[f"dY.s{s}"] = B * p * (H + 2 * D) * 2 + (B * p * D * 2 if args.local_grad else B * p * 8)
+                flops[f"{tag}.s{s}"] = 2.0 * Bi * p * d_s * D
+                nbytes[f"{tag}.s{s}"] = Bi * p * (d_s + D) * 2
+            flops[f"dY.s{s}"] = 2.0 * Bi * p * H * D
+            nbytes[f"dY.s{s}"] = Bi * p * (H + 2 * D) * 2 + (Bi * p * D * 2 if args.local_grad else Bi * p * 8)
         flops["E4"] = flops["dW1"] = 2.0 * R * D * H
         nbytes["E4"] = nbytes["dW1"] = R * (D + H) * 2
         rows_c = sum(Ps) - P0
@@ -426,7 +429,7 @@ def main():
             "mm_dispatch_rows": 2 * sum(p * d for p, d in zip(Ps, HIDDEN)) * 2,
             "mm_undispatch_rows": 2 * sum(p * d for p, d in zip(Ps, HIDDEN)) * 2,
         }.items():
-            nbytes[k] = v * B
+            nbytes[k] = v * Bi
         kernels = {}
         total_kernel_ms = sum(t for _, t in kern.values())
         for label, (n, t) in sorted(kern.items(), key=lambda kv: -kv[1][1]):

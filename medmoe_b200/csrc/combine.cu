@@ -525,511 +525,7 @@ MM_DEVINL bool row_pair_update(RowPair<NE>& c, const __nv_bfloat16* mat, long lo
     return two;
 }
 
-// ------------------------------------------------------------------------------------
-// forward, run-based (requires Ps[0] == P).
-//   pass 1  combine_logits_kernel : warp = 32-token run; per scale the 32 partial dots are reduced
-//           with one 31-shuffle transpose-reduction; lane t ends up with the 4 logits of token t,
-//           applies the softmax over scales and writes beta coalesced.
-//   pass 2  combine_out_kernel    : warp = (run, column half); beta comes in by one coalesced load
-//           + shuffle broadcast, coarse Y rows live in registers, one 8-byte load per 4 channels.
-// ------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
-combine_logits_kernel(const CombineArgs a) {
-    constexpr int NE = D / 256;
-    constexpr int E = NE * 4;
-    constexpr int H = D / 2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 8 + warp;
-    if (c >= a.nruns) return;
-    const int item = blockIdx.y;
-    const int slot = a.inv_perm[item];
-    const int e = a.slot_expert[slot];
-    const int t0 = c * RUN_TOKENS;
-    float w2[E];
-    load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
-    const float b2 = a.b2[e];
-    float lg0 = 0.f, lg1 = 0.f, lg2 = 0.f, lg3 = 0.f;
-    for (int s = 0; s < 4; ++s) {
-        const long long base = a.slot_row[s * a.n_items + slot];
-        const int Ps = a.Ps[s];
-        const float scale = a.scale[s];
-        RowPair<NE> z;
-        float part[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const int p = t0 + t;
-            float acc = 0.f;
-            if (p < a.P) {
-                const LerpSrc L = lerp_src(p, scale, Ps);
-                const bool two = row_pair_update<NE>(z, a.Z, base, H, L, lane);
-                const float l0 = 1.0f - L.lam;
-#pragma unroll
-                for (int k = 0; k < E; ++k) {
-                    const float h = two ? (l0 * z.a[k] + L.lam * z.b[k]) : z.a[k];
-                    acc = fmaf(fmaxf(h, 0.f), w2[k], acc);
-                }
-            }
-            part[t] = acc;
-        }
-        const float tot = warp_colsum32(part, lane) + b2;     // lane t: logit of token t0 + t at scale s
-        if (s == 0) lg0 = tot; else if (s == 1) lg1 = tot; else if (s == 2) lg2 = tot; else lg3 = tot;
-    }
-    const float mx = fmaxf(fmaxf(lg0, lg1), fmaxf(lg2, lg3));
-    const float e0 = expf(lg0 - mx), e1 = expf(lg1 - mx), e2 = expf(lg2 - mx), e3 = expf(lg3 - mx);
-    const float inv = 1.0f / (e0 + e1 + e2 + e3);
-    if (t0 + lane < a.P)
-        *reinterpret_cast<float4*>(a.beta + (static_cast<size_t>(slot) * a.P + t0 + lane) * 4) =
-            make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
-}
-
-constexpr int OUT_RUNS_PER_BLOCK = 4;   // 8 warps = 4 runs x 2 column halves
-
-template <int D, typename OutT>
-__global__ void __launch_bounds__(256, MM_COMBINE_MINBLOCKS)
-combine_out_kernel(const CombineArgs a) {
-    constexpr int NE = D / 256;
-    constexpr int E = NE * 4;
-    constexpr int H = D / 2;
-    __shared__ float s_g[OUT_RUNS_PER_BLOCK][D];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * OUT_RUNS_PER_BLOCK + (warp >> 1);
-    const int col0 = (warp & 1) * H;
-    const int b = blockIdx.y;
-    const int t0 = c * RUN_TOKENS;
-    float gsum[E];
-#pragma unroll
-    for (int k = 0; k < E; ++k) gsum[k] = 0.f;
-    if (c < a.nruns) {
-        const int n_tok = min(RUN_TOKENS, a.P - t0);
-        for (int jk = 0; jk < a.topk; ++jk) {
-            const int item = b * a.topk + jk;
-            const int slot = a.inv_perm[item];
-            const float g = a.gate ? a.gate[item] : 1.0f;
-            float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < n_tok) bl = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + t0 + lane) * 4);
-            long long base[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) base[s] = a.slot_row[s * a.n_items + slot];
-            RowPair<NE> y1, y2, y3;
-            float y0[E];
-            load_row_bf16x4<NE>(a.Y + (base[0] + t0) * D + col0, lane, y0);
-            for (int t = 0; t < n_tok; ++t) {
-                const int p = t0 + t;
-                float yn[E];     // next token's finest-scale row: issued before this token's math
-#pragma unroll
-                for (int k = 0; k < E; ++k) yn[k] = 0.f;
-                if (t + 1 < n_tok) load_row_bf16x4<NE>(a.Y + (base[0] + p + 1) * D + col0, lane, yn);
-                const float bt0 = __shfl_sync(0xffffffffu, bl.x, t) * g;
-                const float bt1 = __shfl_sync(0xffffffffu, bl.y, t) * g;
-                const float bt2 = __shfl_sync(0xffffffffu, bl.z, t) * g;
-                const float bt3 = __shfl_sync(0xffffffffu, bl.w, t) * g;
-                float o[E];
-#pragma unroll
-                for (int k = 0; k < E; ++k) o[k] = bt0 * y0[k];
-                {
-                    const LerpSrc L = lerp_src(p, a.scale[1], a.Ps[1]);
-                    const bool two = row_pair_update<NE>(y1, a.Y + col0, base[1], D, L, lane);
-                    const float c0 = bt1 * (1.0f - L.lam), c1 = bt1 * L.lam;
-#pragma unroll
-                    for (int k = 0; k < E; ++k) o[k] = two ? fmaf(c0, y1.a[k], fmaf(c1, y1.b[k], o[k])) : fmaf(bt1, y1.a[k], o[k]);
-                }
-                {
-                    const LerpSrc L = lerp_src(p, a.scale[2], a.Ps[2]);
-                    const bool two = row_pair_update<NE>(y2, a.Y + col0, base[2], D, L, lane);
-                    const float c0 = bt2 * (1.0f - L.lam), c1 = bt2 * L.lam;
-#pragma unroll
-                    for (int k = 0; k < E; ++k) o[k] = two ? fmaf(c0, y2.a[k], fmaf(c1, y2.b[k], o[k])) : fmaf(bt2, y2.a[k], o[k]);
-                }
-                {
-                    const LerpSrc L = lerp_src(p, a.scale[3], a.Ps[3]);
-                    const bool two = row_pair_update<NE>(y3, a.Y + col0, base[3], D, L, lane);
-                    const float c0 = bt3 * (1.0f - L.lam), c1 = bt3 * L.lam;
-#pragma unroll
-                    for (int k = 0; k < E; ++k) o[k] = two ? fmaf(c0, y3.a[k], fmaf(c1, y3.b[k], o[k])) : fmaf(bt3, y3.a[k], o[k]);
-                }
-#pragma unroll
-                for (int k = 0; k < E; ++k) gsum[k] += o[k];
-                OutT* orow = static_cast<OutT*>(a.out) + (static_cast<size_t>(b) * a.P + p) * D + col0;
-                if (jk > 0) {   // top-k extension: accumulate onto the previous choice's contribution
-                    float prev[E];
-                    load_slab<NE, OutT>(orow, lane, prev);
-#pragma unroll
-                    for (int k = 0; k < E; ++k) o[k] += prev[k];
-                }
-                if constexpr (sizeof(OutT) == 2) store_slab_bf16<NE>(reinterpret_cast<__nv_bfloat16*>(orow), lane, o);
-                else store_slab_f32<NE>(reinterpret_cast<float*>(orow), lane, o);
-#pragma unroll
-                for (int k = 0; k < E; ++k) y0[k] = yn[k];
-            }
-        }
-    }
-    // deterministic per-block partial of the global mean: [b, block, D]
-#pragma unroll
-    for (int t = 0; t < NE; ++t)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s_g[warp >> 1][col0 + 4 * (lane + 32 * t) + k] = gsum[4 * t + k];
-    __syncthreads();
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float acc = 0.f;
-#pragma unroll
-        for (int w = 0; w < OUT_RUNS_PER_BLOCK; ++w) acc += s_g[w][d];
-        a.gpart[(static_cast<size_t>(b) * a.nblk + blockIdx.x) * D + d] = acc;
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// TMA-staged persistent kernels (forward logits, forward combine, backward dbeta).
-//
-// One CTA per SM walks over (item, token-tile) work items.  A producer thread stages, per scale,
-// the contiguous range of native rows the tile touches with ONE bulk copy (cp.async.bulk ->
-// shared memory, completion on an mbarrier), several tiles ahead; eight consumer warps read rows
-// with conflict-free LDS.128 and never issue a dependent global load.  Loads in flight per SM are
-// set by the stage depth (~75 KB), not by registers or occupancy.
-// ------------------------------------------------------------------------------------
-constexpr int ST_CONSUMER_WARPS = 8;
-constexpr int ST_THREADS = (ST_CONSUMER_WARPS + 1) * 32;
-
-struct TileRows { int i_lo[4]; int n[4]; };
-MM_DEVINL TileRows tile_rows(const CombineArgs& a, int t0, int t1) {
-    TileRows r;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const LerpSrc A = lerp_src(t0, a.scale[s], a.Ps[s]);
-        const LerpSrc B = lerp_src(t1 - 1, a.scale[s], a.Ps[s]);
-        r.i_lo[s] = A.i0;
-        r.n[s] = B.i1 - A.i0 + 1;
-    }
-    return r;
-}
-
-// producer: stage the rows of tile (slot, [t0, t1)) of the [rows, W] bf16 matrix `mat`
-template <int W>
-MM_DEVINL void stage_tile(const CombineArgs& a, const __nv_bfloat16* mat, int slot, int t0, int t1, uint8_t* dst, uint64_t* bar,
-                          uint32_t extra_bytes) {
-    const TileRows r = tile_rows(a, t0, t1);
-    uint32_t bytes = extra_bytes;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) bytes += static_cast<uint32_t>(r.n[s]) * W * 2;
-    mbar_expect_tx(bar, bytes);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const long long row = static_cast<long long>(a.slot_row[s * a.n_items + slot]) + r.i_lo[s];
-        bulk_load_1d(dst + static_cast<size_t>(a.cap_off[s]) * W * 2, mat + row * W, static_cast<uint32_t>(r.n[s]) * W * 2, bar);
-    }
-}
-
-// a [W]-wide staged row in the x8 lane layout (lane owns 16-byte chunks lane, lane+32, ...)
-template <int N>
-MM_DEVINL void lds_row_x8(const uint8_t* row, int lane, float (&f)[N * 8]) {
-#pragma unroll
-    for (int t = 0; t < N; ++t) {
-        const uint4 u = *reinterpret_cast<const uint4*>(row + 16 * (lane + 32 * t));
-        f[8 * t + 0] = bf16lo(u.x); f[8 * t + 1] = bf16hi(u.x); f[8 * t + 2] = bf16lo(u.y); f[8 * t + 3] = bf16hi(u.y);
-        f[8 * t + 4] = bf16lo(u.z); f[8 * t + 5] = bf16hi(u.z); f[8 * t + 6] = bf16lo(u.w); f[8 * t + 7] = bf16hi(u.w);
-    }
-}
-template <int NE>
-MM_DEVINL void lds_row_x4(const uint8_t* row, int lane, float (&f)[NE * 4]) {
-#pragma unroll
-    for (int t = 0; t < NE; ++t) {
-        const uint2 u = *reinterpret_cast<const uint2*>(row + 8 * (lane + 32 * t));
-        f[4 * t + 0] = bf16lo(u.x); f[4 * t + 1] = bf16hi(u.x); f[4 * t + 2] = bf16lo(u.y); f[4 * t + 3] = bf16hi(u.y);
-    }
-}
-
-// ---- forward pass 1: logits over scales + softmax -> beta.  Work item = (item, tile); Z rows staged. ----
-template <int D, int STAGES>
-__global__ void __launch_bounds__(ST_THREADS, 1)
-combine_logits_staged_kernel(const CombineArgs a) {
-    constexpr int NE = D / 256;
-    constexpr int E = NE * 4;
-    constexpr int H = D / 2;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const size_t stage_bytes = static_cast<size_t>(a.cap_total) * H * 2;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-    uint64_t* empty = full + STAGES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const int total = a.n_items * a.tiles_per_img;
-    const int TT = a.tile_tokens;
-    if (warp == ST_CONSUMER_WARPS) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int slot = w / a.tiles_per_img, tt = w - slot * a.tiles_per_img;
-                const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
-                mbar_wait(&empty[stage], phase ^ 1);
-                stage_tile<H>(a, a.Z, slot, t0, t1, smem + stage * stage_bytes, &full[stage], 0);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
-        return;
-    }
-    int stage = 0; uint32_t phase = 0;
-    const int tok_per_warp = TT / ST_CONSUMER_WARPS;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int slot = w / a.tiles_per_img, tt = w - slot * a.tiles_per_img;
-        const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
-        const int e = a.slot_expert[slot];
-        float w2[E];
-        load_row_f32x4<NE>(a.w2 + static_cast<size_t>(e) * H, lane, w2);
-        const float b2 = a.b2[e];
-        const TileRows r = tile_rows(a, t0, t1);
-        mbar_wait(&full[stage], phase);
-        const uint8_t* st = smem + stage * stage_bytes;
-        for (int k = 0; k < tok_per_warp; ++k) {
-            const int p = t0 + warp * tok_per_warp + k;
-            if (p >= t1) break;
-            float lg[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
-                const uint8_t* ra = st + static_cast<size_t>(a.cap_off[s] + L.i0 - r.i_lo[s]) * H * 2;
-                float za[E];
-                lds_row_x4<NE>(ra, lane, za);
-                float acc = 0.f;
-                if (L.i1 != L.i0 && L.lam != 0.f) {
-                    float zb[E];
-                    lds_row_x4<NE>(ra + H * 2, lane, zb);
-                    const float l0 = 1.0f - L.lam;
-#pragma unroll
-                    for (int i = 0; i < E; ++i) acc = fmaf(fmaxf(l0 * za[i] + L.lam * zb[i], 0.f), w2[i], acc);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < E; ++i) acc = fmaf(fmaxf(za[i], 0.f), w2[i], acc);
-                }
-                lg[s] = warp_sum(acc) + b2;
-            }
-            const float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
-            const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx), e3 = expf(lg[3] - mx);
-            const float inv = 1.0f / (e0 + e1 + e2 + e3);
-            if (lane == 0)
-                *reinterpret_cast<float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4) =
-                    make_float4(e0 * inv, e1 * inv, e2 * inv, e3 * inv);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
-}
-
-// ---- forward pass 2: out = sum_s beta_s interp(Y_s); work item = (image, tile, top-k choice); Y rows staged. ----
-template <int D, typename OutT, int STAGES>
-__global__ void __launch_bounds__(ST_THREADS, 1)
-combine_out_staged_kernel(const CombineArgs a) {
-    constexpr int N = D / 256;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const size_t stage_bytes = static_cast<size_t>(a.cap_total) * D * 2;
-    float* s_g = reinterpret_cast<float*>(smem + STAGES * stage_bytes);          // [8 warps][D]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_g + ST_CONSUMER_WARPS * D);
-    uint64_t* empty = full + STAGES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const int total = a.B * a.tiles_per_img;       // (image, tile); the top-k choices are the inner pipeline items
-    const int TT = a.tile_tokens;
-    if (warp == ST_CONSUMER_WARPS) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
-                const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
-                for (int jk = 0; jk < a.topk; ++jk) {
-                    const int slot = a.inv_perm[b * a.topk + jk];
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    stage_tile<D>(a, a.Y, slot, t0, t1, smem + stage * stage_bytes, &full[stage], 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        return;
-    }
-    int stage = 0; uint32_t phase = 0;
-    const int tok_per_warp = TT / ST_CONSUMER_WARPS;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
-        const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
-        const TileRows r = tile_rows(a, t0, t1);
-        float gsum[N * 8];
-#pragma unroll
-        for (int i = 0; i < N * 8; ++i) gsum[i] = 0.f;
-        for (int jk = 0; jk < a.topk; ++jk) {
-            const int item = b * a.topk + jk;
-            const int slot = a.inv_perm[item];
-            const float g = a.gate ? a.gate[item] : 1.0f;
-            mbar_wait(&full[stage], phase);
-            const uint8_t* st = smem + stage * stage_bytes;
-            for (int k = 0; k < tok_per_warp; ++k) {
-                const int p = t0 + warp * tok_per_warp + k;
-                if (p >= t1) break;
-                const float4 bt4 = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
-                const float bt[4] = {bt4.x * g, bt4.y * g, bt4.z * g, bt4.w * g};
-                float o[N * 8];
-#pragma unroll
-                for (int i = 0; i < N * 8; ++i) o[i] = 0.f;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
-                    const uint8_t* ra = st + static_cast<size_t>(a.cap_off[s] + L.i0 - r.i_lo[s]) * D * 2;
-                    float ya[N * 8];
-                    lds_row_x8<N>(ra, lane, ya);
-                    if (L.i1 != L.i0 && L.lam != 0.f) {
-                        float yb[N * 8];
-                        lds_row_x8<N>(ra + D * 2, lane, yb);
-                        const float c0 = bt[s] * (1.0f - L.lam), c1 = bt[s] * L.lam;
-#pragma unroll
-                        for (int i = 0; i < N * 8; ++i) o[i] = fmaf(c0, ya[i], fmaf(c1, yb[i], o[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < N * 8; ++i) o[i] = fmaf(bt[s], ya[i], o[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < N * 8; ++i) gsum[i] += o[i];
-                OutT* orow = static_cast<OutT*>(a.out) + (static_cast<size_t>(b) * a.P + p) * D;
-                if (jk > 0) {   // top-k extension: add onto the previous choice's contribution (same thread wrote it)
-                    float prev[N * 8];
-                    load_row_x8<N, OutT>(orow, lane, prev);
-#pragma unroll
-                    for (int i = 0; i < N * 8; ++i) o[i] += prev[i];
-                }
-                store_row_x8<N, OutT>(orow, lane, o);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        // deterministic partial of the global mean: one [D] vector per (image, tile)
-#pragma unroll
-        for (int t = 0; t < N; ++t)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s_g[warp * D + 8 * (lane + 32 * t) + i] = gsum[8 * t + i];
-        named_bar_sync(1, ST_CONSUMER_WARPS * 32);
-        for (int d = threadIdx.x; d < D; d += ST_CONSUMER_WARPS * 32) {
-            float acc = 0.f;
-#pragma unroll
-            for (int ww = 0; ww < ST_CONSUMER_WARPS; ++ww) acc += s_g[ww * D + d];
-            a.gpart[(static_cast<size_t>(b) * a.nblk + tt) * D + d] = acc;
-        }
-        named_bar_sync(1, ST_CONSUMER_WARPS * 32);
-    }
-}
-
-// ---- backward pass A: dbeta_s = <dF, interp(Y_s)>, then the softmax-over-scales backward -> dlogit.
-// Work item = (image, tile, top-k choice); stage = Y rows of the tile [+ the dlocal rows of the tile].
-template <int D, typename OutT, int STAGES>
-__global__ void __launch_bounds__(ST_THREADS, 1)
-combine_bwd_logit_staged_kernel(const CombineArgs a) {
-    constexpr int N = D / 256;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    const int TT = a.tile_tokens;
-    const size_t y_bytes = static_cast<size_t>(a.cap_total) * D * 2;
-    const size_t df_bytes = a.dlocal ? static_cast<size_t>(TT) * D * sizeof(OutT) : 0;
-    const size_t stage_bytes = y_bytes + df_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-    uint64_t* empty = full + STAGES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const int total = a.B * a.tiles_per_img;
-    if (warp == ST_CONSUMER_WARPS) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x) {
-                const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
-                const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
-                for (int jk = 0; jk < a.topk; ++jk) {
-                    const int slot = a.inv_perm[b * a.topk + jk];
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* dst = smem + stage * stage_bytes;
-                    const uint32_t extra = a.dlocal ? static_cast<uint32_t>(t1 - t0) * D * sizeof(OutT) : 0u;
-                    stage_tile<D>(a, a.Y, slot, t0, t1, dst, &full[stage], extra);
-                    if (a.dlocal)
-                        bulk_load_1d(dst + y_bytes, static_cast<const OutT*>(a.dlocal) + (static_cast<size_t>(b) * a.P + t0) * D, extra,
-                                     &full[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        return;
-    }
-    int stage = 0; uint32_t phase = 0;
-    const int tok_per_warp = TT / ST_CONSUMER_WARPS;
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int b = w / a.tiles_per_img, tt = w - b * a.tiles_per_img;
-        const int t0 = tt * TT, t1 = min(a.P, t0 + TT);
-        const TileRows r = tile_rows(a, t0, t1);
-        float dg[N * 8];
-        load_dglobal<N, D>(a, b, lane, dg);
-        for (int jk = 0; jk < a.topk; ++jk) {
-            const int item = b * a.topk + jk;
-            const int slot = a.inv_perm[item];
-            const float g = a.gate ? a.gate[item] : 1.0f;
-            float dgate_acc = 0.f;
-            mbar_wait(&full[stage], phase);
-            const uint8_t* st = smem + stage * stage_bytes;
-            for (int k = 0; k < tok_per_warp; ++k) {
-                const int p = t0 + warp * tok_per_warp + k;
-                if (p >= t1) break;
-                float df[N * 8];
-                if (a.dlocal) {
-                    const OutT* drow = reinterpret_cast<const OutT*>(st + y_bytes) + static_cast<size_t>(p - t0) * D;
-                    load_row_x8<N, OutT>(drow, lane, df);      // generic load from shared memory
-#pragma unroll
-                    for (int i = 0; i < N * 8; ++i) df[i] += dg[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < N * 8; ++i) df[i] = dg[i];
-                }
-                float dbeta[4];
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
-                    const uint8_t* ra = st + static_cast<size_t>(a.cap_off[s] + L.i0 - r.i_lo[s]) * D * 2;
-                    float ya[N * 8];
-                    lds_row_x8<N>(ra, lane, ya);
-                    float acc = 0.f;
-                    if (L.i1 != L.i0 && L.lam != 0.f) {
-                        float yb[N * 8];
-                        lds_row_x8<N>(ra + D * 2, lane, yb);
-                        const float l0 = 1.0f - L.lam;
-#pragma unroll
-                        for (int i = 0; i < N * 8; ++i) acc = fmaf(df[i], l0 * ya[i] + L.lam * yb[i], acc);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < N * 8; ++i) acc = fmaf(df[i], ya[i], acc);
-                    }
-                    dbeta[s] = warp_sum(acc);
-                }
-                const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
-                const float dot = bt.x * dbeta[0] + bt.y * dbeta[1] + bt.z * dbeta[2] + bt.w * dbeta[3];
-                dgate_acc += dot;
-                if (lane == 0)
-                    *reinterpret_cast<float4*>(a.dlogit + (static_cast<size_t>(slot) * a.P + p) * 4) =
-                        make_float4(g * bt.x * (dbeta[0] - dot), g * bt.y * (dbeta[1] - dot), g * bt.z * (dbeta[2] - dot),
-                                    g * bt.w * (dbeta[3] - dot));
-            }
-            if (a.dgate && lane == 0) atomicAdd(a.dgate + item, dgate_acc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-    }
-}
+constexpr int OUT_RUNS_PER_BLOCK = 4;   // run-based backward kernels: 8 warps = 4 runs x 2 column halves
 
 }  // namespace mm
 #include "combine_staged.cuh"
@@ -1555,19 +1051,6 @@ static int fill_common(CombineArgs& a, int B, int topk, int P, const int32_t* Ps
 // global-mean partial blocks per image the forward needs room for (one per 32-token tile)
 extern "C" int mm_combine_num_token_blocks(int P) { return (P + RUN_TOKENS - 1) / RUN_TOKENS; }
 
-// tile geometry of the TMA-staged kernels; returns the bytes of one stage of a [rows, W] bf16 matrix per W element
-static void setup_tiles(CombineArgs& a, int TT) {
-    a.tile_tokens = TT;
-    a.tiles_per_img = (a.P + TT - 1) / TT;
-    int off = 0;
-    for (int s = 0; s < 4; ++s) {
-        a.cap[s] = static_cast<int>((static_cast<long long>(TT) * a.Ps[s] + a.P - 1) / a.P) + 3;
-        a.cap_off[s] = off;
-        off += a.cap[s];
-    }
-    a.cap_total = off;
-}
-constexpr size_t ST_SMEM_LIMIT = 227 * 1024;
 template <typename K>
 static int opt_in_smem(K kern, size_t bytes, const char* what) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
@@ -1575,43 +1058,6 @@ static int opt_in_smem(K kern, size_t bytes, const char* what) {
         mm::set_error("%s: cannot opt in to %zu B of shared memory (%s)", what, bytes, cudaGetErrorString(e));
         return MM_ERR_CUDA;
     }
-    return MM_OK;
-}
-template <int D>
-static int launch_logits_staged(const CombineArgs& a, cudaStream_t st) {
-    constexpr int STAGES = 4;
-    const size_t smem = STAGES * static_cast<size_t>(a.cap_total) * (D / 2) * 2 + 2 * STAGES * 8 + 128;
-    if (smem > ST_SMEM_LIMIT) return 1;
-    auto kern = combine_logits_staged_kernel<D, STAGES>;
-    if (int rc = opt_in_smem(kern, smem, "combine_logits")) return rc;
-    const int total = a.n_items * a.tiles_per_img;
-    kern<<<total < mm::sm_count() ? total : mm::sm_count(), ST_THREADS, smem, st>>>(a);
-    mm::note_launches(1);
-    return MM_OK;
-}
-template <int D, typename OutT>
-static int launch_out_staged(const CombineArgs& a, cudaStream_t st) {
-    constexpr int STAGES = 2;
-    const size_t smem = STAGES * static_cast<size_t>(a.cap_total) * D * 2 + ST_CONSUMER_WARPS * D * 4 + 2 * STAGES * 8 + 128;
-    if (smem > ST_SMEM_LIMIT) return 1;
-    auto kern = combine_out_staged_kernel<D, OutT, STAGES>;
-    if (int rc = opt_in_smem(kern, smem, "combine_out")) return rc;
-    const int total = a.B * a.tiles_per_img;
-    kern<<<total < mm::sm_count() ? total : mm::sm_count(), ST_THREADS, smem, st>>>(a);
-    mm::note_launches(1);
-    return MM_OK;
-}
-template <int D, typename OutT>
-static int launch_bwd_logit_staged(const CombineArgs& a, cudaStream_t st) {
-    constexpr int STAGES = 2;
-    const size_t stage = static_cast<size_t>(a.cap_total) * D * 2 + (a.dlocal ? static_cast<size_t>(a.tile_tokens) * D * sizeof(OutT) : 0);
-    const size_t smem = STAGES * stage + 2 * STAGES * 8 + 128;
-    if (smem > ST_SMEM_LIMIT) return 1;
-    auto kern = combine_bwd_logit_staged_kernel<D, OutT, STAGES>;
-    if (int rc = opt_in_smem(kern, smem, "combine_bwd_logit")) return rc;
-    const int total = a.B * a.tiles_per_img;
-    kern<<<total < mm::sm_count() ? total : mm::sm_count(), ST_THREADS, smem, st>>>(a);
-    mm::note_launches(1);
     return MM_OK;
 }
 #define MM_STAGED_D(D, F32, FN, ARGS, ST, RC)                                                            \
