@@ -419,7 +419,7 @@ def main():
         rows_c = sum(Ps) - P0
         for k, v in {
             "combine_fwd.logits": sum(Ps) * H * 2 + P0 * 16,
-            "combine_fwd.out": sum(Ps) * D * 2 + P0 * D * 2 + P0 * 16,
+            "combine_fwd.out": sum(Ps) * D * 2 + P0 * D * 2 / args.topk + P0 * 16,      # out is per image, Y rows per item
             "combine_bwd.dbeta": sum(Ps) * D * 2 + P0 * (16 + 32) + dloc,
             "combine_bwd.dUT": sum(Ps) * D * 2 + P0 * 16 + dloc,
             "combine_bwd.dZ": sum(Ps) * H * 2 * 2 + P0 * (16 + 32),

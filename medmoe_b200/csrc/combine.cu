@@ -1078,6 +1078,11 @@ static int cm_launch_out(CombineArgs& a, CmArgs& c, int D, long long total_rows,
     c.D = D;
     c.n_pass = D / CM_BN;
     c.out_f32 = out_f32;
+    const bool img = a.topk > 1;        // top-k > 1: image-centric tiles, the k choices are extra K groups of the same accumulator
+    c.n_src = img ? a.topk : 1;
+    c.stages = img ? 2 : CM_STAGES;
+    c.tiles_per_img = (a.P + TILE_M - 1) / TILE_M;
+    if (img && !a.inv_perm) return 1;
     const size_t smem = cm_smem_bytes(c, out_f32 != 0);
     if (smem > 227 * 1024) return 1;
     CUtensorMap tmY[4], tmOut;
@@ -1092,16 +1097,17 @@ static int cm_launch_out(CombineArgs& a, CmArgs& c, int D, long long total_rows,
                                           static_cast<uint64_t>(D), 32, 32, 64, "combine_out(out)");
         if (rc) return rc;
     }
-    const int grid = c.n_tiles < mm::sm_count() ? c.n_tiles : mm::sm_count();
-    if (out_f32) {
-        auto kern = cm_out_kernel<true>;
-        if (int rc = opt_in_smem(kern, smem, "combine_out(mma)")) return rc;
-        kern<<<grid, CM_THREADS, smem, st>>>(tmY[0], tmY[1], tmY[2], tmY[3], tmOut, a, c);
-    } else {
-        auto kern = cm_out_kernel<false>;
-        if (int rc = opt_in_smem(kern, smem, "combine_out(mma)")) return rc;
-        kern<<<grid, CM_THREADS, smem, st>>>(tmY[0], tmY[1], tmY[2], tmY[3], tmOut, a, c);
+    const int n_work = img ? a.B * c.tiles_per_img : c.n_tiles;
+    const int grid = n_work < mm::sm_count() ? n_work : mm::sm_count();
+#define MM_CM_LAUNCH(F32, IMGV)                                                                          \
+    {                                                                                                    \
+        auto kern = cm_out_kernel<F32, IMGV>;                                                            \
+        if (int rc = opt_in_smem(kern, smem, "combine_out(mma)")) return rc;                             \
+        kern<<<grid, CM_THREADS, smem, st>>>(tmY[0], tmY[1], tmY[2], tmY[3], tmOut, a, c);               \
     }
+    if (out_f32) { if (img) MM_CM_LAUNCH(true, true) else MM_CM_LAUNCH(true, false) }
+    else         { if (img) MM_CM_LAUNCH(false, true) else MM_CM_LAUNCH(false, false) }
+#undef MM_CM_LAUNCH
     mm::note_launches(1);
     return MM_OK;
 }

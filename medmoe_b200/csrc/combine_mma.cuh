@@ -23,7 +23,7 @@
 namespace mm {
 
 constexpr int CM_BN = 128;              // output columns per accumulator pass
-constexpr int CM_STAGES = 3;
+constexpr int CM_STAGES = 3;             // maximum (the IMG / top-k > 1 variant runs 2: its coefficient matrices take the room)
 constexpr int CM_ACC = 4;               // TMEM ring: 4 accumulators x 128 columns
 constexpr int CM_EPI_WARPS = 8;
 constexpr int CM_COEF_WARPS = 4;
@@ -39,6 +39,9 @@ struct CmArgs {
     int cap[4], koff[4], ktot;   // rows staged per scale, their first k index, total (multiple of 16)
     int D, n_pass;               // D / CM_BN
     int out_f32;
+    // IMG tiling (top-k > 1): a tile is 128 consecutive tokens of one IMAGE; its n_src = topk expert choices are extra
+    // K groups accumulated into the same TMEM tile (one coefficient matrix per choice, gate weights folded in)
+    int tiles_per_img, n_src, stages;
 };
 
 MM_DEVINL int cm_floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -49,7 +52,7 @@ MM_DEVINL uint32_t cm_a_off(int m, int k) {
     return static_cast<uint32_t>(kb * 16384 + m * 128 + ((((kin >> 3) ^ (m & 7))) << 4) + (kin & 7) * 2);
 }
 
-template <bool OUT_F32>
+template <bool OUT_F32, bool IMG>
 __global__ void __launch_bounds__(CM_THREADS, 1)
 cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ CUtensorMap tmY1,
               const __grid_constant__ CUtensorMap tmY2, const __grid_constant__ CUtensorMap tmY3,
@@ -58,9 +61,11 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = ((c.ktot + 63) / 64) * 16384;
     const int stage_bytes = c.ktot * 256;                       // 2 column chunks x ktot rows x 128 B
-    uint8_t* sA = smem;
-    uint8_t* sB = sA + a_bytes;
-    uint8_t* sOut = sB + CM_STAGES * stage_bytes;               // [CM_EPI_WARPS][2 slots] (bf16 output only)
+    const int n_src = IMG ? c.n_src : 1;
+    const int n_stages = c.stages;
+    uint8_t* sA = smem;                                         // [n_src] coefficient matrices
+    uint8_t* sB = sA + n_src * a_bytes;
+    uint8_t* sOut = sB + n_stages * stage_bytes;                // [CM_EPI_WARPS][2 slots] (bf16 output only)
     uint64_t* full = reinterpret_cast<uint64_t*>(sOut + (OUT_F32 ? 0 : CM_EPI_WARPS * 2 * EPI_SLOT_BYTES));
     uint64_t* empty = full + CM_STAGES;
     uint64_t* tfull = empty + CM_STAGES;
@@ -84,40 +89,57 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     // the coefficient matrix starts as all zeros; only the 7 fixed positions of every row are ever rewritten
-    for (int i = threadIdx.x * 16; i < a_bytes; i += CM_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x * 16; i < n_src * a_bytes; i += CM_THREADS * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nk = c.ktot >> 4;
+    const int n_work = IMG ? a.B * c.tiles_per_img : c.n_tiles;
 
     if (threadIdx.x == 0) {
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
-        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
-            const int e = c.tile_info[t].x;
-            if (e < 0) continue;
-            const int row0 = c.region_row[0] + t * TILE_M;
-            const int rel0 = row0 - c.seg_start[e];                 // multiple of 128
-            int row_s[4];
-            row_s[0] = row0;
+        for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
+            int row_s[2][4];        // first staged row of every scale, per source (n_src <= 2 is enforced by the host)
+            if constexpr (IMG) {
+                const int b = t / c.tiles_per_img, t0 = (t - b * c.tiles_per_img) * TILE_M;
 #pragma unroll
-            for (int s = 1; s < 4; ++s) row_s[s] = c.seg_start[s * c.K + e] + rel0 / a.ratio[s] - 1;
-            for (int n = 0; n < c.n_pass; ++n) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], static_cast<uint32_t>(stage_bytes));
-                uint8_t* dst = sB + stage * stage_bytes;
+                for (int j = 0; j < 2; ++j) {
+                    if (j >= n_src) break;
+                    const int slot = a.inv_perm[b * a.topk + j];
+                    row_s[j][0] = a.slot_row[slot] + t0;
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint8_t* d = dst + ch * (c.ktot * 128);
-                    const int col = n * CM_BN + ch * 64;
-                    tma_load_2d(d + c.koff[0] * 128, &tmY0, &full[stage], col, row_s[0]);
-                    tma_load_2d(d + c.koff[1] * 128, &tmY1, &full[stage], col, row_s[1]);
-                    tma_load_2d(d + c.koff[2] * 128, &tmY2, &full[stage], col, row_s[2]);
-                    tma_load_2d(d + c.koff[3] * 128, &tmY3, &full[stage], col, row_s[3]);
+                    for (int s = 1; s < 4; ++s) row_s[j][s] = a.slot_row[s * a.n_items + slot] + t0 / a.ratio[s] - 1;
                 }
-                if (++stage == CM_STAGES) { stage = 0; phase ^= 1; }
+            } else {
+                const int e = c.tile_info[t].x;
+                if (e < 0) continue;
+                const int row0 = c.region_row[0] + t * TILE_M;
+                const int rel0 = row0 - c.seg_start[e];                 // multiple of 128
+                row_s[0][0] = row0;
+#pragma unroll
+                for (int s = 1; s < 4; ++s) row_s[0][s] = c.seg_start[s * c.K + e] + rel0 / a.ratio[s] - 1;
+            }
+            for (int n = 0; n < c.n_pass; ++n) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j >= n_src) break;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], static_cast<uint32_t>(stage_bytes));
+                    uint8_t* dst = sB + stage * stage_bytes;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        uint8_t* d = dst + ch * (c.ktot * 128);
+                        const int col = n * CM_BN + ch * 64;
+                        tma_load_2d(d + c.koff[0] * 128, &tmY0, &full[stage], col, row_s[j][0]);
+                        tma_load_2d(d + c.koff[1] * 128, &tmY1, &full[stage], col, row_s[j][1]);
+                        tma_load_2d(d + c.koff[2] * 128, &tmY2, &full[stage], col, row_s[j][2]);
+                        tma_load_2d(d + c.koff[3] * 128, &tmY3, &full[stage], col, row_s[j][3]);
+                    }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (threadIdx.x == 32) {
@@ -128,25 +150,28 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
         uint32_t a_phase = 0;
         const uint32_t a_addr = smem_u32(sA);
         const uint32_t lbo = static_cast<uint32_t>(c.ktot) * 128u;
-        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
-            if (c.tile_info[t].x < 0) continue;
+        for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
+            if (!IMG && c.tile_info[t].x < 0) continue;
             mbar_wait(a_full, a_phase);
             a_phase ^= 1;
             tc_fence_after();
             for (int n = 0; n < c.n_pass; ++n) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * CM_BN;
-                const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
-                for (int j = 0; j < nk; ++j) {
-                    const uint64_t da = make_smem_desc(a_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024);
-                    const uint64_t db = make_smem_desc(b_addr + j * 2048, lbo, 1024);
-                    umma_bf16(d_tmem, da, db, idesc, j != 0);
+                for (int j = 0; j < n_src; ++j) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
+                    const uint32_t aj = a_addr + j * a_bytes;
+                    for (int k = 0; k < nk; ++k) {
+                        const uint64_t da = make_smem_desc(aj + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc(b_addr + k * 2048, lbo, 1024);
+                        umma_bf16(d_tmem, da, db, idesc, (j | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty[stage]);
                 umma_commit(&tfull[acc]);
-                if (++stage == CM_STAGES) { stage = 0; phase ^= 1; }
                 if (++acc == CM_ACC) { acc = 0; acc_phase ^= 1; }
             }
             umma_commit(a_empty);       // every MMA that reads this tile's coefficients has retired
@@ -164,39 +189,70 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
             offa[s] = cm_a_off(m, c.koff[s] + j0 + 1);
             offb[s] = cm_a_off(m, c.koff[s] + j0 + 2);
         }
-        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
-            const int2 ti = c.tile_info[t];
-            const int e = ti.x;
-            if (e < 0) continue;
-            float v0 = 0.f, va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
-            if (m < ti.y) {
-                const int rel0 = c.region_row[0] + t * TILE_M - c.seg_start[e];
-                const int rel = rel0 + m;
-                const int j = rel / a.P, p = rel - j * a.P;
-                const int slot = c.offsets[e] + j;
-                const float g = a.gate ? a.gate[a.perm[slot]] : 1.0f;
-                const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
-                const float bs[4] = {bt.x * g, bt.y * g, bt.z * g, bt.w * g};
-                v0 = bs[0];
+        for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
+            float v0[2] = {0.f, 0.f}, va[2][4] = {}, vb[2][4] = {};
+            if constexpr (IMG) {
+                const int b = t / c.tiles_per_img, t0 = (t - b * c.tiles_per_img) * TILE_M;
+                const int p = t0 + m;
+                if (p < a.P) {
 #pragma unroll
-                for (int s = 1; s < 4; ++s) {
-                    const int r = a.ratio[s];
-                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
-                    const int fs = c.seg_start[s * c.K + e] + rel0 / r - 1;
-                    const int base = a.slot_row[s * a.n_items + slot];
-                    const int qa = base + L.i0 - fs, qb = base + L.i1 - fs;
-                    const int q0 = cm_floor_div(2 * m + 1 - r, 2 * r) + 1;
-                    va[s] = bs[s] * ((qa == q0 ? 1.0f - L.lam : 0.f) + (qb == q0 ? L.lam : 0.f));
-                    vb[s] = bs[s] * ((qa == q0 + 1 ? 1.0f - L.lam : 0.f) + (qb == q0 + 1 ? L.lam : 0.f));
+                    for (int j = 0; j < 2; ++j) {
+                        if (j >= n_src) break;
+                        const int item = b * a.topk + j;
+                        const int slot = a.inv_perm[item];
+                        const float g = a.gate ? a.gate[item] : 1.0f;
+                        const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+                        const float bs[4] = {bt.x * g, bt.y * g, bt.z * g, bt.w * g};
+                        v0[j] = bs[0];
+#pragma unroll
+                        for (int s = 1; s < 4; ++s) {
+                            const int r = a.ratio[s];
+                            const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                            const int qa = L.i0 - (t0 / r - 1), qb = L.i1 - (t0 / r - 1);
+                            const int q0 = cm_floor_div(2 * m + 1 - r, 2 * r) + 1;
+                            va[j][s] = bs[s] * ((qa == q0 ? 1.0f - L.lam : 0.f) + (qb == q0 ? L.lam : 0.f));
+                            vb[j][s] = bs[s] * ((qa == q0 + 1 ? 1.0f - L.lam : 0.f) + (qb == q0 + 1 ? L.lam : 0.f));
+                        }
+                    }
+                }
+            } else {
+                const int2 ti = c.tile_info[t];
+                const int e = ti.x;
+                if (e < 0) continue;
+                if (m < ti.y) {
+                    const int rel0 = c.region_row[0] + t * TILE_M - c.seg_start[e];
+                    const int rel = rel0 + m;
+                    const int j = rel / a.P, p = rel - j * a.P;
+                    const int slot = c.offsets[e] + j;
+                    const float g = a.gate ? a.gate[a.perm[slot]] : 1.0f;
+                    const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+                    const float bs[4] = {bt.x * g, bt.y * g, bt.z * g, bt.w * g};
+                    v0[0] = bs[0];
+#pragma unroll
+                    for (int s = 1; s < 4; ++s) {
+                        const int r = a.ratio[s];
+                        const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                        const int fs = c.seg_start[s * c.K + e] + rel0 / r - 1;
+                        const int base = a.slot_row[s * a.n_items + slot];
+                        const int qa = base + L.i0 - fs, qb = base + L.i1 - fs;
+                        const int q0 = cm_floor_div(2 * m + 1 - r, 2 * r) + 1;
+                        va[0][s] = bs[s] * ((qa == q0 ? 1.0f - L.lam : 0.f) + (qb == q0 ? L.lam : 0.f));
+                        vb[0][s] = bs[s] * ((qa == q0 + 1 ? 1.0f - L.lam : 0.f) + (qb == q0 + 1 ? L.lam : 0.f));
+                    }
                 }
             }
             mbar_wait(a_empty, a_phase ^ 1);
             a_phase ^= 1;
-            *reinterpret_cast<__nv_bfloat16*>(sA + off0) = __float2bfloat16_rn(v0);
 #pragma unroll
-            for (int s = 1; s < 4; ++s) {
-                *reinterpret_cast<__nv_bfloat16*>(sA + offa[s]) = __float2bfloat16_rn(va[s]);
-                *reinterpret_cast<__nv_bfloat16*>(sA + offb[s]) = __float2bfloat16_rn(vb[s]);
+            for (int j = 0; j < 2; ++j) {
+                if (j >= n_src) break;
+                uint8_t* Aj = sA + j * a_bytes;
+                *reinterpret_cast<__nv_bfloat16*>(Aj + off0) = __float2bfloat16_rn(v0[j]);
+#pragma unroll
+                for (int s = 1; s < 4; ++s) {
+                    *reinterpret_cast<__nv_bfloat16*>(Aj + offa[s]) = __float2bfloat16_rn(va[j][s]);
+                    *reinterpret_cast<__nv_bfloat16*>(Aj + offb[s]) = __float2bfloat16_rn(vb[j][s]);
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -210,20 +266,29 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
         uint8_t* my_out = sOut + ew * 2 * EPI_SLOT_BYTES;
         int acc = 0; uint32_t acc_phase = 0;
         int oslot = 0;
-        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
-            const int2 ti = c.tile_info[t];
-            const int e = ti.x;
-            if (e < 0) continue;
+        for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
             const int m0 = q * 32;
-            const bool valid = m0 < ti.y;            // P % 32 == 0: a warp's 32 tokens are all valid or all padding
+            bool valid;                              // P % 32 == 0: a warp's 32 tokens are all valid or all padding
             long long orow = 0;
             int blk = 0, b = 0;
-            if (valid) {
-                const int rel = c.region_row[0] + t * TILE_M - c.seg_start[e] + m0;
-                const int j = rel / a.P, p0 = rel - j * a.P;
-                b = a.perm[c.offsets[e] + j] / a.topk;
+            if constexpr (IMG) {
+                b = t / c.tiles_per_img;
+                const int p0 = (t - b * c.tiles_per_img) * TILE_M + m0;
+                valid = p0 < a.P;
                 orow = static_cast<long long>(b) * a.P + p0;
                 blk = p0 >> 5;
+            } else {
+                const int2 ti = c.tile_info[t];
+                const int e = ti.x;
+                if (e < 0) continue;
+                valid = m0 < ti.y;
+                if (valid) {
+                    const int rel = c.region_row[0] + t * TILE_M - c.seg_start[e] + m0;
+                    const int j = rel / a.P, p0 = rel - j * a.P;
+                    b = a.perm[c.offsets[e] + j] / a.topk;
+                    orow = static_cast<long long>(b) * a.P + p0;
+                    blk = p0 >> 5;
+                }
             }
             for (int n = 0; n < c.n_pass; ++n) {
                 mbar_wait(&tfull[acc], acc_phase);
@@ -290,7 +355,7 @@ static inline bool cm_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 // fills the K layout; false when the tensor-core path does not apply
 static inline bool cm_geometry(const CombineArgs& a, int D, CmArgs& c) {
-    if (a.topk != 1 || a.Ps[0] != a.P || a.P % 32 != 0 || D % CM_BN != 0) return false;
+    if (a.topk < 1 || a.topk > 2 || a.Ps[0] != a.P || a.P % 32 != 0 || D % CM_BN != 0) return false;
     int off = 0;
     for (int s = 0; s < 4; ++s) {
         if (a.Ps[s] <= 0 || a.P % a.Ps[s] != 0) return false;
@@ -305,7 +370,7 @@ static inline bool cm_geometry(const CombineArgs& a, int D, CmArgs& c) {
 }
 
 static inline size_t cm_smem_bytes(const CmArgs& c, bool out_f32) {
-    return static_cast<size_t>((c.ktot + 63) / 64) * 16384 + static_cast<size_t>(CM_STAGES) * c.ktot * 256 +
+    return static_cast<size_t>(c.n_src) * ((c.ktot + 63) / 64) * 16384 + static_cast<size_t>(c.stages) * c.ktot * 256 +
            (out_f32 ? 0 : CM_EPI_WARPS * 2 * EPI_SLOT_BYTES) + (2 * CM_STAGES + 2 * CM_ACC + 2) * 8 + 16 + 1024;
 }
 
@@ -325,8 +390,9 @@ static inline size_t cm_smem_bytes(const CmArgs& c, bool out_f32) {
 // Roles (512 threads) as in cm_out_kernel.  Stages alternate {finest-scale rows} / {coarse rows of the 3 other scales}
 // of one column pass.  Requirements: those of cm_geometry plus H = D / 2 a multiple of 128 or 192.
 // =======================================================================================
-constexpr int CL_STAGES = 3;
-constexpr int CL_ACC_COLS = 256;       // TMEM columns per accumulator slot (2 slots)
+constexpr int CL_STAGES = 4;
+constexpr int CL_MAX_ACC = 4;          // TMEM accumulator ring: 512 / HB slots of HB columns (4 x 128: the MMA warp runs up to three
+                                       // (column pass, scale) steps ahead of the epilogue, which hides the mbarrier hand-off latency)
 
 struct ClArgs {
     int n_tiles;
@@ -335,7 +401,7 @@ struct ClArgs {
     const int* seg_start;
     const int* offsets;
     int K;
-    int H, HB, n_half;           // hidden width, columns per pass (<= 192), passes per scale
+    int H, HB, n_half, n_acc;    // hidden width, columns per pass (128 or 192), passes per scale, accumulator slots
     int cap[4], koff[4], kc;     // coarse scales 1..3: rows staged (multiple of 16), first k, total
 };
 
@@ -362,8 +428,8 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
     uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * TILE_M);
     uint64_t* empty = full + CL_STAGES;
     uint64_t* tfull = empty + CL_STAGES;
-    uint64_t* tempty = tfull + 2;
-    uint64_t* a_full = tempty + 2;
+    uint64_t* tempty = tfull + CL_MAX_ACC;
+    uint64_t* a_full = tempty + CL_MAX_ACC;
     uint64_t* a_empty = a_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
@@ -371,7 +437,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
     if (threadIdx.x == 0) { tma_prefetch_desc(&tmZ0); tma_prefetch_desc(&tmZ1); tma_prefetch_desc(&tmZ2); tma_prefetch_desc(&tmZ3); }
     if (threadIdx.x == 32) {
         for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CM_EPI_WARPS); }
+        for (int s = 0; s < CL_MAX_ACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CM_EPI_WARPS); }
         mbar_init(a_full, CM_COEF_WARPS);
         mbar_init(a_empty, 1);
         fence_barrier_init();
@@ -440,7 +506,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 tc_fence_after();
                 {
                     const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
-                    const uint32_t d_tmem = tmem_base + acc * CL_ACC_COLS;
+                    const uint32_t d_tmem = tmem_base + acc * c.HB;
                     for (int j = 0; j < TILE_M / 16; ++j)
                         umma_bf16(d_tmem, make_smem_desc(ai_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
                                   make_smem_desc(b_addr + j * 2048, TILE_M * 128, 1024), idesc, j != 0);
@@ -448,7 +514,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     umma_commit(&tfull[acc]);
                 }
                 if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 // ---- coarse scales ----
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -456,14 +522,14 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 for (int s = 1; s < 4; ++s) {
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * CL_ACC_COLS;
+                    const uint32_t d_tmem = tmem_base + acc * c.HB;
                     const int j0 = c.koff[s] >> 4, j1 = (c.koff[s] + c.cap[s]) >> 4;
                     for (int j = j0; j < j1; ++j)
                         umma_bf16(d_tmem, make_smem_desc(ac_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
                                   make_smem_desc(b_addr + j * 2048, static_cast<uint32_t>(c.kc) * 128u, 1024), idesc, j != j0);
                     if (s == 3) umma_commit(&empty[stage]);
                     umma_commit(&tfull[acc]);
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 }
                 if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -540,7 +606,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 for (int s = 0; s < 4; ++s) {
                     mbar_wait(&tfull[acc], acc_phase);
                     tc_fence_after();
-                    const uint32_t t_row = tmem_base + acc * CL_ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+                    const uint32_t t_row = tmem_base + acc * c.HB + (static_cast<uint32_t>(q * 32) << 16);
                     float part = 0.f;
 #pragma unroll 1
                     for (int cc = hsel; cc < n_ch; cc += 2) {
@@ -563,7 +629,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 }
             }
             // the two warps of a lane quarter hold the two column halves of the same 32 tokens
@@ -599,10 +665,11 @@ static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
     if (!cm_geometry(one, D, tmp)) return false;
     const int H = D / 2;
     c.H = H;
-    if (H % 192 == 0) c.HB = 192;
-    else if (H % 128 == 0) c.HB = 128;
+    if (H % 128 == 0) c.HB = 128;
+    else if (H % 192 == 0) c.HB = 192;
     else return false;
     c.n_half = H / c.HB;
+    c.n_acc = 512 / c.HB;
     int off = 0;
     c.cap[0] = TILE_M; c.koff[0] = 0;
     for (int s = 1; s < 4; ++s) {
@@ -617,7 +684,7 @@ static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
 
 static inline size_t cl_smem_bytes(const ClArgs& c) {
     return 32768 + static_cast<size_t>((c.kc + 63) / 64) * 16384 + static_cast<size_t>(CL_STAGES) * c.HB * 256 +
-           static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 4 + 2) * 8 + 16 + 1024;
+           static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 2 * CL_MAX_ACC + 2) * 8 + 16 + 1024;
 }
 
 }  // namespace mm

@@ -336,13 +336,13 @@ def test_global_only_cotangent_rank1_path(topk, Ps):
     assert launches[0] < launches[1]      # the rank-1 path really ran (fewer kernels: no dbeta / dUT / finalize passes)
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
-def test_tensor_core_and_cuda_core_forward_combine_agree(dtype):
+@pytest.mark.parametrize("dtype,topk", [(torch.bfloat16, 1), (torch.float32, 1), (torch.bfloat16, 2), (torch.float32, 2)])
+def test_tensor_core_and_cuda_core_forward_combine_agree(dtype, topk):
     """The tcgen05 forward combine (out = C * Yrows, bf16 coefficients) against the CUDA-core kernel (fp32 coefficients):
     same beta, same Y; they differ by the bf16 rounding of the 7 coefficients per token (<= 2^-9 relative each)."""
     K, hidden, D, Ps, B = 3, [96, 192, 384, 768], 768, [3136, 784, 196, 49], 7
     params = mo.init_params(K, hidden, D, D, seed=61)
-    moe = _module_from(params, K, hidden, D)
+    moe = _module_from(params, K, hidden, D, topk=topk)     # topk = 2: image-centric tiles, both choices in one accumulator
     torch.manual_seed(62)
     feats = [torch.randn(B, p, d, device="cuda", dtype=dtype) for p, d in zip(Ps, hidden)]
     sw = torch.randn(B, D, device="cuda")
