@@ -15,6 +15,9 @@
 #ifndef MM_EPI_WARPS_PLAIN
 #define MM_EPI_WARPS_PLAIN 16
 #endif
+#ifndef MM_EPI_WARPS_RANK1
+#define MM_EPI_WARPS_RANK1 12      // rank-1 aux epilogue: only the gate tile is prefetched, which leaves room for twelve warps
+#endif
 
 namespace mm {
 
@@ -135,7 +138,7 @@ static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t
     // plain bf16 epilogues are bound by the latency of their TMEM -> registers -> staging -> TMA-store chain: sixteen
     // epilogue warps (four per scheduler, one staging slot each) hide it; aux/gate epilogues keep eight (their prefetch
     // slots take the shared memory) as does the fp32-output path.
-    constexpr int EW = (AUX == 0 && !OUT_F32 && BN >= 128) ? MM_EPI_WARPS_PLAIN : 8;
+    constexpr int EW = (AUX == 0 && !OUT_F32 && BN >= 128) ? MM_EPI_WARPS_PLAIN : (AUX == 2 ? MM_EPI_WARPS_RANK1 : 8);
     // smem: pipeline stages + output staging (32 KB, or 16 KB + 64 KB aux/gate staging) must fit 227 KB
     constexpr int STAGES = AUX ? ((BN > 128) ? 3 : 4) : ((BN > 192) ? 4 : (BN > 128 ? 4 : 5));
     using S = GemmSmem<BN, STAGES, AUX, EW>;

@@ -165,25 +165,37 @@ bwd_z_ident_kernel(const CombineArgs a, const ZScratch zs) {
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < n_tok) mine = *reinterpret_cast<const float4*>(dlog + 4LL * (t0 + lane));
         db2 = mine.x + mine.y + mine.z + mine.w;                 // summed over lanes by the partial reduction below
-        float z[E];
-        load_row_bf16x4<NE>(a.Z + (base + t0) * H, lane, z);
-        for (int t = 0; t < n_tok; ++t) {
-            float zn[E];
+        // eight rows per batch: all of a batch's loads are issued before its first use, so a warp keeps 8 x D bytes in flight
+        constexpr int ZB = 8;
+        for (int tb = 0; tb < n_tok; tb += ZB) {
+            uint2 raw[ZB][NE];
 #pragma unroll
-            for (int k = 0; k < E; ++k) zn[k] = 0.f;
-            if (t + 1 < n_tok) load_row_bf16x4<NE>(a.Z + (base + t0 + t + 1) * H, lane, zn);
-            const float dl = __shfl_sync(0xffffffffu, mine.x, t);
-            float gk[E];
+            for (int u = 0; u < ZB; ++u) {
+                const int t = min(tb + u, n_tok - 1);
 #pragma unroll
-            for (int k = 0; k < E; ++k) {
-                const bool open = z[k] > 0.f;
-                gk[k] = open ? dl * w2[k] : 0.f;
-                if (open) dw2[k] = fmaf(dl, z[k], dw2[k]);
-                db1[k] += gk[k];
+                for (int c = 0; c < NE; ++c)
+                    raw[u][c] = *reinterpret_cast<const uint2*>(a.Z + (base + t0 + t) * H + 4 * (lane + 32 * c));
             }
-            store_slab_bf16<NE>(a.dZ + (base + t0 + t) * H, lane, gk);
 #pragma unroll
-            for (int k = 0; k < E; ++k) z[k] = zn[k];
+            for (int u = 0; u < ZB; ++u) {
+                const int t = tb + u;
+                if (t >= n_tok) break;
+                const float dl = __shfl_sync(0xffffffffu, mine.x, t);
+                float gk[E];
+#pragma unroll
+                for (int c = 0; c < NE; ++c) {
+                    const float zv[4] = {bf16lo(raw[u][c].x), bf16hi(raw[u][c].x), bf16lo(raw[u][c].y), bf16hi(raw[u][c].y)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = 4 * c + i;
+                        const bool open = zv[i] > 0.f;
+                        gk[k] = open ? dl * w2[k] : 0.f;
+                        if (open) dw2[k] = fmaf(dl, zv[i], dw2[k]);
+                        db1[k] += gk[k];
+                    }
+                }
+                store_slab_bf16<NE>(a.dZ + (base + t0 + t) * H, lane, gk);
+            }
         }
         db2 = warp_sum(db2);
     }

@@ -390,9 +390,8 @@ static inline size_t cm_smem_bytes(const CmArgs& c, bool out_f32) {
 // Roles (512 threads) as in cm_out_kernel.  Stages alternate {finest-scale rows} / {coarse rows of the 3 other scales}
 // of one column pass.  Requirements: those of cm_geometry plus H = D / 2 a multiple of 128 or 192.
 // =======================================================================================
-constexpr int CL_STAGES = 4;
-constexpr int CL_MAX_ACC = 4;          // TMEM accumulator ring: 512 / HB slots of HB columns (4 x 128: the MMA warp runs up to three
-                                       // (column pass, scale) steps ahead of the epilogue, which hides the mbarrier hand-off latency)
+constexpr int CL_STAGES = 4;             // maximum; 48 KB stages (HB = 192) run 3
+constexpr int CL_MAX_ACC = 4;          // TMEM accumulator ring: 512 / HB slots of HB columns
 
 struct ClArgs {
     int n_tiles;
@@ -402,6 +401,7 @@ struct ClArgs {
     const int* offsets;
     int K;
     int H, HB, n_half, n_acc;    // hidden width, columns per pass (128 or 192), passes per scale, accumulator slots
+    int stages;
     int cap[4], koff[4], kc;     // coarse scales 1..3: rows staged (multiple of 16), first k, total
 };
 
@@ -423,7 +423,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
     uint8_t* sAi = smem;                                         // identity, 128 x 128 (two 64-wide k blocks)
     uint8_t* sAc = sAi + 32768;                                  // coarse lerp weights, 128 x kc
     uint8_t* sB = sAc + ac_bytes;
-    float* s_w2 = reinterpret_cast<float*>(sB + CL_STAGES * stage_bytes);          // [H] of the current expert
+    float* s_w2 = reinterpret_cast<float*>(sB + c.stages * stage_bytes);          // [H] of the current expert
     float4* s_x = reinterpret_cast<float4*>(s_w2 + c.H);                           // [2 tile parities][128 tokens]
     uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * TILE_M);
     uint64_t* empty = full + CL_STAGES;
@@ -472,7 +472,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 uint8_t* dst = sB + stage * stage_bytes;
                 for (int ch = 0; ch < n_chunk64; ++ch)
                     tma_load_2d(dst + ch * (TILE_M * 128), &tmZ0, &full[stage], h * c.HB + ch * 64, row_s[0]);
-                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == c.stages) { stage = 0; phase ^= 1; }
                 // coarse scales: kc rows x HB columns
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], static_cast<uint32_t>(c.kc * c.HB * 2));
@@ -484,7 +484,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     tma_load_2d(d + c.koff[2] * 128, &tmZ2, &full[stage], col, row_s[2]);
                     tma_load_2d(d + c.koff[3] * 128, &tmZ3, &full[stage], col, row_s[3]);
                 }
-                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == c.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (threadIdx.x == 32) {
@@ -513,7 +513,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     umma_commit(&empty[stage]);
                     umma_commit(&tfull[acc]);
                 }
-                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == c.stages) { stage = 0; phase ^= 1; }
                 if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 // ---- coarse scales ----
                 mbar_wait(&full[stage], phase);
@@ -531,7 +531,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     umma_commit(&tfull[acc]);
                     if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 }
-                if (++stage == CL_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == c.stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(a_empty);
         }
@@ -665,11 +665,12 @@ static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
     if (!cm_geometry(one, D, tmp)) return false;
     const int H = D / 2;
     c.H = H;
-    if (H % 128 == 0) c.HB = 128;
-    else if (H % 192 == 0) c.HB = 192;
+    if (H % 192 == 0) c.HB = 192;        // fewer, wider column passes win: the per-pass hand-off costs more than ring depth buys
+    else if (H % 128 == 0) c.HB = 128;
     else return false;
     c.n_half = H / c.HB;
     c.n_acc = 512 / c.HB;
+    c.stages = c.HB > 128 ? 3 : CL_STAGES;
     int off = 0;
     c.cap[0] = TILE_M; c.koff[0] = 0;
     for (int s = 1; s < 4; ++s) {
@@ -683,7 +684,7 @@ static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
 }
 
 static inline size_t cl_smem_bytes(const ClArgs& c) {
-    return 32768 + static_cast<size_t>((c.kc + 63) / 64) * 16384 + static_cast<size_t>(CL_STAGES) * c.HB * 256 +
+    return 32768 + static_cast<size_t>((c.kc + 63) / 64) * 16384 + static_cast<size_t>(c.stages) * c.HB * 256 +
            static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 2 * CL_MAX_ACC + 2) * 8 + 16 + 1024;
 }
 

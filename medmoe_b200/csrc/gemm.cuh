@@ -79,7 +79,8 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_SLOTS = (AUX || EPI_WARPS > 8) ? 1 : 2;                // output staging slots per epilogue warp
     static constexpr int EPI_OUT_BYTES = EPI_WARPS * OUT_SLOTS * EPI_SLOT_BYTES;
-    static constexpr int EPI_IN_BYTES = AUX ? EPI_WARPS * 2 * 2 * EPI_SLOT_BYTES : 0;   // double-buffered {aux, gate}
+    static constexpr int IN_PER = (AUX == 1) ? 2 : 1;                               // prefetched tiles per buffer: {aux, gate} or {gate}
+    static constexpr int EPI_IN_BYTES = AUX ? EPI_WARPS * 2 * IN_PER * EPI_SLOT_BYTES : 0;   // double-buffered
     static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;   // + alignment slack
     static constexpr int WGRAD_TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;      // the wgrad kernel has no staging slots
@@ -211,7 +212,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr int NCH = BN / 32;
         constexpr int CSTEP = EPI_WARPS / 4;
         uint8_t* my_out = sOut + ew * S::OUT_SLOTS * EPI_SLOT_BYTES;
-        uint8_t* my_in = sIn + ew * 4 * EPI_SLOT_BYTES;      // slot b: aux at b * 2 * SLOT, gate right after it
+        constexpr int IN_BUF = S::IN_PER * EPI_SLOT_BYTES;
+        uint8_t* my_in = sIn + ew * 2 * IN_BUF;              // buffer b at b * IN_BUF: [aux tile,] gate tile
         uint64_t* my_bar = inbar + ew * 2;
         int acc = 0; uint32_t acc_phase = 0;
         int oslot = 0;                 // staging slot for the next output chunk
@@ -228,8 +230,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
             const int row0 = lt * TILE_M + q * 32, col0 = nt * BN + c * 32;
             mbar_expect_tx(&my_bar[slot], (AUX == 1 ? 2 : 1) * EPI_SLOT_BYTES);
-            if (AUX == 1) tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES, &tmAux, &my_bar[slot], col0, row0);
-            tma_load_2d(my_in + slot * 2 * EPI_SLOT_BYTES + EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
+            if (AUX == 1) tma_load_2d(my_in + slot * IN_BUF, &tmAux, &my_bar[slot], col0, row0);
+            tma_load_2d(my_in + slot * IN_BUF + (S::IN_PER - 1) * EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
         };
 
         int w = next_valid(blockIdx.x);
@@ -293,8 +295,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (AUX) {
                     mbar_wait(&my_bar[islot], iphase[islot]);
                     iphase[islot] ^= 1;
-                    const uint8_t* ax = my_in + islot * 2 * EPI_SLOT_BYTES;
-                    const uint8_t* gt = ax + EPI_SLOT_BYTES;
+                    const uint8_t* ax = my_in + islot * IN_BUF;
+                    const uint8_t* gt = ax + (S::IN_PER - 1) * EPI_SLOT_BYTES;
                     if (AUX == 2) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
