@@ -414,8 +414,9 @@ def main():
                 nbytes[f"{tag}.s{s}"] = Bi * p * (d_s + D) * 2
             flops[f"dY.s{s}"] = 2.0 * Bi * p * H * D
             nbytes[f"dY.s{s}"] = Bi * p * (H + 2 * D) * 2 + (Bi * p * D * 2 if args.local_grad else Bi * p * 8)
-        flops["E4"] = flops["dW1"] = 2.0 * R * D * H
+        flops["E4"] = flops["dW1"] = flops["dY"] = 2.0 * R * D * H
         nbytes["E4"] = nbytes["dW1"] = R * (D + H) * 2
+        nbytes["dY"] = R * (H + 2 * D) * 2 + (R * D * 2 if args.local_grad else R * 8)
         rows_c = sum(Ps) - P0
         for k, v in {
             "combine_fwd.logits": sum(Ps) * H * 2 + P0 * 16,
@@ -453,7 +454,8 @@ def main():
         tag = top_label.split(":")[0]
         # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full captures (profiles/), cfg2 only
         known_traffic = {"combine_fwd.out": 2.964e9, "combine_fwd.logits": 0.836e9, "combine_bwd.dZ.rows": 0.402e9,
-                         "dY.s0": 3.061e9, "E4": 2.439e9, "E1.s0": 1.335e9}
+                         "dY": 4.05e9, "E4": 2.441e9, "E1.s0": 1.337e9, "combine_bwd.dZ.ident": 1.214e9,
+                         "combine_bwd.rowdot": 1.645e9, "dW1": 2.663e9}
         traffic = known_traffic.get(tag) if (B == 256 and args.img == 224 and not args.local_grad) else None
         if top.get("bound") == "tensor":
             roof = {"kernel": top_label, "bound": "tensor", "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",

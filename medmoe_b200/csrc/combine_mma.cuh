@@ -607,7 +607,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     mbar_wait(&tfull[acc], acc_phase);
                     tc_fence_after();
                     const uint32_t t_row = tmem_base + acc * c.HB + (static_cast<uint32_t>(q * 32) << 16);
-                    float part = 0.f;
+                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;      // four independent FMA chains
 #pragma unroll 1
                     for (int cc = hsel; cc < n_ch; cc += 2) {
                         uint32_t v[32];
@@ -619,13 +619,13 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                         tmem_ld_wait();
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 0]), 0.f), w[k].x, part);
-                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 1]), 0.f), w[k].y, part);
-                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 2]), 0.f), w[k].z, part);
-                            part = fmaf(fmaxf(__uint_as_float(v[4 * k + 3]), 0.f), w[k].w, part);
+                            p0 = fmaf(fmaxf(__uint_as_float(v[4 * k + 0]), 0.f), w[k].x, p0);
+                            p1 = fmaf(fmaxf(__uint_as_float(v[4 * k + 1]), 0.f), w[k].y, p1);
+                            p2 = fmaf(fmaxf(__uint_as_float(v[4 * k + 2]), 0.f), w[k].z, p2);
+                            p3 = fmaf(fmaxf(__uint_as_float(v[4 * k + 3]), 0.f), w[k].w, p3);
                         }
                     }
-                    lg[s] += part;
+                    lg[s] += (p0 + p1) + (p2 + p3);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);

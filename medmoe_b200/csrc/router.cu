@@ -16,8 +16,10 @@ namespace mm {
 constexpr int ROUTER_HID = 128;   // fixed by the reference (swin.py:88-90)
 constexpr int ROUTER_MAX_K = 64;
 
-// One CTA (128 threads = 4 warps) per image.
-__global__ void __launch_bounds__(128)
+// One CTA (512 threads = 16 warps) per image: the 128 hidden units are latency-bound dot products over W1 rows, so the
+// more warps share them the shorter each warp's serial chain of L2 round trips.
+constexpr int ROUTER_FWD_THREADS = 512;
+__global__ void __launch_bounds__(ROUTER_FWD_THREADS)
 router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ W1, const float* __restrict__ b1,
                   const float* __restrict__ W2, const float* __restrict__ b2, int K, int topk,
                   float* __restrict__ hidden, float* __restrict__ probs, int* __restrict__ topk_idx,
@@ -32,7 +34,8 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
     __syncthreads();
     // hidden: each warp owns 32 outputs; lanes stride the 768-long dot (coalesced W1 reads).
     // Four outputs at a time: four independent load -> FMA chains per lane keep the L2 latency of W1 covered.
-    for (int o = warp * 32; o < warp * 32 + 32; o += 4) {
+    constexpr int PER_WARP = ROUTER_HID / (ROUTER_FWD_THREADS / 32);
+    for (int o = warp * PER_WARP; o < warp * PER_WARP + PER_WARP; o += 4) {
         const float* w = W1 + static_cast<size_t>(o) * D;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
@@ -52,7 +55,7 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
         }
     }
     __syncthreads();
-    for (int e = warp; e < K; e += 4) {
+    for (int e = warp; e < K; e += ROUTER_FWD_THREADS / 32) {
         const float* w = W2 + static_cast<size_t>(e) * ROUTER_HID;
         float acc = 0.f;
         for (int i = lane; i < ROUTER_HID; i += 32) acc = fmaf(w[i], sh[i], acc);
@@ -145,7 +148,7 @@ extern "C" int mm_router_topk(const float* x, int B, int D, const float* W1, con
                "mm_router_topk: need 0 < K <= 64, 1 <= topk <= K");
     if (B == 0) return MM_OK;
     const size_t smem = (static_cast<size_t>(D) + ROUTER_HID + K) * sizeof(float);
-    router_fwd_kernel<<<B, 128, smem, static_cast<cudaStream_t>(stream)>>>(x, D, W1, b1, W2, b2, K, topk, hidden,
+    router_fwd_kernel<<<B, ROUTER_FWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, D, W1, b1, W2, b2, K, topk, hidden,
                                                                           probs, topk_idx, topk_w);
     mm::note_launches(1);
     return mm_check_launch("mm_router_topk");

@@ -106,10 +106,12 @@ class _ExpertsFunction(torch.autograd.Function):
 
         Y = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
         Z = torch.empty(layout.total_rows, H, dtype=torch.bfloat16, device=dev)
-        for s in range(S):   # E1: Y_s = ReLU(f_s W_s^T + b_s)
+        def e1(s):   # E1: Y_s = ReLU(f_s W_s^T + b_s)
             r0 = layout.region_base[s]
-            ops.gemm_rows(fs[s], Wp[s], D, Y[r0:r0 + layout.region_rows[s]], plan=plan, tile_begin=layout.tile_base[s],
-                          tile_count=layout.region_tiles[s], bias=bp[s], flags=ops.EPI_RELU | ops.EPI_ZERO_PAD, tag=f"E1.s{s}")
+            return lambda: ops.gemm_rows(fs[s], Wp[s], D, Y[r0:r0 + layout.region_rows[s]], plan=plan,
+                                         tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], bias=bp[s],
+                                         flags=ops.EPI_RELU | ops.EPI_ZERO_PAD, tag=f"E1.s{s}")
+        ops.run_scales([e1(s) for s in range(S)])
         # E4 at native resolution: Z = Y W1^T + b1 (the lerp commutes with the affine map)
         ops.gemm_rows(Y, W1, H, Z, plan=plan, tile_begin=0, tile_count=layout.total_tiles, bias=b1, flags=ops.EPI_ZERO_PAD,
                       tag="E4")
@@ -147,33 +149,28 @@ class _ExpertsFunction(torch.autograd.Function):
             # only global_feat has a cotangent: d fused / d Y is rank-1 per image and is rebuilt in the dY epilogue
             row_coef, row_img, dZ, dw2, db1, db2, dgate = ops.combine_bwd_global(Y, Z, w2, plan, D, gate_flat, beta, dglobal32,
                                                                                 ctx.gate_needs_grad)
+            # one launch over the whole row space: every scale shares W1, and the rank-1 tables are indexed by global row
             dPre = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
-            for s in range(S):
-                r0, nr = layout.region_base[s], layout.region_rows[s]
-                ops.gemm_rows_rank1(dZ[r0:r0 + nr], W1T, D, dPre[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
-                                    tile_count=layout.region_tiles[s], row_coef=row_coef[r0:r0 + nr], row_vec=row_img[r0:r0 + nr],
-                                    vecs=dglobal32, gate=Y[r0:r0 + nr], tag=f"dY.s{s}")
+            ops.gemm_rows_rank1(dZ, W1T, D, dPre, plan=plan, tile_begin=0, tile_count=layout.total_tiles, row_coef=row_coef,
+                                row_vec=row_img, vecs=dglobal32, gate=Y, tag="dY")
         else:
             dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
                                                             ctx.gate_needs_grad)
             # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT
-            for s in range(S):
-                r0, nr = layout.region_base[s], layout.region_rows[s]
-                ops.gemm_rows(dZ[r0:r0 + nr], W1T, D, dUT[r0:r0 + nr], plan=plan, tile_begin=layout.tile_base[s],
-                              tile_count=layout.region_tiles[s], aux=dUT[r0:r0 + nr], gate=Y[r0:r0 + nr],
-                              flags=ops.EPI_ZERO_PAD, tag=f"dY.s{s}")
+            ops.gemm_rows(dZ, W1T, D, dUT, plan=plan, tile_begin=0, tile_count=layout.total_tiles, aux=dUT, gate=Y,
+                          flags=ops.EPI_ZERO_PAD, tag="dY")
             dPre = dUT
 
         grads_feats: List = [None] * S
         if any(ctx.feat_needs_grad):
-            dfs = []
-            for s in range(S):   # df_s = dPre_s W_s
+            WsT = [ops.transpose_cast_bf16(Wp32[s].float()).view(E * widths[s], D) for s in range(S)]   # [E, D_s, D]
+            dfs = [torch.empty(layout.region_rows[s], widths[s], dtype=torch.bfloat16, device=dev) for s in range(S)]
+
+            def dx(s):   # df_s = dPre_s W_s
                 r0, nr = layout.region_base[s], layout.region_rows[s]
-                WsT = ops.transpose_cast_bf16(Wp32[s].float()).view(E * widths[s], D)   # [E, D_s, D]
-                out = torch.empty(nr, widths[s], dtype=torch.bfloat16, device=dev)
-                ops.gemm_rows(dPre[r0:r0 + nr], WsT, widths[s], out, plan=plan, tile_begin=layout.tile_base[s],
-                              tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
-                dfs.append(out)
+                return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfs[s], plan=plan,
+                                             tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
+            ops.run_scales([dx(s) for s in range(S)])
             outs = ops.undispatch_rows(dfs, plan, widths, in_dtype)
             grads_feats = [o if need else None for o, need in zip(outs, ctx.feat_needs_grad)]
 
@@ -181,13 +178,13 @@ class _ExpertsFunction(torch.autograd.Function):
         if ctx.param_needs_grad:
             dW1 = torch.zeros(E, H, D, dtype=torch.float32, device=dev)
             ops.gemm_wgrad(dZ, Y, dW1, plan, 0, layout.total_chunks, 0, tag="dW1")
-            dWp = []
-            for s in range(S):
+            dWp = [torch.zeros(E, D, widths[s], dtype=torch.float32, device=dev) for s in range(S)]
+
+            def dwp(s):
                 r0, nr = layout.region_base[s], layout.region_rows[s]
-                g = torch.zeros(E, D, widths[s], dtype=torch.float32, device=dev)
-                ops.gemm_wgrad(dPre[r0:r0 + nr], fs[s], g, plan, layout.chunk_base[s], layout.chunk_cap[s],
-                               layout.tile_base[s], tag=f"dWp.s{s}", colsum=dbp[s])
-                dWp.append(g)
+                return lambda: ops.gemm_wgrad(dPre[r0:r0 + nr], fs[s], dWp[s], plan, layout.chunk_base[s], layout.chunk_cap[s],
+                                              layout.tile_base[s], tag=f"dWp.s{s}", colsum=dbp[s])
+            ops.run_scales([dwp(s) for s in range(S)])
             for e in range(E):
                 for s in range(S):
                     grads_params[e * per + 2 * s] = dWp[s][e].unsqueeze(-1)       # Conv1d weight [D, D_s, 1]

@@ -31,6 +31,40 @@ def _st():
     return _lib.stream_ptr()
 
 
+# ---- side streams: the per-scale launches of one logical op are independent -----------------------
+# The finest scale holds 75 % of the rows; the three coarse-scale launches are small persistent kernels.  Issued on side
+# streams they fill the SMs that the big launch's last wave leaves idle instead of paying their own ramp-up and tail.
+# Plain fork/join with events, so the pattern is captured as parallel branches of a CUDA graph.
+_SIDE_STREAMS = {}
+USE_SIDE_STREAMS = True
+
+
+def run_scales(fns):
+    """Run fns[0] on the current stream and fns[1:] on side streams; join before returning."""
+    if not USE_SIDE_STREAMS or len(fns) <= 1:
+        for f in fns:
+            f()
+        return
+    cur = torch.cuda.current_stream()
+    dev = cur.device
+    pool = _SIDE_STREAMS.setdefault(dev, [])
+    while len(pool) < len(fns) - 1:
+        pool.append(torch.cuda.Stream(device=dev))
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    joins = []
+    for f, side in zip(fns[1:], pool):
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            f()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        joins.append(ev)
+    fns[0]()
+    for ev in joins:
+        cur.wait_event(ev)
+
+
 # ---- router ---------------------------------------------------------------------------
 def router_topk(x, W1, b1, W2, b2, topk: int):
     _need_cuda(x, W1, b1, W2, b2)
