@@ -31,12 +31,12 @@ def _st():
     return _lib.stream_ptr()
 
 
-# ---- side streams: the per-scale launches of one logical op are independent -----------------------
-# The finest scale holds 75 % of the rows; the three coarse-scale launches are small persistent kernels.  Issued on side
-# streams they fill the SMs that the big launch's last wave leaves idle instead of paying their own ramp-up and tail.
-# Plain fork/join with events, so the pattern is captured as parallel branches of a CUDA graph.
+# ---- per-scale launches ------------------------------------------------------------------------------
+# The four per-scale launches of one logical op are independent.  Forking the three small ones onto side streams
+# (events, CUDA-graph capturable) was measured on B200: no gain (5.87 vs 5.81 ms/step) — every kernel here is a
+# persistent one-CTA-per-SM kernel, so a side launch only gets SMs when the big launch retires.  Kept as a switch.
 _SIDE_STREAMS = {}
-USE_SIDE_STREAMS = True
+USE_SIDE_STREAMS = False
 
 
 def run_scales(fns):
