@@ -204,13 +204,16 @@ bwd_z_ident_kernel(const CombineArgs a, const ZScratch zs) {
 
 // S0 / S1 of the open-gate token set of interval m for one element with end values (za, zb): the open set is the
 // token range [lo, hi) of the interval (a prefix, a suffix, everything or nothing), read from the prefix sums.
-// Branch-free: lanes of a warp see all four cases.  The crossing point uses the fast division: a gate can only
-// differ from the forward's when interp(Z) is within ~1e-6 relative of zero, far below the bf16 storage noise of Z.
+// Branch-free: lanes of a warp see all four cases.  The crossing point uses the approximate reciprocal: a gate can only
+// differ from the forward's when interp(Z) is within ~1e-6 relative of zero, far below the bf16 storage noise of Z
+// (za == zb gives inf/NaN here, but then oa == ob and the crossing is not used; NaN converts to 0).
 MM_DEVINL void z_open_sums(float za, float zb, int r, const float2* __restrict__ pa, float& S0, float& S1) {
     const bool oa = za > 0.f, ob = zb > 0.f;
-    const float x = __fdividef(za, za - zb) * static_cast<float>(r) - 0.5f;     // crossing, in token units
-    const int n_pre = min(max(static_cast<int>(ceilf(x)), 0), r);               // open for lambda_j < t: tokens j < x
-    const int n_suf = min(max(static_cast<int>(floorf(x)) + 1, 0), r);          // open for lambda_j > t: tokens j > x
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(za - zb));
+    const float x = za * rc * static_cast<float>(r) - 0.5f;                      // crossing, in token units
+    const int n_pre = min(max(__float2int_ru(x), 0), r);                        // open for lambda_j < t: tokens j < x
+    const int n_suf = min(max(__float2int_rd(x) + 1, 0), r);                    // open for lambda_j > t: tokens j > x
     const int hi = oa ? (ob ? r : n_pre) : (ob ? r : 0);
     const int lo = (ob && !oa) ? n_suf : 0;
     const float2 h = __ldg(pa + hi), l = __ldg(pa + lo);

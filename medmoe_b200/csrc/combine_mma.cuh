@@ -496,11 +496,9 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
         const uint32_t ai_addr = smem_u32(sAi), ac_addr = smem_u32(sAc);
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
             if (c.tile_info[t].x < 0) continue;
-            mbar_wait(a_full, a_phase);
-            a_phase ^= 1;
-            tc_fence_after();
             for (int h = 0; h < c.n_half; ++h) {
-                // ---- finest scale: identity x Z_0 tile ----
+                // ---- finest scale: identity x Z_0 tile (the identity block is static: no need to wait for this tile's
+                //      lerp weights yet, so their rebuild hides behind these MMAs) ----
                 mbar_wait(&full[stage], phase);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -516,6 +514,10 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 if (++stage == c.stages) { stage = 0; phase ^= 1; }
                 if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 // ---- coarse scales ----
+                if (h == 0) {
+                    mbar_wait(a_full, a_phase);
+                    a_phase ^= 1;
+                }
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
