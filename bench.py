@@ -342,6 +342,7 @@ def main():
     if any(k.startswith("combine_bwd.") for k in sub):
         kern.pop("mm_interp_softmax_combine_bwd", None)
         kern.pop("mm_interp_softmax_combine_bwd_global", None)
+        kern.pop("mm_interp_softmax_combine_bwd_tc", None)
     kern.update(sub)
 
     # ---------------- timed region 2: end to end from pinned host buffers ----------------

@@ -100,15 +100,15 @@ int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, 
                          const float* bias, const void* aux, long long ld_aux, const void* gate, long long ld_gate,
                          void* out, long long ld_out, int out_f32, float* colsum, float out_scale, int flags,
                          void* stream);
-/* the same product with a rank-1 aux that is never materialised (backward of E4 + ReLU of E1 when only
- * global_feat has a cotangent, see mm_interp_softmax_combine_bwd_global):
- *   out[row, :] = (A[row, :] W_e^T + row_coef[row] * vecs[row_vec[row], :]) masked by gate > 0
- * row_coef fp32 [rows], row_vec int32 [rows], vecs fp32 [n_vecs, ld_vecs]; colsum as above. */
+/* the same product with a rank-1 aux that is never materialised (backward of E4 + ReLU of E1; the rank-1 term is the
+ * per-image constant part of d fused / d Y, see mm_interp_softmax_combine_bwd_tc), plus an optional tensor aux:
+ *   out[row, :] = (A[row, :] W_e^T + row_coef[row] * vecs[row_vec[row], :] + aux[row, :]) masked by gate > 0
+ * row_coef fp32 [rows], row_vec int32 [rows], vecs fp32 [n_vecs, ld_vecs]; aux bf16 or NULL; colsum as above. */
 int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
                                long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
                                const float* row_coef, const int32_t* row_vec, const float* vecs, long long ld_vecs,
-                               const void* gate, long long ld_gate, void* out, long long ld_out, float* colsum,
-                               void* stream);
+                               const void* aux, long long ld_aux, const void* gate, long long ld_gate, void* out,
+                               long long ld_out, float* colsum, void* stream);
 /* dW[e][N1, N2] += sum_{rows of expert e} A[row, N1]^T B[row, N2]  (fp32 red.add; caller zeroes dW). */
 int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
                           int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,
@@ -152,12 +152,26 @@ int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const float* w2,
                                   float* dlogit, float* dgate, void* dUT, void* dZ, float* part, float* dw2_db1_db2,
                                   float* mom_u, float* mom_z, int force_generic, void* stream);
 
-/* backward when dlocal == NULL (only global_feat = mean_p fused has a cotangent, as in BASELINE config 2 where the
- * contrastive loss consumes global_feat alone): dF is constant per image, so d fused / d Y is rank-1 per image.
- * Instead of dUT this writes row_dot [rows] (scratch), row_coef [rows] fp32 and row_img [rows] int32 for
- * mm_grouped_gemm_rows_rank1 (vecs = dglobal).  zscr: mm_combine_bwd_z_scratch_floats floats per item.
- * Requires mm_combine_bwd_global_supported(P, Ps, D) (Ps[0] == P, even integer scale ratios). */
+/* backward on the tensor-core / rank-1 path (even integer scale ratios, Ps[0] == P; mm_combine_bwd_*_supported).
+ * dF(p) = dlocal[b, p, :] + dglobal[b, :] / P splits into
+ *   - the per-image constant: d fused / d Y is rank-1 per image and never written; row_dot [rows] (scratch), row_coef [rows]
+ *     fp32 and row_img [rows] int32 feed mm_grouped_gemm_rows_rank1 (vecs = dglobal);
+ *   - the local part (dlocal bf16 [B, P, D]): dbeta by a tcgen05 GEMM against the staged Y rows (dbeta_loc [n_items, P, 4]
+ *     scratch) and dUT [rows, D] bf16 (the aux of the dY GEMM); mom_u as in mm_interp_softmax_combine_bwd.
+ * Either cotangent may be NULL (BASELINE config 2 has dlocal == NULL: the contrastive loss consumes global_feat alone).
+ * tile_info0 / n_tiles0 / region0_row / total_rows as in mm_interp_softmax_combine_fwd (needed when dlocal != NULL).
+ * zscr: mm_combine_bwd_z_scratch_floats floats per item. */
 int mm_combine_bwd_global_supported(int P, const int32_t* Ps, int D);
+int mm_combine_bwd_tc_supported(int P, const int32_t* Ps, int D);
+int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, const float* w2, int B, int topk, int P, const int32_t* Ps,
+                                     int D, int K, const int32_t* perm, const int32_t* inv_perm, const int32_t* slot_expert,
+                                     const int32_t* slot_row, const int32_t* counts, const int32_t* seg_start,
+                                     const int32_t* offsets, const int32_t* tile_info0, int n_tiles0, int region0_row,
+                                     long long total_rows, const float* gate, const float* beta, const void* dlocal,
+                                     const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
+                                     float* dbeta_loc, void* dUT, float* mom_u, float* dgate, void* dZ, float* part,
+                                     float* dw2_db1_db2, float* zscr, void* stream);
+/* the dlocal == NULL special case of the above (kept as its own entry point) */
 int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
                                          const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,
                                          const int32_t* slot_expert, const int32_t* slot_row, const int32_t* counts,

@@ -36,7 +36,7 @@ SIGNATURES = {
     "mm_grouped_gemm_rows": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                      c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_int, c_vp, c_f, c_int, c_vp]),
     "mm_grouped_gemm_rows_rank1": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int,
-                                           c_vp, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp]),
+                                           c_vp, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp]),
     "mm_grouped_gemm_wgrad": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                       c_vp, c_vp]),
     "mm_grouped_gemm_wgrad_colsum": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,
@@ -53,6 +53,10 @@ SIGNATURES = {
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "mm_combine_bwd_global_supported": (c_int, [c_int, c_vp, c_int]),
+    "mm_combine_bwd_tc_supported": (c_int, [c_int, c_vp, c_int]),
+    "mm_interp_softmax_combine_bwd_tc": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
+                                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp, c_vp,
+                                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mm_interp_softmax_combine_bwd_global": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp,
                                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                                      c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -70,7 +74,7 @@ SIGNATURES = {
 # entry points that return a plain value, not an mm_status
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats",
-                "mm_combine_bwd_global_supported"}
+                "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported"}
 
 
 def library_path() -> Path:

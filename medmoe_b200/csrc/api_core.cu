@@ -249,7 +249,7 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
                "mm_grouped_gemm_rows: aux and gate must be given together");
     MM_REQUIRE(!(gate && out_f32), MM_ERR_UNSUPPORTED, "mm_grouped_gemm_rows: aux/gate need a bf16 output");
     if (r1) {
-        MM_REQUIRE(!aux && r1->row_coef && r1->row_vec && r1->vecs && r1->ld_vecs >= N && r1->ld_vecs % 4 == 0 &&
+        MM_REQUIRE(r1->row_coef && r1->row_vec && r1->vecs && r1->ld_vecs >= N && r1->ld_vecs % 4 == 0 &&
                        (reinterpret_cast<uintptr_t>(r1->vecs) & 15) == 0,
                    MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows_rank1: row_coef / row_vec / vecs (16-byte aligned rows) required");
     }
@@ -309,7 +309,7 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
 #define MM_ROWS_CASE(bn)                                                                          \
     case bn:                                                                                      \
         if (out_f32) return launch_rows<bn, true, 0>(m, g, st);                                   \
-        if (r1) return launch_rows<bn, false, 2>(m, g, st);                                       \
+        if (r1) return aux ? launch_rows<bn, false, 3>(m, g, st) : launch_rows<bn, false, 2>(m, g, st);      \
         return aux ? launch_rows<bn, false, 1>(m, g, st) : launch_rows<bn, false, 0>(m, g, st);
     switch (BN) {
         MM_ROWS_CASE(256)
@@ -338,11 +338,11 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
 extern "C" int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
                                           long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
                                           const float* row_coef, const int32_t* row_vec, const float* vecs,
-                                          long long ld_vecs, const void* gate, long long ld_gate, void* out,
-                                          long long ld_out, float* colsum, void* stream) {
+                                          long long ld_vecs, const void* aux, long long ld_aux, const void* gate,
+                                          long long ld_gate, void* out, long long ld_out, float* colsum, void* stream) {
     MM_REQUIRE(tile_info, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows_rank1: tile_info required");
     const Rank1Aux r1{row_coef, row_vec, vecs, ld_vecs};
-    return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, nullptr, nullptr, 0, &r1,
+    return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, nullptr, aux, ld_aux, &r1,
                           gate, ld_gate, out, ld_out, 0, colsum, 1.0f, 0, stream);
 }
 

@@ -75,6 +75,7 @@ struct CombineArgs {
     int z_rows_path;                // dZ comes from the interval-prefix kernels: finalize only writes dUT
     int dlogit_is_halves;           // dlogit holds two column-half partial dbeta ([.., 2, 4]) instead of finished dlogit
     const float* row_dot;           // [rows] <dglobal[b], Y[row]> / P: dbeta is its lerp (rank-1 path, combine_rank1.cuh) or nullptr
+    const float* dbeta_loc;         // [n_items, P, 4] <dlocal(p), interp(Y_s)(p)> from the tensor-core kernel (cm_dbeta_kernel) or nullptr
     float* mom_u;                   // [n_items, nruns, 2, D]   zeroth / first moments of beta_s * dF per 32-token run
     float* mom_z;                   // [n_items, nruns, 2, D/2] same for dlogit_s * w2 * gate
 };
@@ -637,14 +638,20 @@ MM_DEVINL float4 token_dlogit(const CombineArgs& a, int slot, int p, float g, fl
     dot_out = 0.f;
     if (p < 0 || p >= a.P) return make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t tok = static_cast<size_t>(slot) * a.P + p;
-    if (a.row_dot) {             // dF is constant per image: dbeta_s(p) = interp(G_s)(p)
+    if (a.row_dot || a.dbeta_loc) {   // tensor-core / rank-1 path: dbeta = local part (GEMM) + interp(G_s)(p) (dF's per-image constant)
         const float4 bt = *reinterpret_cast<const float4*>(a.beta + tok * 4);
-        float d[4];
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.dbeta_loc) {
+            const float4 dl = *reinterpret_cast<const float4*>(a.dbeta_loc + tok * 4);
+            d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = dl.w;
+        }
+        if (a.row_dot) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
-            const float* G = a.row_dot + a.slot_row[s * a.n_items + slot];
-            d[s] = (1.0f - L.lam) * G[L.i0] + L.lam * G[L.i1];
+            for (int s = 0; s < 4; ++s) {
+                const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                const float* G = a.row_dot + a.slot_row[s * a.n_items + slot];
+                d[s] += (1.0f - L.lam) * G[L.i0] + L.lam * G[L.i1];
+            }
         }
         const float dot = bt.x * d[0] + bt.y * d[1] + bt.z * d[2] + bt.w * d[3];
         dot_out = dot;
@@ -1353,7 +1360,43 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
     return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");
 }
 
-// ---- backward when only global_feat has a cotangent (dlocal == NULL): rank-1 path, see combine_rank1.cuh ----
+// tensor-core dbeta (combine_mma.cuh): 0 = launched, 1 = does not apply, < 0 = error
+static int cm_launch_dbeta(CombineArgs& a, CdArgs& c, int D, long long total_rows, const void* dlocal, float* dbeta_loc,
+                           cudaStream_t st) {
+    CmArgs g{};
+    CombineArgs one = a;
+    one.topk = 1;
+    if (!c.tile_info || !cm_geometry(one, D, g) || a.P % 64 != 0 || D % 64 != 0) return 1;
+    for (int s = 0; s < 4; ++s) { a.ratio[s] = a.P / a.Ps[s]; c.cap[s] = g.cap[s]; c.koff[s] = g.koff[s]; }
+    c.ktot = g.ktot;
+    c.D = D;
+    c.n_kb = D / 64;
+    c.stages = 5;
+    c.dbeta_loc = dbeta_loc;
+    const size_t stage = static_cast<size_t>(TILE_M) * 128 + static_cast<size_t>(c.ktot) * 128;
+    while (c.stages > 2 && c.stages * stage + 512 + 1024 > 227 * 1024) --c.stages;
+    const size_t smem = c.stages * stage + 512 + 1024;
+    if (smem > 227 * 1024) return 1;
+    CUtensorMap tmDL, tmY[4];
+    int rc = mm::encode_tmap_bf16(&tmDL, dlocal, static_cast<uint64_t>(D), static_cast<uint64_t>(a.B) * a.P, static_cast<uint64_t>(D),
+                                  64, 64, "combine_dbeta(dlocal)");
+    if (rc) return rc;
+    for (int s = 0; s < 4; ++s) {
+        rc = mm::encode_tmap_bf16(&tmY[s], a.Y, static_cast<uint64_t>(D), static_cast<uint64_t>(total_rows),
+                                  static_cast<uint64_t>(D), 64, static_cast<uint32_t>(c.cap[s]), "combine_dbeta(Y)");
+        if (rc) return rc;
+    }
+    auto kern = cm_dbeta_kernel;
+    if (int r2 = opt_in_smem(kern, smem, "combine_dbeta(mma)")) return r2;
+    const int grid = c.n_tiles < mm::sm_count() ? c.n_tiles : mm::sm_count();
+    kern<<<grid, CD_THREADS, smem, st>>>(tmDL, tmY[0], tmY[1], tmY[2], tmY[3], a, c);
+    mm::note_launches(1);
+    return MM_OK;
+}
+
+// ---- backward on the tensor-core / rank-1 path (combine_rank1.cuh, combine_mma.cuh) ----
+//   dglobal != NULL : dF's per-image constant -> row_dot / row_coef / row_img (rank-1, never materialised)
+//   dlocal  != NULL : (bf16) dbeta by GEMM (cm_dbeta_kernel) and dUT [rows, D] bf16 (the local part of d fused / d Y)
 extern "C" int mm_combine_bwd_global_supported(int P, const int32_t* Ps, int D) {
     if (!(D == 256 || D == 512 || D == 768 || D == 1024)) return 0;
     CombineArgs a{};
@@ -1361,20 +1404,37 @@ extern "C" int mm_combine_bwd_global_supported(int P, const int32_t* Ps, int D) 
     for (int s = 0; s < 4; ++s) a.Ps[s] = Ps[s];
     return z_rows_path_ok(a) ? 1 : 0;
 }
-
-extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
-                                                    const int32_t* Ps, int D, int K, const int32_t* perm,
-                                                    const int32_t* inv_perm, const int32_t* slot_expert,
-                                                    const int32_t* slot_row, const int32_t* counts, const int32_t* seg_start,
-                                                    const int32_t* offsets, const float* gate, const float* beta,
-                                                    const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
-                                                    float* dgate, void* dZ, float* part, float* dw2_db1_db2, float* zscr,
-                                                    void* stream) {
+extern "C" int mm_combine_bwd_tc_supported(int P, const int32_t* Ps, int D) {
+    if (!mm_combine_bwd_global_supported(P, Ps, D)) return 0;
     CombineArgs a{};
-    int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_bwd_global");
+    a.P = P; a.topk = 1;
+    for (int s = 0; s < 4; ++s) a.Ps[s] = Ps[s];
+    CmArgs g{};
+    return (cm_geometry(a, D, g) && P % 64 == 0 && classify_scales(a)) ? 1 : 0;
+}
+
+extern "C" int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
+                                                const int32_t* Ps, int D, int K, const int32_t* perm,
+                                                const int32_t* inv_perm, const int32_t* slot_expert,
+                                                const int32_t* slot_row, const int32_t* counts, const int32_t* seg_start,
+                                                const int32_t* offsets, const int32_t* tile_info0, int n_tiles0,
+                                                int region0_row, long long total_rows, const float* gate, const float* beta,
+                                                const void* dlocal, const float* dglobal, float* row_dot, float* row_coef,
+                                                int32_t* row_img, float* dbeta_loc, void* dUT, float* mom_u, float* dgate,
+                                                void* dZ, float* part, float* dw2_db1_db2, float* zscr, void* stream) {
+    CombineArgs a{};
+    int rc = fill_common(a, B, topk, P, Ps, D, "mm_interp_softmax_combine_bwd_tc");
     if (rc) return rc;
-    if (!(Y && Z && w2 && beta && dglobal && row_dot && row_coef && row_img && dZ && part && dw2_db1_db2 && zscr)) {
-        mm::set_error("mm_interp_softmax_combine_bwd_global: null operand");
+    if (!(Y && Z && w2 && beta && dZ && part && dw2_db1_db2 && zscr && (dglobal || dlocal))) {
+        mm::set_error("mm_interp_softmax_combine_bwd_tc: null operand");
+        return MM_ERR_BAD_SHAPE;
+    }
+    if (dglobal && !(row_dot && row_coef && row_img)) {
+        mm::set_error("mm_interp_softmax_combine_bwd_tc: dglobal needs row_dot / row_coef / row_img");
+        return MM_ERR_BAD_SHAPE;
+    }
+    if (dlocal && !(dbeta_loc && dUT && mom_u && tile_info0)) {
+        mm::set_error("mm_interp_softmax_combine_bwd_tc: dlocal needs dbeta_loc / dUT / mom_u / tile_info0");
         return MM_ERR_BAD_SHAPE;
     }
     a.perm = perm; a.inv_perm = inv_perm; a.slot_expert = slot_expert; a.slot_row = slot_row; a.gate = gate;
@@ -1382,11 +1442,12 @@ extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z
     a.Y = static_cast<const __nv_bfloat16*>(Y); a.Z = static_cast<const __nv_bfloat16*>(Z);
     a.w2 = w2; a.beta = const_cast<float*>(beta);
     a.dglobal = dglobal; a.dgate = dgate; a.dZ = static_cast<__nv_bfloat16*>(dZ);
-    a.part = part; a.zscr = zscr; a.mom_z = zscr; a.row_dot = row_dot;
+    a.part = part; a.zscr = zscr; a.mom_z = zscr;
+    a.row_dot = dglobal ? row_dot : nullptr;
     a.nblk = mm_combine_num_token_blocks(P);
     a.nruns = mm_combine_num_runs(P);
     if (!z_rows_path_ok(a)) {
-        mm::set_error("mm_interp_softmax_combine_bwd_global: needs Ps[0] == P and even integer scale ratios (use mm_interp_softmax_combine_bwd)");
+        mm::set_error("mm_interp_softmax_combine_bwd_tc: needs Ps[0] == P and even integer scale ratios (use mm_interp_softmax_combine_bwd)");
         return MM_ERR_UNSUPPORTED;
     }
     for (int s = 0; s < 4; ++s) a.ratio[s] = P / Ps[s];
@@ -1395,7 +1456,7 @@ extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int total = Ps[0] + Ps[1] + Ps[2] + Ps[3];
     mm::trace_mark("begin", st);
-    {
+    if (dglobal) {
         dim3 grid((total + R1_WARPS * R1_ROWS_PER_WARP - 1) / (R1_WARPS * R1_ROWS_PER_WARP), a.n_items);
         switch (D) {
             case 256: rank1_rowdot_kernel<256><<<grid, R1_WARPS * 32, 0, st>>>(a, row_dot, row_img); break;
@@ -1405,12 +1466,52 @@ extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z
         }
         mm::note_launches(1);
         mm::trace_mark("combine_bwd.rowdot", st);
+        rank1_coef_kernel<<<dim3((total + 255) / 256, a.n_items), 256, 0, st>>>(a, row_coef);
+        mm::note_launches(1);
+        mm::trace_mark("combine_bwd.coef", st);
+        rc = mm_check_launch("mm_interp_softmax_combine_bwd_tc(rank-1)");
+        if (rc) return rc;
     }
-    rank1_coef_kernel<<<dim3((total + 255) / 256, a.n_items), 256, 0, st>>>(a, row_coef);
-    mm::note_launches(1);
-    mm::trace_mark("combine_bwd.coef", st);
-    rc = mm_check_launch("mm_interp_softmax_combine_bwd_global(rank-1)");
-    if (rc) return rc;
+    if (dlocal) {
+        CdArgs cd{};
+        cd.n_tiles = n_tiles0;
+        cd.tile_info = reinterpret_cast<const int2*>(tile_info0);
+        cd.region_row0 = region0_row;
+        cd.seg_start = seg_start; cd.offsets = offsets; cd.K = K;
+        const int r = cm_launch_dbeta(a, cd, D, total_rows, dlocal, dbeta_loc, st);
+        if (r < 0) return r;
+        if (r != 0) {
+            mm::set_error("mm_interp_softmax_combine_bwd_tc: geometry not supported (check mm_combine_bwd_tc_supported)");
+            return MM_ERR_UNSUPPORTED;
+        }
+        a.dbeta_loc = dbeta_loc;
+        mm::trace_mark("combine_bwd.dbeta", st);
+        // dUT = C^T dlocal (local part only: the dglobal part stays rank-1): token-centric CUDA-core kernel
+        CombineArgs u = a;
+        u.dlocal = dlocal; u.dglobal = nullptr; u.dUT = static_cast<__nv_bfloat16*>(dUT); u.mom_u = mom_u;
+        if (!classify_scales(u)) {
+            mm::set_error("mm_interp_softmax_combine_bwd_tc: scale ratios not supported by the dUT kernel");
+            return MM_ERR_UNSUPPORTED;
+        }
+        u.z_rows_path = 1;      // the finalize kernel then only writes dUT
+        dim3 grid((2 * u.nruns + 7) / 8, u.n_items);
+        MM_DISPATCH_D(D, 0, combine_bwd_u_kernel, grid, st, u)
+        mm::note_launches(1);
+        for (int s = 1; s < 4; ++s) {
+            if (u.mode[s] != SCALE_MOMENT) continue;
+            dim3 gridf((u.Ps[s] + 7) / 8, u.n_items);
+            switch (D) {
+                case 256: combine_bwd_finalize_kernel<256><<<gridf, 256, 0, st>>>(u, s); break;
+                case 512: combine_bwd_finalize_kernel<512><<<gridf, 256, 0, st>>>(u, s); break;
+                case 768: combine_bwd_finalize_kernel<768><<<gridf, 256, 0, st>>>(u, s); break;
+                case 1024: combine_bwd_finalize_kernel<1024><<<gridf, 256, 0, st>>>(u, s); break;
+            }
+            mm::note_launches(1);
+        }
+        mm::trace_mark("combine_bwd.dUT", st);
+        rc = mm_check_launch("mm_interp_softmax_combine_bwd_tc(dUT)");
+        if (rc) return rc;
+    }
     switch (D) {
         case 256: rc = launch_bwd_z_rows_path<256>(a, st); break;
         case 512: rc = launch_bwd_z_rows_path<512>(a, st); break;
@@ -1422,5 +1523,23 @@ extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z
     expert_reduce_kernel<<<dim3((C + 31) / 32, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
     mm::note_launches(1);
     mm::trace_mark("combine_bwd.expert_reduce", st);
-    return mm_check_launch("mm_interp_softmax_combine_bwd_global(reduce)");
+    return mm_check_launch("mm_interp_softmax_combine_bwd_tc(reduce)");
+}
+
+extern "C" int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
+                                                    const int32_t* Ps, int D, int K, const int32_t* perm,
+                                                    const int32_t* inv_perm, const int32_t* slot_expert,
+                                                    const int32_t* slot_row, const int32_t* counts, const int32_t* seg_start,
+                                                    const int32_t* offsets, const float* gate, const float* beta,
+                                                    const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
+                                                    float* dgate, void* dZ, float* part, float* dw2_db1_db2, float* zscr,
+                                                    void* stream) {
+    if (!dglobal) {
+        mm::set_error("mm_interp_softmax_combine_bwd_global: dglobal is NULL");
+        return MM_ERR_BAD_SHAPE;
+    }
+    return mm_interp_softmax_combine_bwd_tc(Y, Z, w2, B, topk, P, Ps, D, K, perm, inv_perm, slot_expert, slot_row, counts,
+                                            seg_start, offsets, nullptr, 0, 0, 0, gate, beta, nullptr, dglobal, row_dot,
+                                            row_coef, row_img, nullptr, nullptr, nullptr, dgate, dZ, part, dw2_db1_db2, zscr,
+                                            stream);
 }

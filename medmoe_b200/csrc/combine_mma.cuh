@@ -690,4 +690,196 @@ static inline size_t cl_smem_bytes(const ClArgs& c) {
            static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 2 * CL_MAX_ACC + 2) * 8 + 16 + 1024;
 }
 
+// =======================================================================================
+// Backward pass A on the tensor cores (general path: local_feat has a cotangent).
+//
+//   dbeta_s(p) = <dF(p), interp(Y_s)(p)>                                  (autograd of swin.py:78-80)
+//
+// For a tile of 128 tokens this is a dense GEMM followed by a 7-entry gather:
+//   G[128 tokens, 192 rows] = dlocal_tile[128, D] * Yrows[192, D]^T        (both operands K-major, K = D)
+//   dbeta_s(p) = (1 - lam) G[p, row_a] + lam G[p, row_b]
+// — the same staged row ranges as the forward, now as the N dimension.  The constant dglobal / P part of dF is not
+// folded in here: it contributes interp(<dglobal, Y[row]> / P), which the rank-1 path already provides (row_dot).
+// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+// Requirements: cm_geometry (any top-k) and P % 64 == 0 (a 64-token half tile belongs to one image); dlocal bf16.
+// =======================================================================================
+constexpr int CD_THREADS = 256;
+
+struct CdArgs {
+    int n_tiles;
+    const int2* tile_info;
+    int region_row0;
+    const int* seg_start;
+    const int* offsets;
+    int K;
+    int cap[4], koff[4], ktot;
+    int D, n_kb, stages;
+    float* dbeta_loc;            // [n_items, P, 4]
+};
+
+// v[idx] for a thread-dependent idx in [0, 32) without local memory
+MM_DEVINL float cm_pick32(const uint32_t (&v)[32], int idx) {
+    uint32_t r = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) r = (idx == j) ? v[j] : r;
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(CD_THREADS, 1)
+cm_dbeta_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant__ CUtensorMap tmY0,
+                const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2,
+                const __grid_constant__ CUtensorMap tmY3, const CombineArgs a, const CdArgs c) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int A_BYTES = TILE_M * 128;                        // 128 tokens x 64 channels
+    const int b_bytes = c.ktot * 128;                            // ktot rows x 64 channels
+    const int stage_bytes = A_BYTES + b_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + c.stages * stage_bytes);
+    uint64_t* empty = full + 8;
+    uint64_t* tfull = empty + 8;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDL); tma_prefetch_desc(&tmY0); tma_prefetch_desc(&tmY1); tma_prefetch_desc(&tmY2); tma_prefetch_desc(&tmY3);
+    }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < c.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int2 ti = c.tile_info[t];
+            const int e = ti.x;
+            if (e < 0) continue;
+            const int row0 = c.region_row0 + t * TILE_M;
+            const int rel0 = row0 - c.seg_start[e];
+            int row_s[4], row_dl[2];
+            row_s[0] = row0;
+#pragma unroll
+            for (int s = 1; s < 4; ++s) row_s[s] = c.seg_start[s * c.K + e] + rel0 / a.ratio[s] - 1;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {     // the two 64-token halves may belong to different images
+                const int rel = rel0 + hh * 64;
+                row_dl[hh] = 0;
+                if (hh * 64 < ti.y) {
+                    const int j = rel / a.P, p = rel - j * a.P;
+                    row_dl[hh] = (a.perm[c.offsets[e] + j] / a.topk) * a.P + p;
+                }
+            }
+            for (int kb = 0; kb < c.n_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], static_cast<uint32_t>(stage_bytes));
+                uint8_t* dA = smem + stage * stage_bytes;
+                uint8_t* dB = dA + A_BYTES;
+                tma_load_2d(dA, &tmDL, &full[stage], kb * 64, row_dl[0]);
+                tma_load_2d(dA + 8192, &tmDL, &full[stage], kb * 64, row_dl[1]);
+                tma_load_2d(dB + c.koff[0] * 128, &tmY0, &full[stage], kb * 64, row_s[0]);
+                tma_load_2d(dB + c.koff[1] * 128, &tmY1, &full[stage], kb * 64, row_s[1]);
+                tma_load_2d(dB + c.koff[2] * 128, &tmY2, &full[stage], kb * 64, row_s[2]);
+                tma_load_2d(dB + c.koff[3] * 128, &tmY3, &full[stage], kb * 64, row_s[3]);
+                if (++stage == c.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_bf16(TILE_M, c.ktot, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            if (c.tile_info[t].x < 0) continue;
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kb = 0; kb < c.n_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+                const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
+                              (kb | k) != 0);
+                umma_commit(&empty[stage]);
+                if (++stage == c.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: thread = token, gather its 7 entries of G =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        int q0[4];
+        q0[0] = m;
+#pragma unroll
+        for (int s = 1; s < 4; ++s) q0[s] = cm_floor_div(2 * m + 1 - a.ratio[s], 2 * a.ratio[s]) + 1;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int2 ti = c.tile_info[t];
+            const int e = ti.x;
+            if (e < 0) continue;
+            // lerp weights of this token (positions q0[s], q0[s] + 1 of scale s), as in the forward
+            float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+            size_t tok = 0;
+            const bool valid = m < ti.y;
+            if (valid) {
+                const int rel0 = c.region_row0 + t * TILE_M - c.seg_start[e];
+                const int rel = rel0 + m;
+                const int j = rel / a.P, p = rel - j * a.P;
+                const int slot = c.offsets[e] + j;
+                tok = static_cast<size_t>(slot) * a.P + p;
+#pragma unroll
+                for (int s = 1; s < 4; ++s) {
+                    const int r = a.ratio[s];
+                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                    const int fs = c.seg_start[s * c.K + e] + rel0 / r - 1;
+                    const int base = a.slot_row[s * a.n_items + slot];
+                    const int qa = base + L.i0 - fs, qb = base + L.i1 - fs;
+                    va[s] = (qa == q0[s] ? 1.0f - L.lam : 0.f) + (qb == q0[s] ? L.lam : 0.f);
+                    vb[s] = (qa == q0[s] + 1 ? 1.0f - L.lam : 0.f) + (qb == q0[s] + 1 ? L.lam : 0.f);
+                }
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+            float d[4];
+            {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c.koff[0] + q * 32, v);      // diagonal block of the finest scale
+                tmem_ld_wait();
+                d[0] = cm_pick32(v, lane);
+            }
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+                const int qbase = __shfl_sync(0xffffffffu, q0[s], 0);      // lane 0 has the warp's smallest position
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c.koff[s] + qbase, v);
+                tmem_ld_wait();
+                const int idx = q0[s] - qbase;
+                d[s] = va[s] * cm_pick32(v, idx) + vb[s] * cm_pick32(v, idx + 1);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (valid) *reinterpret_cast<float4*>(c.dbeta_loc + tok * 4) = make_float4(d[0], d[1], d[2], d[3]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace mm

@@ -50,7 +50,7 @@ struct RowsGemmArgs {
     float* colsum;           // [E, N] fp32, += column sums of the written tile (bias gradients) or nullptr
     float out_scale;         // multiplies the accumulator before bias (1.0 for the MoE path)
     int flags;
-    // AUX == 2 ("rank-1 aux"): aux[row, col] = row_coef[row] * vecs[row_vec[row], col], never materialised
+    // AUX bit 1 ("rank-1 aux"): aux[row, col] = row_coef[row] * vecs[row_vec[row], col], never materialised
     const float* row_coef;   // [rows] fp32
     const int* row_vec;      // [rows] index of the row's vector
     const float* vecs;       // [n_vecs, ld_vecs] fp32
@@ -70,8 +70,8 @@ struct WgradArgs {
 constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
 constexpr int rows_threads(int epi_warps) { return (4 + epi_warps) * 32; }   // gemm_rows_kernel: 4 role warps + epilogue warps
 
-// AUX: 0 = plain epilogue, 1 = out = (acc + aux) * [gate > 0] with aux/gate tiles TMA-prefetched,
-//      2 = same with aux given as a rank-1 product (only the gate tile is loaded)
+// AUX (bit flags): 0 = plain epilogue; otherwise out = (acc + aux) * [gate > 0] with the gate tile TMA-prefetched and
+//      bit 0: aux tile, TMA-prefetched next to the gate;  bit 1: rank-1 aux coef[row] * vec[idx[row]] (never materialised)
 template <int BN, int STAGES, int AUX = 0, int EPI_WARPS = 8>
 struct GemmSmem {
     static constexpr int A_BYTES = TILE_M * 64 * 2;                 // 16 KB: 128 rows x 64 bf16 (K-major) or 2 x (64 k-rows x 64 mn)
@@ -79,7 +79,7 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_SLOTS = (AUX || EPI_WARPS > 8) ? 1 : 2;                // output staging slots per epilogue warp
     static constexpr int EPI_OUT_BYTES = EPI_WARPS * OUT_SLOTS * EPI_SLOT_BYTES;
-    static constexpr int IN_PER = (AUX == 1) ? 2 : 1;                               // prefetched tiles per buffer: {aux, gate} or {gate}
+    static constexpr int IN_PER = (AUX & 1) ? 2 : 1;                               // prefetched tiles per buffer: {aux, gate} or {gate}
     static constexpr int EPI_IN_BYTES = AUX ? EPI_WARPS * 2 * IN_PER * EPI_SLOT_BYTES : 0;   // double-buffered
     static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;   // + alignment slack
@@ -127,7 +127,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (!OUT_F32) tma_prefetch_desc(&tmOut);
-        if (AUX == 1) tma_prefetch_desc(&tmAux);
+        if (AUX & 1) tma_prefetch_desc(&tmAux);
         if (AUX) tma_prefetch_desc(&tmGate);
     }
     if (threadIdx.x == 32) {
@@ -229,8 +229,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         auto issue_in = [&](int w, int c, int slot) {   // lane 0 only
             const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
             const int row0 = lt * TILE_M + q * 32, col0 = nt * BN + c * 32;
-            mbar_expect_tx(&my_bar[slot], (AUX == 1 ? 2 : 1) * EPI_SLOT_BYTES);
-            if (AUX == 1) tma_load_2d(my_in + slot * IN_BUF, &tmAux, &my_bar[slot], col0, row0);
+            mbar_expect_tx(&my_bar[slot], ((AUX & 1) ? 2 : 1) * EPI_SLOT_BYTES);
+            if (AUX & 1) tma_load_2d(my_in + slot * IN_BUF, &tmAux, &my_bar[slot], col0, row0);
             tma_load_2d(my_in + slot * IN_BUF + (S::IN_PER - 1) * EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
         };
 
@@ -251,7 +251,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool row_valid = r_in_tile < valid;
             float r1_coef = 0.f;
             const float* r1_vec = a.vecs;
-            if (AUX == 2 && row_valid) {     // issued before the accumulator wait: the two dependent loads hide behind it
+            if ((AUX & 2) && row_valid) {     // issued before the accumulator wait: the two dependent loads hide behind it
                 r1_coef = __ldg(a.row_coef + row);
                 r1_vec = a.vecs + static_cast<long long>(__ldg(a.row_vec + row)) * a.ld_vecs;
             }
@@ -270,7 +270,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 const int col0 = nt * BN + c * 32;
                 float4 xv[8];
-                if (AUX == 2) {      // rank-1 aux vector: issued before the TMEM wait so that both latencies overlap
+                if (AUX & 2) {      // rank-1 aux vector: issued before the TMEM wait so that both latencies overlap
                     const float4* vp = reinterpret_cast<const float4*>(r1_vec + col0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) xv[j] = __ldg(vp + j);
@@ -297,7 +297,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     iphase[islot] ^= 1;
                     const uint8_t* ax = my_in + islot * IN_BUF;
                     const uint8_t* gt = ax + (S::IN_PER - 1) * EPI_SLOT_BYTES;
-                    if (AUX == 2) {
+                    if (AUX & 2) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             f[4 * j + 0] = fmaf(r1_coef, xv[j].x, f[4 * j + 0]); f[4 * j + 1] = fmaf(r1_coef, xv[j].y, f[4 * j + 1]);
@@ -307,7 +307,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 g = *reinterpret_cast<const uint4*>(gt + epi_slot_off(lane, j));
-                        if (AUX == 1) {
+                        if (AUX & 1) {
                             const uint4 u = *reinterpret_cast<const uint4*>(ax + epi_slot_off(lane, j));
                             f[8 * j + 0] += bf16lo(u.x); f[8 * j + 1] += bf16hi(u.x);
                             f[8 * j + 2] += bf16lo(u.y); f[8 * j + 3] += bf16hi(u.y);

@@ -145,14 +145,25 @@ class _ExpertsFunction(torch.autograd.Function):
         W1T = ops.transpose_cast_bf16(W1_32.float()).view(E * D, H)          # [E, D, H]
         # conv bias gradients = column sums of dPre: they come out of the dWp weight-gradient MMAs (ones block)
         dbp = [torch.zeros(E, D, dtype=torch.float32, device=dev) for _ in range(S)]
-        if dfused is None and not ops.FORCE_GENERIC_COMBINE_BWD and ops.combine_bwd_global_supported(plan, D):
-            # only global_feat has a cotangent: d fused / d Y is rank-1 per image and is rebuilt in the dY epilogue
-            row_coef, row_img, dZ, dw2, db1, db2, dgate = ops.combine_bwd_global(Y, Z, w2, plan, D, gate_flat, beta, dglobal32,
-                                                                                ctx.gate_needs_grad)
+        use_tc = not ops.FORCE_GENERIC_COMBINE_BWD and (
+            ops.combine_bwd_global_supported(plan, D) if dfused is None else ops.combine_bwd_tc_supported(plan, D))
+        if use_tc:
+            # tensor-core / rank-1 path: dF = dlocal + dglobal / P.  The per-image constant part of d fused / d Y is rank-1
+            # (rebuilt in the dY epilogue, never written); the local part goes through a tcgen05 GEMM (dbeta) and dUT.
+            dlocal16 = None
+            if dfused is not None:
+                dlocal16 = dfused if dfused.dtype == torch.bfloat16 else ops.cast_bf16(dfused)
+            row_coef, row_img, dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd_tc(Y, Z, w2, plan, D, gate_flat, beta, dlocal16,
+                                                                                  dglobal32, ctx.gate_needs_grad)
             # one launch over the whole row space: every scale shares W1, and the rank-1 tables are indexed by global row
-            dPre = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
-            ops.gemm_rows_rank1(dZ, W1T, D, dPre, plan=plan, tile_begin=0, tile_count=layout.total_tiles, row_coef=row_coef,
-                                row_vec=row_img, vecs=dglobal32, gate=Y, tag="dY")
+            if dglobal32 is not None:
+                dPre = dUT if dUT is not None else torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
+                ops.gemm_rows_rank1(dZ, W1T, D, dPre, plan=plan, tile_begin=0, tile_count=layout.total_tiles, row_coef=row_coef,
+                                    row_vec=row_img, vecs=dglobal32, gate=Y, aux=dUT, tag="dY")
+            else:
+                ops.gemm_rows(dZ, W1T, D, dUT, plan=plan, tile_begin=0, tile_count=layout.total_tiles, aux=dUT, gate=Y,
+                              flags=ops.EPI_ZERO_PAD, tag="dY")
+                dPre = dUT
         else:
             dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
                                                             ctx.gate_needs_grad)

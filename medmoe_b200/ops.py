@@ -156,13 +156,14 @@ def gemm_rows(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, pl
 
 def gemm_rows_rank1(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, plan: DispatchPlan, tile_begin: int,
                     tile_count: int, row_coef: torch.Tensor, row_vec: torch.Tensor, vecs: torch.Tensor, gate: torch.Tensor,
-                    colsum=None, tag: str = ""):
-    """out[row] = (A[row] W_e^T + row_coef[row] * vecs[row_vec[row]]) * [gate[row] > 0] (rank-1 aux, never materialised)."""
-    _need_cuda(A, W, out, row_coef, row_vec, vecs, gate)
+                    aux: Optional[torch.Tensor] = None, colsum=None, tag: str = ""):
+    """out[row] = (A[row] W_e^T + row_coef[row] * vecs[row_vec[row]] [+ aux[row]]) * [gate[row] > 0]
+    (the rank-1 aux is never materialised)."""
+    _need_cuda(A, W, out, row_coef, row_vec, vecs, gate, aux)
     E = W.shape[0] // N
     _lib.call("mm_grouped_gemm_rows_rank1", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(W), E, N, W.stride(0),
-              _P(plan.tile_info), tile_begin, tile_count, _P(row_coef), _P(row_vec), _P(vecs), vecs.stride(0), _P(gate),
-              gate.stride(0), _P(out), out.stride(0), _P(colsum), _st(),
+              _P(plan.tile_info), tile_begin, tile_count, _P(row_coef), _P(row_vec), _P(vecs), vecs.stride(0), _P(aux),
+              aux.stride(0) if aux is not None else 0, _P(gate), gate.stride(0), _P(out), out.stride(0), _P(colsum), _st(),
               label=f"{tag}:gemm_rows_rank1[K={A.shape[1]},N={N}]")
     return out
 
@@ -235,29 +236,45 @@ def combine_bwd_global_supported(plan: DispatchPlan, D: int) -> bool:
     return bool(_lib.call("mm_combine_bwd_global_supported", lay.P[0], _lib.host_i32(lay.P), D))
 
 
-def combine_bwd_global(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dglobal, need_dgate: bool):
-    """Backward of the combine when only global_feat has a cotangent: returns (row_coef, row_img, dZ, dw2, db1, db2, dgate);
-    d fused / d Y = row_coef[row] * dglobal[row_img[row]] is rebuilt inside the dY GEMM (gemm_rows_rank1)."""
+def combine_bwd_tc_supported(plan: DispatchPlan, D: int) -> bool:
     lay = plan.layout
-    _need_cuda(Y, Z, w2, beta, dglobal)
+    return bool(_lib.call("mm_combine_bwd_tc_supported", lay.P[0], _lib.host_i32(lay.P), D))
+
+
+def combine_bwd_tc(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool):
+    """Backward of the combine on the tensor-core / rank-1 path.  dlocal: bf16 [B, P, D] or None; dglobal: fp32 [B, D] or None.
+    Returns (row_coef, row_img, dUT, dZ, dw2, db1, db2, dgate): d fused / d Y = dUT (local part, None without dlocal)
+    + row_coef[row] * dglobal[row_img[row]] (rebuilt inside the dY GEMM, None without dglobal)."""
+    lay = plan.layout
+    _need_cuda(Y, Z, w2, beta, dlocal, dglobal)
     B, P, K = lay.n_images, lay.P[0], lay.num_experts
     dev = Y.device
     f32 = dict(dtype=torch.float32, device=dev)
     nrb = _lib.call("mm_combine_num_part_blocks", P, _lib.host_i32(lay.P))
     zscr = torch.empty(lay.n_items, _lib.call("mm_combine_bwd_z_scratch_floats", P, _lib.host_i32(lay.P), D), **f32)
-    row_dot = torch.empty(lay.total_rows, **f32)
-    row_coef = torch.empty(lay.total_rows, **f32)
-    row_img = torch.empty(lay.total_rows, dtype=torch.int32, device=dev)
+    row_dot = row_coef = row_img = dbeta_loc = dUT = mom_u = None
+    if dglobal is not None:
+        row_dot = torch.empty(lay.total_rows, **f32)
+        row_coef = torch.empty(lay.total_rows, **f32)
+        row_img = torch.empty(lay.total_rows, dtype=torch.int32, device=dev)
+    if dlocal is not None:
+        if dlocal.dtype != torch.bfloat16 or not dlocal.is_contiguous():
+            raise RuntimeError("combine_bwd_tc: dlocal must be a contiguous bf16 [B, P, D] tensor")
+        dbeta_loc = torch.empty(lay.n_items, P, 4, **f32)
+        dUT = torch.empty(lay.total_rows, D, dtype=torch.bfloat16, device=dev)
+        mom_u = torch.empty(lay.n_items, _lib.call("mm_combine_num_runs", P), 2, D, **f32)
     dgate = torch.zeros(lay.n_items, **f32) if need_dgate else None
     dZ = torch.empty(lay.total_rows, D // 2, dtype=torch.bfloat16, device=dev)
     part = torch.empty(lay.n_items, nrb, D + 1, **f32)
     red = torch.empty(K, D + 1, **f32)
-    _lib.call("mm_interp_softmax_combine_bwd_global", _P(Y), _P(Z), _P(w2), B, lay.topk, P, _lib.host_i32(lay.P), D, K,
+    tile0 = plan.tile_info[lay.tile_base[0]:lay.tile_base[0] + lay.region_tiles[0]]
+    _lib.call("mm_interp_softmax_combine_bwd_tc", _P(Y), _P(Z), _P(w2), B, lay.topk, P, _lib.host_i32(lay.P), D, K,
               _P(plan.perm), _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(plan.counts),
-              _P(plan.seg_start), _P(plan.offsets), _P(gate), _P(beta), _P(dglobal), _P(row_dot), _P(row_coef),
-              _P(row_img), _P(dgate), _P(dZ), _P(part), _P(red), _P(zscr), _st())
+              _P(plan.seg_start), _P(plan.offsets), _P(tile0), lay.region_tiles[0], lay.region_base[0], Y.shape[0],
+              _P(gate), _P(beta), _P(dlocal), _P(dglobal), _P(row_dot), _P(row_coef), _P(row_img), _P(dbeta_loc), _P(dUT),
+              _P(mom_u), _P(dgate), _P(dZ), _P(part), _P(red), _P(zscr), _st())
     H = D // 2
-    return row_coef, row_img, dZ, red[:, :H], red[:, H:2 * H], red[:, 2 * H], dgate
+    return row_coef, row_img, dUT, dZ, red[:, :H], red[:, H:2 * H], red[:, 2 * H], dgate
 
 
 # ---- losses ---------------------------------------------------------------------------

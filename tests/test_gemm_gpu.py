@@ -196,8 +196,8 @@ def test_wgrad_region_subrange():
         assert err <= 1e-3 * max(1.0, ref.abs().max().item()), f"expert {e}: max abs err {err}"
 
 
-@pytest.mark.parametrize("K,N", [(384, 768), (768, 384), (128, 256)])
-def test_grouped_rows_gemm_rank1_aux(K, N):
+@pytest.mark.parametrize("K,N,with_aux", [(384, 768, False), (768, 384, False), (128, 256, False), (384, 768, True)])
+def test_grouped_rows_gemm_rank1_aux(K, N, with_aux):
     """mm_grouped_gemm_rows_rank1: out = (A W_e^T + row_coef[row] * vecs[row_vec[row]]) * [gate > 0]; tiles no expert owns
     come back zero-filled (the combine kernels stage whole row ranges and rely on finite contents)."""
     n_items, E, P = 37, 4, [49, 20]
@@ -212,9 +212,11 @@ def test_grouped_rows_gemm_rank1_aux(K, N):
     row_coef = torch.randn(rows, device="cuda", generator=g)
     row_vec = torch.randint(0, n_vec, (rows,), device="cuda", generator=g, dtype=torch.int32)
     out = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    aux = _bf16(rows, N, seed=29) if with_aux else None
     _lib.call("mm_grouped_gemm_rows_rank1", _lib.ptr(A), rows, K, A.stride(0), _lib.ptr(W), E, N, W.stride(0),
               _lib.ptr(plan.tile_info), 0, layout.total_tiles, _lib.ptr(row_coef), _lib.ptr(row_vec), _lib.ptr(vecs),
-              vecs.stride(0), _lib.ptr(gate), gate.stride(0), _lib.ptr(out), out.stride(0), 0, _lib.stream_ptr())
+              vecs.stride(0), _lib.ptr(aux), N if with_aux else 0, _lib.ptr(gate), gate.stride(0), _lib.ptr(out),
+              out.stride(0), 0, _lib.stream_ptr())
     torch.cuda.synchronize()
     row_e = _row_expert(layout, plan)
     valid = row_e >= 0
@@ -222,7 +224,8 @@ def test_grouped_rows_gemm_rank1_aux(K, N):
     ref = torch.zeros(rows, N, device="cuda")
     for e in range(E):
         m = row_e == e
-        ref[m] = (A[m].float() @ Wf[e].t() + row_coef[m, None] * vecs[row_vec[m].long()]) * (gate[m] > 0)
+        ref[m] = (A[m].float() @ Wf[e].t() + row_coef[m, None] * vecs[row_vec[m].long()]
+                  + (aux[m].float() if with_aux else 0.0)) * (gate[m] > 0)
     got = out.float()
     assert torch.isfinite(got).all()                     # every tile is written: owned (result / zero padding) or zero-filled
     assert (got[~valid] == 0).all()
