@@ -244,9 +244,10 @@ def main():
         else:
             g_loss = loss_mod(gf.float(), d["txt"], temp3=10.0)
         loss = 0.5 * g_loss + 2.0 * F.cross_entropy(probs, d["labels"])
-        if cot_local is not None:
-            loss = loss + (lf * cot_local).sum().float()
-        loss.backward()
+        if cot_local is not None:     # a dense synthetic cotangent for local_feat, handed straight to autograd (no glue kernels)
+            torch.autograd.backward([loss, lf], [None, cot_local])
+        else:
+            loss.backward()
         if world > 1:   # DDP gradient averaging, one flat bucket over NVLink
             grads = [p.grad for p in params]
             flat = torch._utils._flatten_dense_tensors(grads)

@@ -171,6 +171,8 @@ int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, const float* 
                                      const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
                                      float* dbeta_loc, void* dUT, float* mom_u, float* dgate, void* dZ, float* part,
                                      float* dw2_db1_db2, float* zscr, void* stream);
+/* test hook: 1 = compute dUT with the CUDA-core kernel instead of the tcgen05 one (process-wide) */
+void mm_debug_force_cuda_core_dut(int on);
 /* the dlocal == NULL special case of the above (kept as its own entry point) */
 int mm_interp_softmax_combine_bwd_global(const void* Y, const void* Z, const float* w2, int B, int topk, int P,
                                          const int32_t* Ps, int D, int K, const int32_t* perm, const int32_t* inv_perm,

@@ -54,6 +54,7 @@ SIGNATURES = {
                                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "mm_combine_bwd_global_supported": (c_int, [c_int, c_vp, c_int]),
     "mm_combine_bwd_tc_supported": (c_int, [c_int, c_vp, c_int]),
+    "mm_debug_force_cuda_core_dut": (None, [c_int]),
     "mm_interp_softmax_combine_bwd_tc": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -74,7 +75,8 @@ SIGNATURES = {
 # entry points that return a plain value, not an mm_status
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats",
-                "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported"}
+                "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported",
+                "mm_debug_force_cuda_core_dut"}
 
 
 def library_path() -> Path:

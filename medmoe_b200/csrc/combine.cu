@@ -1394,6 +1394,9 @@ static int cm_launch_dbeta(CombineArgs& a, CdArgs& c, int D, long long total_row
     return MM_OK;
 }
 
+static int force_cuda_core_dut = 0;     // test hook (mm_debug_force_cuda_core_dut): run the CUDA-core dUT kernel instead of cm_dut_kernel
+extern "C" void mm_debug_force_cuda_core_dut(int on) { force_cuda_core_dut = on; }
+
 // ---- backward on the tensor-core / rank-1 path (combine_rank1.cuh, combine_mma.cuh) ----
 //   dglobal != NULL : dF's per-image constant -> row_dot / row_coef / row_img (rank-1, never materialised)
 //   dlocal  != NULL : (bf16) dbeta by GEMM (cm_dbeta_kernel) and dUT [rows, D] bf16 (the local part of d fused / d Y)
@@ -1486,27 +1489,55 @@ extern "C" int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, co
         }
         a.dbeta_loc = dbeta_loc;
         mm::trace_mark("combine_bwd.dbeta", st);
-        // dUT = C^T dlocal (local part only: the dglobal part stays rank-1): token-centric CUDA-core kernel
-        CombineArgs u = a;
-        u.dlocal = dlocal; u.dglobal = nullptr; u.dUT = static_cast<__nv_bfloat16*>(dUT); u.mom_u = mom_u;
-        if (!classify_scales(u)) {
-            mm::set_error("mm_interp_softmax_combine_bwd_tc: scale ratios not supported by the dUT kernel");
-            return MM_ERR_UNSUPPORTED;
-        }
-        u.z_rows_path = 1;      // the finalize kernel then only writes dUT
-        dim3 grid((2 * u.nruns + 7) / 8, u.n_items);
-        MM_DISPATCH_D(D, 0, combine_bwd_u_kernel, grid, st, u)
-        mm::note_launches(1);
-        for (int s = 1; s < 4; ++s) {
-            if (u.mode[s] != SCALE_MOMENT) continue;
-            dim3 gridf((u.Ps[s] + 7) / 8, u.n_items);
-            switch (D) {
-                case 256: combine_bwd_finalize_kernel<256><<<gridf, 256, 0, st>>>(u, s); break;
-                case 512: combine_bwd_finalize_kernel<512><<<gridf, 256, 0, st>>>(u, s); break;
-                case 768: combine_bwd_finalize_kernel<768><<<gridf, 256, 0, st>>>(u, s); break;
-                case 1024: combine_bwd_finalize_kernel<1024><<<gridf, 256, 0, st>>>(u, s); break;
-            }
+        // dUT = C^T dlocal (local part only: the dglobal part stays rank-1)
+        bool dut_mma = !(force_cuda_core_dut);
+        for (int s = 1; s < 4; ++s) dut_mma = dut_mma && a.ratio[s] >= 2 && a.ratio[s] <= 2 * CU_HALO;
+        if (dut_mma) {      // tensor cores: tile-owned rows, 32-token halo (combine_mma.cuh)
+            CuArgs cu{};
+            cu.n_tiles = n_tiles0;
+            cu.tile_info = reinterpret_cast<const int2*>(tile_info0);
+            cu.region_row0 = region0_row;
+            cu.seg_start = seg_start; cu.offsets = offsets; cu.counts = counts; cu.K = K;
+            int orow = 0;
+            for (int s = 1; s < 4; ++s) { cu.n_own[s] = TILE_M / a.ratio[s]; cu.o_row[s] = orow; orow += cu.n_own[s]; }
+            cu.D = D;
+            cu.n_pass = D / CU_BN;
+            cu.dUT = static_cast<__nv_bfloat16*>(dUT);
+            CUtensorMap tmDL, tmOut;
+            rc = mm::encode_tmap_bf16(&tmDL, dlocal, static_cast<uint64_t>(D), static_cast<uint64_t>(B) * P, static_cast<uint64_t>(D),
+                                      64, 32, "combine_dut(dlocal)");
+            if (rc) return rc;
+            rc = mm::encode_tmap_bf16_swz(&tmOut, dUT, static_cast<uint64_t>(D), static_cast<uint64_t>(total_rows),
+                                          static_cast<uint64_t>(D), 32, 32, 64, "combine_dut(dUT)");
+            if (rc) return rc;
+            const size_t smem = cu_smem_bytes();
+            auto kern = cm_dut_kernel;
+            if (int r2 = opt_in_smem(kern, smem, "combine_dut(mma)")) return r2;
+            const int grid = n_tiles0 < mm::sm_count() ? n_tiles0 : mm::sm_count();
+            kern<<<grid, CU_THREADS, smem, st>>>(tmDL, tmOut, a, cu);
             mm::note_launches(1);
+        } else {            // token-centric CUDA-core kernel
+            CombineArgs u = a;
+            u.dlocal = dlocal; u.dglobal = nullptr; u.dUT = static_cast<__nv_bfloat16*>(dUT); u.mom_u = mom_u;
+            if (!classify_scales(u)) {
+                mm::set_error("mm_interp_softmax_combine_bwd_tc: scale ratios not supported by the dUT kernel");
+                return MM_ERR_UNSUPPORTED;
+            }
+            u.z_rows_path = 1;      // the finalize kernel then only writes dUT
+            dim3 grid((2 * u.nruns + 7) / 8, u.n_items);
+            MM_DISPATCH_D(D, 0, combine_bwd_u_kernel, grid, st, u)
+            mm::note_launches(1);
+            for (int s = 1; s < 4; ++s) {
+                if (u.mode[s] != SCALE_MOMENT) continue;
+                dim3 gridf((u.Ps[s] + 7) / 8, u.n_items);
+                switch (D) {
+                    case 256: combine_bwd_finalize_kernel<256><<<gridf, 256, 0, st>>>(u, s); break;
+                    case 512: combine_bwd_finalize_kernel<512><<<gridf, 256, 0, st>>>(u, s); break;
+                    case 768: combine_bwd_finalize_kernel<768><<<gridf, 256, 0, st>>>(u, s); break;
+                    case 1024: combine_bwd_finalize_kernel<1024><<<gridf, 256, 0, st>>>(u, s); break;
+                }
+                mm::note_launches(1);
+            }
         }
         mm::trace_mark("combine_bwd.dUT", st);
         rc = mm_check_launch("mm_interp_softmax_combine_bwd_tc(dUT)");

@@ -882,4 +882,278 @@ cm_dbeta_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// =======================================================================================
+// Backward pass B on the tensor cores (general path): the local part of d fused / d Y,
+//
+//   dU_s[i, :] = sum_p w_i(p) g beta_s(p) dlocal(p, :)                     (transpose of the forward's C, autograd of swin.py:42,78-80)
+//
+// A tile owns 128 finest-scale rows and the 128 / r_s coarse rows below them.  The token window of an owned coarse row
+// reaches r_s / 2 tokens outside the tile, so the tile stages the 192 tokens [R0 - 32, R0 + 160) of dlocal (MN-major B
+// operand, tokens = K) and every owned row is complete: no atomics, no partial sums.  Two MMAs per 64-column pass:
+//   D0[128, 64] = diag(g beta_0) * dlocal[R0 .. R0+128)          (A0: 128 x 128 diagonal, B rows 32..160)
+//   D1[128, 64] = C1^T * dlocal[R0-32 .. R0+160)                  (A1: rows 0..n1+n2+n3 = the owned coarse rows, K = 192 tokens)
+// The coefficient matrices are written by one thread per token at fixed positions (7 values per tile and token).
+// Roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-9 coefficient builders,
+// warps 10-17 epilogue.  Requirements: those of cm_dbeta_kernel (P % 64 == 0, ratios 2..64 powers of two).
+// =======================================================================================
+constexpr int CU_TOK = 192;                  // tokens staged per tile (halo 32 on both sides)
+constexpr int CU_HALO = 32;
+constexpr int CU_BN = 64;                    // columns per pass
+constexpr int CU_STAGES = 4;
+constexpr int CU_ACC = 4;                    // TMEM ring: 4 x (D0 64 + D1 64) columns
+constexpr int CU_BUILD_WARPS = CU_TOK / 32;
+constexpr int CU_EPI_WARPS = 8;
+constexpr int CU_THREADS = (4 + CU_BUILD_WARPS + CU_EPI_WARPS) * 32;
+
+struct CuArgs {
+    int n_tiles;
+    const int2* tile_info;
+    int region_row0;
+    const int* seg_start;
+    const int* offsets;
+    const int* counts;
+    int K;
+    int n_own[4], o_row[4];      // owned coarse rows per scale (128 / r) and their first row in D1
+    int D, n_pass;
+    __nv_bfloat16* dUT;
+};
+
+__global__ void __launch_bounds__(CU_THREADS, 1)
+cm_dut_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant__ CUtensorMap tmOut, const CombineArgs a,
+              const CuArgs c) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int A0_BYTES = 2 * 16384;                          // 128 x 128 (two 64-wide k blocks)
+    constexpr int A1_BYTES = 3 * 16384;                          // 128 x 192
+    constexpr int STAGE_BYTES = CU_TOK * 128;                    // 192 tokens x 64 columns
+    uint8_t* sA0 = smem;
+    uint8_t* sA1 = sA0 + A0_BYTES;
+    uint8_t* sB = sA1 + A1_BYTES;
+    uint8_t* sOut = sB + CU_STAGES * STAGE_BYTES;                // [CU_EPI_WARPS][2 slots]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sOut + CU_EPI_WARPS * 2 * EPI_SLOT_BYTES);
+    uint64_t* empty = full + CU_STAGES;
+    uint64_t* tfull = empty + CU_STAGES;
+    uint64_t* tempty = tfull + CU_ACC;
+    uint64_t* a_full = tempty + CU_ACC;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) { tma_prefetch_desc(&tmDL); tma_prefetch_desc(&tmOut); }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < CU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CU_ACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CU_EPI_WARPS); }
+        mbar_init(a_full, CU_BUILD_WARPS);
+        mbar_init(a_empty, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    for (int i = threadIdx.x * 16; i < A0_BYTES + A1_BYTES; i += CU_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int e = c.tile_info[t].x;
+            if (e < 0) continue;
+            const int rel0 = c.region_row0 + t * TILE_M - c.seg_start[e];
+            const int seg_tokens = c.counts[e] * a.P;
+            int row_g[CU_TOK / 32];                 // dlocal row of each 32-token group (a group never straddles images)
+#pragma unroll
+            for (int g = 0; g < CU_TOK / 32; ++g) {
+                const int rel = rel0 - CU_HALO + 32 * g;
+                row_g[g] = 0;
+                if (rel >= 0 && rel < seg_tokens) {
+                    const int j = rel / a.P, p = rel - j * a.P;
+                    row_g[g] = (a.perm[c.offsets[e] + j] / a.topk) * a.P + p;
+                }
+            }
+            for (int n = 0; n < c.n_pass; ++n) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], STAGE_BYTES);
+                uint8_t* dst = sB + stage * STAGE_BYTES;
+#pragma unroll
+                for (int g = 0; g < CU_TOK / 32; ++g) tma_load_2d(dst + g * 4096, &tmDL, &full[stage], n * CU_BN, row_g[g]);
+                if (++stage == CU_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(TILE_M, CU_BN, 0, 1);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t a_phase = 0;
+        const uint32_t a0_addr = smem_u32(sA0), a1_addr = smem_u32(sA1);
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            if (c.tile_info[t].x < 0) continue;
+            mbar_wait(a_full, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+            for (int n = 0; n < c.n_pass; ++n) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + acc * 128, d1 = d0 + 64;
+                const uint32_t b_addr = smem_u32(sB + stage * STAGE_BYTES);
+                for (int k = 0; k < TILE_M / 16; ++k)           // finest scale: tokens R0 .. R0+128 = staged rows 32 .. 160
+                    umma_bf16(d0, make_smem_desc(a0_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                              make_smem_desc(b_addr + CU_HALO * 128 + k * 2048, STAGE_BYTES, 1024), idesc, k != 0);
+                for (int k = 0; k < CU_TOK / 16; ++k)           // owned coarse rows: all 192 staged tokens
+                    umma_bf16(d1, make_smem_desc(a1_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                              make_smem_desc(b_addr + k * 2048, STAGE_BYTES, 1024), idesc, k != 0);
+                umma_commit(&empty[stage]);
+                umma_commit(&tfull[acc]);
+                if (++stage == CU_STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == CU_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+            umma_commit(a_empty);
+        }
+    } else if (warp >= 4 && warp < 4 + CU_BUILD_WARPS) {
+        // ===================== coefficient builders: thread = staged token u (tile-relative token u - 32) =====================
+        const int u = (warp - 4) * 32 + lane;
+        const int tr = u - CU_HALO;
+        uint32_t a_phase = 0;
+        const bool has0 = tr >= 0 && tr < TILE_M;
+        const uint32_t off0 = has0 ? cm_a_off(tr, tr) : 0u;
+        uint32_t offa[4], offb[4];
+        bool ina[4], inb[4];
+        int j0[4];
+#pragma unroll
+        for (int s = 1; s < 4; ++s) {
+            const int r = a.ratio[s];
+            j0[s] = cm_floor_div(2 * tr + 1 - r, 2 * r);       // unclamped lower lerp row, relative to the tile's first owned row
+            ina[s] = j0[s] >= 0 && j0[s] < c.n_own[s];
+            inb[s] = j0[s] + 1 >= 0 && j0[s] + 1 < c.n_own[s];
+            offa[s] = ina[s] ? cm_a_off(c.o_row[s] + j0[s], u) : 0u;
+            offb[s] = inb[s] ? cm_a_off(c.o_row[s] + j0[s] + 1, u) : 0u;
+        }
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int e = c.tile_info[t].x;
+            if (e < 0) continue;
+            const int rel0 = c.region_row0 + t * TILE_M - c.seg_start[e];
+            const int rel = rel0 + tr;
+            float v0 = 0.f, va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+            if (rel >= 0 && rel < c.counts[e] * a.P) {
+                const int j = rel / a.P, p = rel - j * a.P;
+                const int slot = c.offsets[e] + j;
+                const float g = a.gate ? a.gate[a.perm[slot]] : 1.0f;
+                const float4 bt = *reinterpret_cast<const float4*>(a.beta + (static_cast<size_t>(slot) * a.P + p) * 4);
+                const float bs[4] = {bt.x * g, bt.y * g, bt.z * g, bt.w * g};
+                v0 = bs[0];
+#pragma unroll
+                for (int s = 1; s < 4; ++s) {
+                    const int r = a.ratio[s];
+                    const LerpSrc L = lerp_src(p, a.scale[s], a.Ps[s]);
+                    const int own0 = c.seg_start[s * c.K + e] + rel0 / r;          // row-space row of the first owned row
+                    const int base = a.slot_row[s * a.n_items + slot];
+                    const int qa = base + L.i0 - own0, qb = base + L.i1 - own0;
+                    va[s] = bs[s] * ((qa == j0[s] ? 1.0f - L.lam : 0.f) + (qb == j0[s] ? L.lam : 0.f));
+                    vb[s] = bs[s] * ((qa == j0[s] + 1 ? 1.0f - L.lam : 0.f) + (qb == j0[s] + 1 ? L.lam : 0.f));
+                }
+            }
+            mbar_wait(a_empty, a_phase ^ 1);
+            a_phase ^= 1;
+            if (has0) *reinterpret_cast<__nv_bfloat16*>(sA0 + off0) = __float2bfloat16_rn(v0);
+#pragma unroll
+            for (int s = 1; s < 4; ++s) {
+                if (ina[s]) *reinterpret_cast<__nv_bfloat16*>(sA1 + offa[s]) = __float2bfloat16_rn(va[s]);
+                if (inb[s]) *reinterpret_cast<__nv_bfloat16*>(sA1 + offb[s]) = __float2bfloat16_rn(vb[s]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+        }
+    } else if (warp >= 4 + CU_BUILD_WARPS) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                                  // TMEM lane quarter
+        const int ew = warp - 4 - CU_BUILD_WARPS;
+        const int hsel = ew >> 2;                                // 32-column chunk of the 64-column pass
+        uint8_t* my_out = sOut + ew * 2 * EPI_SLOT_BYTES;
+        int acc = 0; uint32_t acc_phase = 0;
+        int oslot = 0;
+        const int r_in = q * 32 + lane;                          // row of D0 / D1 this thread reads
+        // which owned coarse row is D1 row r_in?
+        int cs = 0, ci = 0;
+        for (int s = 1; s < 4; ++s)
+            if (r_in >= c.o_row[s] && r_in < c.o_row[s] + c.n_own[s]) { cs = s; ci = r_in - c.o_row[s]; }
+        for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
+            const int e = c.tile_info[t].x;
+            if (e < 0) continue;
+            const int row0 = c.region_row0 + t * TILE_M;
+            const int rel0 = row0 - c.seg_start[e];
+            // coarse row this thread owns (if any), only inside the expert's 128-row padded segment of that region
+            __nv_bfloat16* crow = nullptr;
+            if (cs != 0) {
+                const int rr = rel0 / a.ratio[cs] + ci;
+                const int seg_rows = (c.counts[e] * a.Ps[cs] + TILE_M - 1) / TILE_M * TILE_M;
+                if (rr < seg_rows) crow = c.dUT + (static_cast<long long>(c.seg_start[cs * c.K + e]) + rr) * c.D;
+            }
+            const bool any_coarse = __any_sync(0xffffffffu, crow != nullptr);
+            for (int n = 0; n < c.n_pass; ++n) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + acc * 128 + (static_cast<uint32_t>(q * 32) << 16);
+                const int col0 = n * CU_BN + hsel * 32;
+                {   // D0: 32 finest-scale rows x 32 columns -> staging -> TMA store (padding rows come out as zeros)
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + hsel * 32, v);
+                    tmem_ld_wait();
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    uint8_t* so = my_out + oslot * EPI_SLOT_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1]));
+                        w.y = pack_bf16x2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3]));
+                        w.z = pack_bf16x2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
+                        w.w = pack_bf16x2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
+                        *reinterpret_cast<uint4*>(so + epi_slot_off(lane, k)) = w;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, so, col0, row0 + q * 32);
+                        tma_store_commit();
+                    }
+                    oslot ^= 1;
+                }
+                if (any_coarse) {   // D1: owned coarse rows, one row per thread, 64 bytes per pass chunk
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + 64 + hsel * 32, v);
+                    tmem_ld_wait();
+                    if (crow) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            stg_v4(crow + col0 + 8 * k,
+                                   make_uint4(pack_bf16x2(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1])),
+                                              pack_bf16x2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
+                                              pack_bf16x2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                                              pack_bf16x2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]))));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == CU_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+static inline size_t cu_smem_bytes() {
+    return 2 * 16384 + 3 * 16384 + static_cast<size_t>(CU_STAGES) * CU_TOK * 128 + CU_EPI_WARPS * 2 * EPI_SLOT_BYTES +
+           (2 * CU_STAGES + 2 * CU_ACC + 2) * 8 + 16 + 1024;
+}
+
 }  // namespace mm

@@ -359,3 +359,37 @@ def test_tensor_core_and_cuda_core_forward_combine_agree(dtype, topk):
     assert torch.isfinite(l_t).all()
     assert rel_err(l_t, l_c) < 4e-3 and rel_err(g_t, g_c) < 2e-3
     assert not torch.equal(l_t, l_c)          # the two paths really are different kernels
+
+
+@pytest.mark.parametrize("topk", [1, 2])
+def test_tensor_core_and_cuda_core_dut_agree(topk):
+    """Local cotangent present: d fused / d Y (local part) from the tcgen05 kernel (tile-owned rows, 32-token halo, bf16
+    coefficients) against the token-centric CUDA-core kernel (fp32 coefficients)."""
+    K, hidden, D, Ps, B = 3, [96, 192, 384, 768], 768, [3136, 784, 196, 49], 6
+    params = mo.init_params(K, hidden, D, D, seed=71)
+    moe = _module_from(params, K, hidden, D, topk=topk)
+    torch.manual_seed(72)
+    feats = [torch.randn(B, p, d, device="cuda", dtype=torch.bfloat16) for p, d in zip(Ps, hidden)]
+    sw = torch.randn(B, D, device="cuda")
+    cg = torch.randn(B, D, device="cuda")
+    cl = (torch.randn(B, D, 56, 56, device="cuda") / 3136).to(torch.bfloat16)
+    lib = medmoe_b200._lib.load()
+    results = []
+    for force in (0, 1):
+        lib.mm_debug_force_cuda_core_dut(force)
+        try:
+            moe.zero_grad()
+            fg = [f.clone().requires_grad_(True) for f in feats]
+            gf, lf, _ = moe(fg, sw)
+            ((gf.float() * cg).sum() + (lf.float() * cl.float()).sum()).backward()
+            results.append(([f.grad.float().clone() for f in fg],
+                            {k: p.grad.clone() for k, p in moe.named_parameters() if p.grad is not None}))
+        finally:
+            lib.mm_debug_force_cuda_core_dut(0)
+    (fa, pa), (fb, pb) = results
+    for s in range(4):
+        assert rel_err(fa[s], fb[s]) < 1e-2, f"d_feat{s}: {rel_err(fa[s], fb[s])}"
+    for k in pa:
+        if k.startswith("experts.") and pb[k].abs().max() > 0 and ".proj_convs." in k:
+            assert rel_err(pa[k], pb[k]) < 1e-2, k
+    assert not all(torch.equal(x, y) for x, y in zip(fa, fb))      # two different kernels really ran
