@@ -248,13 +248,11 @@ def main():
             torch.autograd.backward([loss, lf], [None, cot_local])
         else:
             loss.backward()
-        if world > 1:   # DDP gradient averaging, one flat bucket over NVLink
+        if world > 1:   # DDP gradient averaging: one flat bucket, one NCCL all-reduce (AVG) over NVLink, one multi-tensor copy back
             grads = [p.grad for p in params]
             flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat)
-            flat.div_(world)
-            for gr, new in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                gr.copy_(new)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
         return loss
 
     def barrier():
