@@ -140,7 +140,11 @@ static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t
     // slots take the shared memory) as does the fp32-output path.
     constexpr int EW = (AUX == 0 && !OUT_F32 && BN >= 128) ? MM_EPI_WARPS_PLAIN : (AUX == 2 ? MM_EPI_WARPS_RANK1 : 8);
     // smem: pipeline stages + output staging (32 KB, or 16 KB + 64 KB aux/gate staging) must fit 227 KB
+#ifdef MM_ROWS_STAGES_DELTA     // tuning experiments: MEDMOE_NVCC_EXTRA="-DMM_ROWS_STAGES_DELTA=-1" (measured: -3..5 % with one stage less)
+    constexpr int STAGES = (AUX ? ((BN > 128) ? 3 : 4) : ((BN > 192) ? 4 : (BN > 128 ? 4 : 5))) + (AUX ? 0 : MM_ROWS_STAGES_DELTA);
+#else
     constexpr int STAGES = AUX ? ((BN > 128) ? 3 : 4) : ((BN > 192) ? 4 : (BN > 128 ? 4 : 5));
+#endif
     using S = GemmSmem<BN, STAGES, AUX, EW>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32, AUX, EW>;
