@@ -11,12 +11,15 @@
 //     global_feat = mean_p fused
 // The store goes to the image's ORIGINAL batch slot (scatter-back folded into the store).
 //
-// Backward (no reference code — it is autograd of the above):
-//   pass A (token-centric)   dbeta_s = <dF, U_s>, dlogit = softmax backward           -> dlogit[slot, p, 4]
-//   pass B (native-row-centric, the transpose of the lerp as a gather, no atomics)
-//        dUT_s[i] = sum_p w_i(p) beta_s(p) dF(p)                                      -> bf16 [rows, D]
-//        dZ_s[i]  = sum_p w_i(p) dlogit_s(p) w2 * [interp(Z_s)(p) > 0]                -> bf16 [rows, D/2]
-//        dw2, db2, db1 partial sums per CTA (reduced per expert by mm_expert_reduce)
+// Backward (no reference code — it is autograd of the above), dF(p) = dlocal(p) + dglobal / P:
+//   tensor-core / rank-1 path (even integer scale ratios; mm_interp_softmax_combine_bwd_tc):
+//        dbeta_s = <dF, U_s>          GEMM against the staged Y rows (cm_dbeta_kernel) + interp of <dglobal, Y[row]> / P (rank-1)
+//        dUT_s[i] = sum_p w_i(p) beta_s(p) dlocal(p)      cm_dut_kernel; the dglobal part stays rank-1 (never written)
+//        dZ_s[i]  = sum_p w_i(p) dlogit_s(p) w2 * [interp(Z_s)(p) > 0]     interval prefix sums (combine_bwd_z.cuh)
+//   CUDA-core fallbacks (any ratio): token-centric kernels below, and the generic gather kernels
+//        pass A dlogit[slot, p, 4];  pass B (native-row-centric, the transpose of the lerp as a gather, no atomics) dUT, dZ
+//   dw2, db2, db1 partial sums per CTA (reduced per expert by expert_reduce_kernel)
+// The forward / backward kernels that run on the tensor cores live in combine_mma.cuh, the rank-1 ones in combine_rank1.cuh.
 #include "mm_common.cuh"
 #include "api_internal.h"
 

@@ -9,16 +9,16 @@
 //         E1  Y_s = ReLU(f_s W_s^T + b_s)      (reference swin.py:41, Conv1d k=1 + ReLU)
 //         E4  Z   = Y W1^T + b1                (reference swin.py:63, first Linear of attn_proj,
 //                                               evaluated at native resolution — lerp commutes)
-//         dY  = (dUT + dZ W1) * [Y > 0]        (backward of E4 + ReLU of E1)
+//         dY  = (dUT + c[row] dglobal[img] + dZ W1) * [Y > 0]   (backward of E4 + ReLU of E1; tensor and / or rank-1 aux)
 //         df_s = dPre_s W_s                    (backward of E1 w.r.t. the Swin stage features)
 //
 //   gemm_wgrad_kernel  dW_e[i, j] = sum_m A[m, i] * B[m, j]             both operands MN-major
 //       reduction over the rows of expert e (split into chunks, fp32 red.add into dW).
 //
-// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-// warps 4.. = epilogue (TMEM lane quarter = warp_idx % 4).  gemm_rows runs EIGHT epilogue warps (384 threads):
-// two warps share a lane quarter and take the even / odd 32-column chunks, so every scheduler has two
-// epilogue warps to hide tcgen05.ld / LDS / shuffle latency behind each other.
+// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warp 3 = zero fill of
+// the tiles no expert owns, warps 4.. = epilogue (TMEM lane quarter = warp_idx % 4).  gemm_rows takes its epilogue warp
+// count as a template parameter (8, 12 or 16): the warps of a lane quarter interleave the 32-column chunks, so every
+// scheduler has 2-4 epilogue warps to hide tcgen05.ld / LDS / TMA-store latency behind each other.
 // Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator ring
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
