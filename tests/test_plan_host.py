@@ -56,3 +56,19 @@ def test_layout_capacity_is_routing_independent():
     for experts in ([0] * 256, [i % 4 for i in range(256)]):
         ref = mmplan.reference_plan(experts, lay)
         assert len(ref["tile_info"]) == lay.total_tiles and len(ref["chunks"]) == lay.total_chunks
+
+
+def test_tensor_core_path_geometry_predicates():
+    """Which token geometries take the tensor-core / rank-1 backward (pure host logic of the C-ABI, no GPU needed)."""
+    from medmoe_b200 import _lib
+
+    def sup(name, Ps, D=768):
+        return bool(_lib.call(name, Ps[0], _lib.host_i32(Ps), D))
+
+    swin224, swin384 = [3136, 784, 196, 49], [9216, 2304, 576, 144]
+    for Ps in (swin224, swin384, [64, 16, 4, 1]):
+        assert sup("mm_combine_bwd_global_supported", Ps) and sup("mm_combine_bwd_tc_supported", Ps)
+    assert not sup("mm_combine_bwd_global_supported", [100, 30, 7, 1])        # non-integer ratios: generic kernels
+    assert not sup("mm_combine_bwd_tc_supported", [96, 24, 6, 3])             # ratio 32 at the coarsest scale but P % 64 != 0
+    assert sup("mm_combine_bwd_global_supported", [96, 24, 6, 3])             # the rank-1 path only needs even integer ratios
+    assert not sup("mm_combine_bwd_tc_supported", swin224, D=640)             # output_dim must be one of 256/512/768/1024
