@@ -455,8 +455,10 @@ def main():
         # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full captures (profiles/), cfg2 only
         known_traffic = {"combine_fwd.out": 2.964e9, "combine_fwd.logits": 0.836e9, "combine_bwd.dZ.rows": 0.402e9,
                          "dY": 4.05e9, "E4": 2.441e9, "E1.s0": 1.337e9, "combine_bwd.dZ.ident": 1.214e9,
-                         "combine_bwd.rowdot": 1.645e9, "dW1": 2.663e9}
-        traffic = known_traffic.get(tag) if (B == 256 and args.img == 224 and not args.local_grad) else None
+                         "combine_bwd.rowdot": 1.645e9, "dW1": 2.650e9}
+        if B == 256 and args.img == 224 and args.local_grad:
+            known_traffic = {"combine_bwd.dbeta": 2.898e9, "combine_bwd.dUT": 2.838e9}
+        traffic = known_traffic.get(tag) if (B == 256 and args.img == 224 and args.topk == 1 and args.experts == 4) else None
         if top.get("bound") == "tensor":
             roof = {"kernel": top_label, "bound": "tensor", "achieved": top["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": top["tflops"] / peak_tf, "traffic": traffic,
