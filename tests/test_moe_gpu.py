@@ -393,3 +393,13 @@ def test_tensor_core_and_cuda_core_dut_agree(topk):
         if k.startswith("experts.") and pb[k].abs().max() > 0 and ".proj_convs." in k:
             assert rel_err(pa[k], pb[k]) < 1e-2, k
     assert not all(torch.equal(x, y) for x, y in zip(fa, fb))      # two different kernels really ran
+
+
+@pytest.mark.parametrize("D,hidden,Ps", [(256, [32, 64, 128, 256], [256, 64, 16, 4]), (512, [96, 192, 384, 768], [1024, 256, 64, 16])])
+def test_other_output_dims_vs_oracle(D, hidden, Ps):
+    """output_dim 256 / 512 (hidden width 128 / 256: the 128-column pass variants of the tensor-core kernels), both cotangents."""
+    K, B = 3, 4
+    params, feats, sw, labels, cg, cl, ref_out, ref_grads, pgrads = _oracle_case(K, hidden, D, Ps, B, seed=81)
+    moe = _module_from(params, K, hidden, D)
+    grads = _check_against(moe, feats, sw, ref_out, ref_grads, cg, cl, labels)
+    _check_param_grads(grads, lambda k: pgrads[k], set(ref_out["top_expert"].tolist()), TIGHT)
