@@ -52,6 +52,25 @@ MM_DEVINL uint32_t cm_a_off(int m, int k) {
     return static_cast<uint32_t>(kb * 16384 + m * 128 + ((((kin >> 3) ^ (m & 7))) << 4) + (kin & 7) * 2);
 }
 
+// Issue nk tcgen05.mma steps (K = 16 each) of a K-major SWIZZLE_128B A operand laid out in 64-wide k blocks of 16 KB
+// (step s at + (s >> 2) * 16384 + (s & 3) * 32) against an MN-major B operand whose 16 k-rows per step are 2048 B apart.
+// da0 / db0 are the descriptors of step 0; they advance by constant increments (no per-step descriptor rebuild: the
+// single issuing lane is otherwise bound by its own instruction stream, ~200 cycles per MMA instead of the ~100 the pipe needs).
+MM_DEVINL void cm_issue_mmas(uint32_t d_tmem, uint64_t da0, uint64_t db0, uint32_t idesc, int nk, bool accumulate_first) {
+    int s = 0;
+    for (; s + 4 <= nk; s += 4) {
+        const uint64_t da = smem_desc_advance(da0, (s >> 2) * 16384);
+        const uint64_t db = smem_desc_advance(db0, s * 2048);
+        umma_bf16(d_tmem, da, db, idesc, (accumulate_first || s != 0) ? 1u : 0u);
+        umma_bf16(d_tmem, smem_desc_advance(da, 32), smem_desc_advance(db, 2048), idesc, 1);
+        umma_bf16(d_tmem, smem_desc_advance(da, 64), smem_desc_advance(db, 4096), idesc, 1);
+        umma_bf16(d_tmem, smem_desc_advance(da, 96), smem_desc_advance(db, 6144), idesc, 1);
+    }
+    for (; s < nk; ++s)
+        umma_bf16(d_tmem, smem_desc_advance(da0, (s >> 2) * 16384 + (s & 3) * 32), smem_desc_advance(db0, s * 2048), idesc,
+                  (accumulate_first || s != 0) ? 1u : 0u);
+}
+
 template <bool OUT_F32, bool IMG>
 __global__ void __launch_bounds__(CM_THREADS, 1)
 cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ CUtensorMap tmY1,
@@ -98,7 +117,7 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
     const int nk = c.ktot >> 4;
     const int n_work = IMG ? a.B * c.tiles_per_img : c.n_tiles;
 
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
@@ -142,14 +161,15 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
                 }
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1 && elect_one()) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_bf16(TILE_M, CM_BN, 0, 1);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t a_phase = 0;
-        const uint32_t a_addr = smem_u32(sA);
         const uint32_t lbo = static_cast<uint32_t>(c.ktot) * 128u;
+        const uint64_t da_base = make_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t db_base = make_smem_desc(smem_u32(sB), lbo, 1024);
         for (int t = blockIdx.x; t < n_work; t += gridDim.x) {
             if (!IMG && c.tile_info[t].x < 0) continue;
             mbar_wait(a_full, a_phase);
@@ -161,13 +181,8 @@ cm_out_kernel(const __grid_constant__ CUtensorMap tmY0, const __grid_constant__ 
                 for (int j = 0; j < n_src; ++j) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
-                    const uint32_t aj = a_addr + j * a_bytes;
-                    for (int k = 0; k < nk; ++k) {
-                        const uint64_t da = make_smem_desc(aj + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-                        const uint64_t db = make_smem_desc(b_addr + k * 2048, lbo, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (j | k) != 0);
-                    }
+                    cm_issue_mmas(d_tmem, smem_desc_advance(da_base, j * a_bytes), smem_desc_advance(db_base, stage * stage_bytes),
+                                  idesc, nk, j != 0);
                     umma_commit(&empty[stage]);
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
@@ -453,7 +468,7 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     const int n_chunk64 = c.HB / 64;
 
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
@@ -487,13 +502,16 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 if (++stage == c.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1 && elect_one()) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_bf16(TILE_M, c.HB, 0, 1);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t a_phase = 0;
-        const uint32_t ai_addr = smem_u32(sAi), ac_addr = smem_u32(sAc);
+        const uint64_t dai = make_smem_desc(smem_u32(sAi), 16, 1024);
+        const uint64_t dac = make_smem_desc(smem_u32(sAc), 16, 1024);
+        const uint64_t db0_base = make_smem_desc(smem_u32(sB), TILE_M * 128, 1024);                         // finest-scale stage: chunks 16 KB apart
+        const uint64_t dbc_base = make_smem_desc(smem_u32(sB), static_cast<uint32_t>(c.kc) * 128u, 1024);    // coarse stage: chunks kc rows apart
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
             if (c.tile_info[t].x < 0) continue;
             for (int h = 0; h < c.n_half; ++h) {
@@ -503,11 +521,8 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 {
-                    const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
                     const uint32_t d_tmem = tmem_base + acc * c.HB;
-                    for (int j = 0; j < TILE_M / 16; ++j)
-                        umma_bf16(d_tmem, make_smem_desc(ai_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                                  make_smem_desc(b_addr + j * 2048, TILE_M * 128, 1024), idesc, j != 0);
+                    cm_issue_mmas(d_tmem, dai, smem_desc_advance(db0_base, stage * stage_bytes), idesc, TILE_M / 16, false);
                     umma_commit(&empty[stage]);
                     umma_commit(&tfull[acc]);
                 }
@@ -520,15 +535,15 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 }
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB + stage * stage_bytes);
+                const uint64_t dbc = smem_desc_advance(dbc_base, stage * stage_bytes);
                 for (int s = 1; s < 4; ++s) {
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * c.HB;
                     const int j0 = c.koff[s] >> 4, j1 = (c.koff[s] + c.cap[s]) >> 4;
                     for (int j = j0; j < j1; ++j)
-                        umma_bf16(d_tmem, make_smem_desc(ac_addr + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
-                                  make_smem_desc(b_addr + j * 2048, static_cast<uint32_t>(c.kc) * 128u, 1024), idesc, j != j0);
+                        umma_bf16(d_tmem, smem_desc_advance(dac, (j >> 2) * 16384 + (j & 3) * 32), smem_desc_advance(dbc, j * 2048), idesc,
+                                  j != j0);
                     if (s == 3) umma_commit(&empty[stage]);
                     umma_commit(&tfull[acc]);
                     if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
@@ -755,7 +770,7 @@ cm_dbeta_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
@@ -791,11 +806,13 @@ cm_dbeta_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant_
                 if (++stage == c.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1 && elect_one()) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_bf16(TILE_M, c.ktot, 0, 0);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
+        const uint64_t da_base = make_smem_desc(smem_u32(smem), 16, 1024);
+        const uint64_t db_base = make_smem_desc(smem_u32(smem) + A_BYTES, 16, 1024);
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
             if (c.tile_info[t].x < 0) continue;
             mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -804,12 +821,12 @@ cm_dbeta_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant_
             for (int kb = 0; kb < c.n_kb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-                const uint32_t b_addr = a_addr + A_BYTES;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024), make_smem_desc(b_addr + k * 32, 16, 1024), idesc,
-                              (kb | k) != 0);
+                const uint64_t da = smem_desc_advance(da_base, stage * stage_bytes);
+                const uint64_t db = smem_desc_advance(db_base, stage * stage_bytes);
+                umma_bf16(d_tmem, da, db, idesc, kb != 0);
+                umma_bf16(d_tmem, smem_desc_advance(da, 32), smem_desc_advance(db, 32), idesc, 1);
+                umma_bf16(d_tmem, smem_desc_advance(da, 64), smem_desc_advance(db, 64), idesc, 1);
+                umma_bf16(d_tmem, smem_desc_advance(da, 96), smem_desc_advance(db, 96), idesc, 1);
                 umma_commit(&empty[stage]);
                 if (++stage == c.stages) { stage = 0; phase ^= 1; }
             }
@@ -955,7 +972,7 @@ cm_dut_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
         // ===================== TMA producer =====================
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
@@ -982,13 +999,14 @@ cm_dut_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant__ 
                 if (++stage == CU_STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (threadIdx.x == 32) {
+    } else if (warp == 1 && elect_one()) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_bf16(TILE_M, CU_BN, 0, 1);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t a_phase = 0;
-        const uint32_t a0_addr = smem_u32(sA0), a1_addr = smem_u32(sA1);
+        const uint64_t da0 = make_smem_desc(smem_u32(sA0), 16, 1024), da1 = make_smem_desc(smem_u32(sA1), 16, 1024);
+        const uint64_t db_base = make_smem_desc(smem_u32(sB), STAGE_BYTES, 1024);
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
             if (c.tile_info[t].x < 0) continue;
             mbar_wait(a_full, a_phase);
@@ -999,13 +1017,10 @@ cm_dut_kernel(const __grid_constant__ CUtensorMap tmDL, const __grid_constant__ 
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + acc * 128, d1 = d0 + 64;
-                const uint32_t b_addr = smem_u32(sB + stage * STAGE_BYTES);
-                for (int k = 0; k < TILE_M / 16; ++k)           // finest scale: tokens R0 .. R0+128 = staged rows 32 .. 160
-                    umma_bf16(d0, make_smem_desc(a0_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                              make_smem_desc(b_addr + CU_HALO * 128 + k * 2048, STAGE_BYTES, 1024), idesc, k != 0);
-                for (int k = 0; k < CU_TOK / 16; ++k)           // owned coarse rows: all 192 staged tokens
-                    umma_bf16(d1, make_smem_desc(a1_addr + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                              make_smem_desc(b_addr + k * 2048, STAGE_BYTES, 1024), idesc, k != 0);
+                const uint64_t db = smem_desc_advance(db_base, stage * STAGE_BYTES);
+                // finest scale: tokens R0 .. R0+128 = staged rows 32 .. 160; owned coarse rows: all 192 staged tokens
+                cm_issue_mmas(d0, da0, smem_desc_advance(db, CU_HALO * 128), idesc, TILE_M / 16, false);
+                cm_issue_mmas(d1, da1, db, idesc, CU_TOK / 16, false);
                 umma_commit(&empty[stage]);
                 umma_commit(&tfull[acc]);
                 if (++stage == CU_STAGES) { stage = 0; phase ^= 1; }

@@ -145,50 +145,60 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int num_kb = (a.K + 63) / 64;
     const int total_work = a.tile_count * a.n_tiles;
 
-    if (threadIdx.x == 0) {
-        // ===================== TMA producer =====================
-        int stage = 0; uint32_t phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
-            int e = 0;
-            if (a.tile_info) { e = a.tile_info[a.tile_begin + lt].x; if (e < 0) continue; }
-            const int row_a = lt * TILE_M;
-            const int row_b = e * a.N + nt * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], S::A_BYTES + BN * 128);
-                tma_load_2d(sA + stage * S::A_BYTES, &tmA, &full[stage], kb * 64, row_a);
-                tma_load_2d(sB + stage * S::B_BYTES, &tmB, &full[stage], kb * 64, row_b);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
+                int e = 0;
+                if (a.tile_info) { e = a.tile_info[a.tile_begin + lt].x; if (e < 0) continue; }
+                const int row_a = lt * TILE_M;
+                const int row_b = e * a.N + nt * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], S::A_BYTES + BN * 128);
+                    tma_load_2d(sA + stage * S::A_BYTES, &tmA, &full[stage], kb * 64, row_a);
+                    tma_load_2d(sB + stage * S::B_BYTES, &tmB, &full[stage], kb * 64, row_b);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
-    } else if (threadIdx.x == 32) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, 0, 0);
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int lt = w / a.n_tiles;
-            if (a.tile_info && a.tile_info[a.tile_begin + lt].x < 0) continue;
-            mbar_wait(&tempty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full[stage], phase);
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane; descriptors advance by constant increments) =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, 0, 0);
+            const uint64_t da_base = make_smem_desc(smem_u32(sA), 16, 1024);
+            const uint64_t db_base = make_smem_desc(smem_u32(sB), 16, 1024);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int lt = w / a.n_tiles;
+                if (a.tile_info && a.tile_info[a.tile_begin + lt].x < 0) continue;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + stage * S::B_BYTES);
-                const int ksteps = min(4, (a.K - kb * 64 + 15) / 16);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-                    const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = smem_desc_advance(da_base, stage * S::A_BYTES);
+                    const uint64_t db = smem_desc_advance(db_base, stage * S::B_BYTES);
+                    const int ksteps = min(4, (a.K - kb * 64 + 15) / 16);
+                    if (ksteps == 4) {
+                        umma_bf16(d_tmem, da, db, idesc, kb != 0);
+                        umma_bf16(d_tmem, smem_desc_advance(da, 32), smem_desc_advance(db, 32), idesc, 1);
+                        umma_bf16(d_tmem, smem_desc_advance(da, 64), smem_desc_advance(db, 64), idesc, 1);
+                        umma_bf16(d_tmem, smem_desc_advance(da, 96), smem_desc_advance(db, 96), idesc, 1);
+                    } else {
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_bf16(d_tmem, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            umma_commit(&tfull[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp == 3) {
         // ===================== tiles no expert owns =====================
@@ -434,61 +444,64 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int per_chunk = a.n_i * a.n_j;
     const int total_work = a.chunk_count * per_chunk;
 
-    if (threadIdx.x == 0) {
-        int stage = 0; uint32_t phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int c = w / per_chunk, rem = w - c * per_chunk;
-            const int it = rem / a.n_j, jt = rem - it * a.n_j;
-            const int4 ch = a.chunks[a.chunk_begin + c];
-            if (ch.z <= 0) continue;
-            const int row0 = (ch.y - a.tile_base) * TILE_M;
-            const int num_kb = ch.z * 2;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], S::A_BYTES + NB_CHUNKS * 8192);
-                uint8_t* dA = sA + stage * S::A_BYTES;
-                uint8_t* dB = sB + stage * B_STAGE;
-                const int r = row0 + kb * 64;
-                tma_load_2d(dA, &tmA, &full[stage], it * 128, r);
-                tma_load_2d(dA + 8192, &tmA, &full[stage], it * 128 + 64, r);
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int c = w / per_chunk, rem = w - c * per_chunk;
+                const int it = rem / a.n_j, jt = rem - it * a.n_j;
+                const int4 ch = a.chunks[a.chunk_begin + c];
+                if (ch.z <= 0) continue;
+                const int row0 = (ch.y - a.tile_base) * TILE_M;
+                const int num_kb = ch.z * 2;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], S::A_BYTES + NB_CHUNKS * 8192);
+                    uint8_t* dA = sA + stage * S::A_BYTES;
+                    uint8_t* dB = sB + stage * B_STAGE;
+                    const int r = row0 + kb * 64;
+                    tma_load_2d(dA, &tmA, &full[stage], it * 128, r);
+                    tma_load_2d(dA + 8192, &tmA, &full[stage], it * 128 + 64, r);
 #pragma unroll
-                for (int j = 0; j < NB_CHUNKS; ++j)
-                    tma_load_2d(dB + j * 8192, &tmB, &full[stage], jt * BN + j * 64, r);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    for (int j = 0; j < NB_CHUNKS; ++j)
+                        tma_load_2d(dB + j * 8192, &tmB, &full[stage], jt * BN + j * 64, r);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
-    } else if (threadIdx.x == 32) {
-        constexpr uint32_t idesc_plain = make_idesc_bf16(TILE_M, BN, 1, 1);
-        constexpr uint32_t idesc_wide = make_idesc_bf16(TILE_M, BN + 16, 1, 1);
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-            const int c = w / per_chunk;
-            const int4 ch = a.chunks[a.chunk_begin + c];
-            if (ch.z <= 0) continue;
-            const int num_kb = ch.z * 2;
-            const uint32_t idesc = (COLSUM && (w - c * per_chunk) % a.n_j == 0) ? idesc_wide : idesc_plain;
-            mbar_wait(&tempty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full[stage], phase);
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_plain = make_idesc_bf16(TILE_M, BN, 1, 1);
+            constexpr uint32_t idesc_wide = make_idesc_bf16(TILE_M, BN + 16, 1, 1);
+            // 16 k-rows per MMA = 2048 B; 64-element MN chunks are 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO)
+            const uint64_t da_base = make_smem_desc(smem_u32(sA), 8192, 1024);
+            const uint64_t db_base = make_smem_desc(smem_u32(sB), 8192, 1024);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int c = w / per_chunk;
+                const int4 ch = a.chunks[a.chunk_begin + c];
+                if (ch.z <= 0) continue;
+                const int num_kb = ch.z * 2;
+                const uint32_t idesc = (COLSUM && (w - c * per_chunk) % a.n_j == 0) ? idesc_wide : idesc_plain;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + stage * S::A_BYTES);
-                const uint32_t b_addr = smem_u32(sB + stage * B_STAGE);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // 16 k-rows per MMA = 2048 B; 64-element MN chunks are 8192 B apart (LBO),
-                    // 8-row k groups 1024 B apart (SBO).
-                    const uint64_t da = make_smem_desc(a_addr + k * 2048, 8192, 1024);
-                    const uint64_t db = make_smem_desc(b_addr + k * 2048, 8192, 1024);
-                    umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = smem_desc_advance(da_base, stage * S::A_BYTES);
+                    const uint64_t db = smem_desc_advance(db_base, stage * B_STAGE);
+                    umma_bf16(d_tmem, da, db, idesc, kb != 0);
+                    umma_bf16(d_tmem, smem_desc_advance(da, 2048), smem_desc_advance(db, 2048), idesc, 1);
+                    umma_bf16(d_tmem, smem_desc_advance(da, 4096), smem_desc_advance(db, 4096), idesc, 1);
+                    umma_bf16(d_tmem, smem_desc_advance(da, 6144), smem_desc_advance(db, 6144), idesc, 1);
+                    umma_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(&tfull[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            umma_commit(&tfull[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         const int q = warp & 3;

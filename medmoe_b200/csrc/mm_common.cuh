@@ -191,6 +191,23 @@ MM_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (elect.sync): the MMA-issue and TMA-producer roles run as "whole warp enters, one lane
+// elected" so that the compiler keeps descriptor arithmetic on the uniform datapath without per-instruction election loops.
+MM_DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Shared-memory descriptor advanced by `bytes` (a multiple of 16 that stays inside the 14-bit start-address field):
+// one 32-bit add on the low word instead of rebuilding the descriptor for every k step.
+MM_DEVINL uint64_t smem_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread retire.
 MM_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
