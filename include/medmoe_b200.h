@@ -171,6 +171,9 @@ int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, const float* 
                                      const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
                                      float* dbeta_loc, void* dUT, float* mom_u, float* dgate, void* dZ, float* part,
                                      float* dw2_db1_db2, float* zscr, void* stream);
+/* experimental: 1 = run eligible row GEMMs (plain bf16 epilogue, BN 192 / 256) on CTA pairs (tcgen05 cta_group::2);
+ * also switched on by MEDMOE_GEMM_PAIR=1.  Needs 256-row aligned expert segments when tile_info is given. */
+void mm_debug_gemm_pair(int on);
 /* test hook: 1 = compute dUT with the CUDA-core kernel instead of the tcgen05 one (process-wide) */
 void mm_debug_force_cuda_core_dut(int on);
 /* the dlocal == NULL special case of the above (kept as its own entry point) */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mm_combine_bwd_global_supported": (c_int, [c_int, c_vp, c_int]),
     "mm_combine_bwd_tc_supported": (c_int, [c_int, c_vp, c_int]),
     "mm_debug_force_cuda_core_dut": (None, [c_int]),
+    "mm_debug_gemm_pair": (None, [c_int]),
     "mm_interp_softmax_combine_bwd_tc": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -76,7 +77,7 @@ SIGNATURES = {
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats",
                 "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported",
-                "mm_debug_force_cuda_core_dut"}
+                "mm_debug_force_cuda_core_dut", "mm_debug_gemm_pair"}
 
 
 def library_path() -> Path:

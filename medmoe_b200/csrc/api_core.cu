@@ -2,9 +2,11 @@
 // grouped-GEMM entry points.  See include/medmoe_b200.h for the contract.
 #include "api_internal.h"
 #include "gemm.cuh"
+#include "gemm_pair.cuh"
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -189,6 +191,41 @@ static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const Wgra
     return check_launch("gemm_wgrad");
 }
 
+// CTA-pair variant (gemm_pair.cuh): plain bf16 epilogue only
+template <int BN>
+static int launch_rows_pair(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
+    constexpr int EW = 16;
+    constexpr int STAGES = 6;
+    using S = PairSmem<BN, STAGES, EW>;
+    static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_rows_pair_kernel<BN, STAGES, EW>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("gemm_rows_pair: cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            return MM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int work = ((args.tile_count + 1) / 2) * args.n_tiles;
+    int grid = 2 * work < sm_count() ? 2 * work : (sm_count() & ~1);
+    if (grid <= 0) return MM_OK;
+    kern<<<grid, rows_threads(EW), S::TOTAL, st>>>(m.a, m.b, m.out, args);
+    note_launches(1);
+    return check_launch("gemm_rows_pair");
+}
+
+static int g_pair_mode = -1;      // -1: read MEDMOE_GEMM_PAIR on first use; 0 off; 1 on
+extern "C" void mm_debug_gemm_pair(int on) { g_pair_mode = on; }
+static bool pair_mode() {
+    if (g_pair_mode < 0) {
+        const char* v = getenv("MEDMOE_GEMM_PAIR");
+        g_pair_mode = (v && v[0] == '1') ? 1 : 0;
+    }
+    return g_pair_mode == 1;
+}
+
 static int pick_bn_rows(int N) {
     const int cands[] = {256, 192, 128, 96, 64, 32};
     for (int c : cands)
@@ -310,6 +347,14 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
     g.vecs = r1 ? r1->vecs : nullptr;
     g.ld_vecs = r1 ? r1->ld_vecs : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pair_mode() && !aux && !r1 && !gate && !out_f32 && !colsum && out_scale == 1.0f && (BN == 192 || BN == 256) &&
+        (!tile_info || (tile_begin % 2 == 0))) {
+        // each CTA of a pair stages half of the W tile
+        rc = encode_tmap_bf16(&m.b, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64,
+                              BN / 2, "mm_grouped_gemm_rows(W, pair)");
+        if (rc) return rc;
+        return BN == 192 ? launch_rows_pair<192>(m, g, st) : launch_rows_pair<256>(m, g, st);
+    }
 #define MM_ROWS_CASE(bn)                                                                          \
     case bn:                                                                                      \
         if (out_f32) return launch_rows<bn, true, 0>(m, g, st);                                   \

@@ -231,3 +231,51 @@ def test_grouped_rows_gemm_rank1_aux(K, N, with_aux):
     assert (got[~valid] == 0).all()
     err = (got[valid] - ref[valid]).abs().max().item()
     assert err <= 2 ** -7 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.fixture
+def pair_mode():
+    """Route plain row GEMMs with a 192- or 256-wide tile to the CTA-pair kernel (experimental, off by default)."""
+    lib = _lib.load()
+    lib.mm_debug_gemm_pair(1)
+    yield
+    lib.mm_debug_gemm_pair(0)
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 64, 192), (128, 128, 256), (300, 96, 768), (1000, 768, 384), (4096 + 130, 384, 768)])
+def test_pair_rows_gemm_dense_bit_identical_to_single(pair_mode, M, K, N):
+    A = _bf16(M, K, seed=1)
+    W = _bf16(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm_rows(A, W, N, M=M, bias=bias, out=out, flags=EPI_RELU)
+    _lib.load().mm_debug_gemm_pair(0)
+    single = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm_rows(A, W, N, M=M, bias=bias, out=single, flags=EPI_RELU)
+    # same k order, same fp32 accumulation: the two tile shapes must agree bit for bit
+    assert torch.equal(out, single)
+    ref = torch.relu(A.float() @ W.float().t() + bias)
+    assert (out.float() - ref).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
+
+
+def test_pair_rows_gemm_grouped_256_row_segments(pair_mode):
+    # hand-made tile table: every expert segment starts on an even tile (256-row alignment), ragged ends, holes
+    E, K, N = 3, 768, 384
+    tiles = [(0, 128), (0, 77), (1, 128), (-1, 0), (-1, 0), (-1, 0), (2, 5), (-1, 0), (1, 128), (1, 128)]
+    tile_info = torch.tensor(tiles, dtype=torch.int32, device="cuda")
+    rows = len(tiles) * 128
+    A = _bf16(rows, K, seed=4)
+    W = _bf16(E * N, K, scale=K ** -0.5, seed=5)
+    bias = torch.randn(E, N, device="cuda")
+    out = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm_rows(A, W, N, tile_info=tile_info, tile_begin=0, tile_count=len(tiles), bias=bias, out=out, flags=EPI_RELU)
+    Wf = W.float().view(E, N, K)
+    for t, (e, v) in enumerate(tiles):
+        blk = out[t * 128:(t + 1) * 128].float()
+        assert torch.isfinite(blk).all(), f"tile {t} not written"
+        if e < 0:
+            assert (blk == 0).all()
+            continue
+        ref = torch.relu(A[t * 128: t * 128 + v].float() @ Wf[e].t() + bias[e])
+        assert (blk[v:] == 0).all()
+        assert (blk[:v] - ref).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
