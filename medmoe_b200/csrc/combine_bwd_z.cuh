@@ -223,7 +223,7 @@ MM_DEVINL void z_open_sums(float za, float zb, int r, const float2* __restrict__
 
 // coarse scales; grid = (ceil(chunks / 8), n_items); warp = 8 consecutive native rows of one scale
 template <int D>
-__global__ void __launch_bounds__(ZR_WARPS * 32)
+__global__ void __launch_bounds__(ZR_WARPS * 32, 2)   // <= 128 registers: two blocks (16 warps) per SM hide the row-load latency
 bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunks2, int chunks3, int blk_base) {
     constexpr int NE = D / 256;
     constexpr int E = NE * 4;
