@@ -221,7 +221,13 @@ MM_DEVINL void z_open_sums(float za, float zb, int r, const float2* __restrict__
     S1 = h.y - l.y;
 }
 
-// coarse scales; grid = (ceil(chunks / 8), n_items); warp = 8 consecutive native rows of one scale
+template <int N>
+MM_DEVINL void z_load_row_raw(const __nv_bfloat16* row, int lane, uint2 (&q)[N]) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) q[t] = *reinterpret_cast<const uint2*>(row + 4 * (lane + 32 * t));
+}
+
+// coarse scales; grid = (ceil(chunks / 8), n_items); warp = ZR_ROWS_PER_WARP consecutive native rows of one scale
 template <int D>
 __global__ void __launch_bounds__(ZR_WARPS * 32, 2)   // <= 128 registers: two blocks (16 warps) per SM hide the row-load latency
 bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunks2, int chunks3, int blk_base) {
@@ -249,11 +255,15 @@ bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunk
         const float2* PA = reinterpret_cast<const float2*>(sbase + zs.pa_off[s]);
         const float hs = sbase[zs.ht_off + (s - 1) * 2 + 0], ts = sbase[zs.ht_off + (s - 1) * 2 + 1];
         const int i_a = ch * ZR_ROWS_PER_WARP, i_b = min(Ps, i_a + ZR_ROWS_PER_WARP);
-        float za[E], zb[E], zn[E], carry[E];
+        float za[E], zb[E], carry[E];
+        uint2 n1[NE], n2[NE];     // Z[i + 2], Z[i + 3] in flight, still packed bf16 (two rows of prefetch in the registers of one)
 #pragma unroll
-        for (int k = 0; k < E; ++k) { carry[k] = 0.f; zn[k] = 0.f; }
+        for (int k = 0; k < E; ++k) carry[k] = 0.f;
+#pragma unroll
+        for (int t = 0; t < NE; ++t) { n1[t] = make_uint2(0u, 0u); n2[t] = make_uint2(0u, 0u); }
         load_row_bf16x4<NE>(a.Z + (base + i_a) * H, lane, zb);              // zb = Z[i_a]
-        if (i_a + 1 < Ps) load_row_bf16x4<NE>(a.Z + (base + i_a + 1) * H, lane, zn);
+        if (i_a + 1 < Ps) z_load_row_raw<NE>(a.Z + (base + i_a + 1) * H, lane, n1);
+        if (i_a + 2 < Ps && i_a + 1 < i_b) z_load_row_raw<NE>(a.Z + (base + i_a + 2) * H, lane, n2);
         if (i_a >= 1) {   // B-side of the interval that ends in the first row of this chunk
             load_row_bf16x4<NE>(a.Z + (base + i_a - 1) * H, lane, za);
             const float2* pa = PA + static_cast<long long>(i_a - 1) * (r + 1);
@@ -266,8 +276,14 @@ bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunk
         }
         for (int i = i_a; i < i_b; ++i) {
 #pragma unroll
-            for (int k = 0; k < E; ++k) { za[k] = zb[k]; zb[k] = zn[k]; }     // za = Z[i], zb = Z[i + 1]
-            if (i + 2 < Ps && i + 1 < i_b) load_row_bf16x4<NE>(a.Z + (base + i + 2) * H, lane, zn);   // prefetch Z[i + 2]
+            for (int k = 0; k < E; ++k) za[k] = zb[k];                        // za = Z[i]
+#pragma unroll
+            for (int t = 0; t < NE; ++t) {                                      // zb = Z[i + 1]
+                zb[4 * t + 0] = bf16lo(n1[t].x); zb[4 * t + 1] = bf16hi(n1[t].x);
+                zb[4 * t + 2] = bf16lo(n1[t].y); zb[4 * t + 3] = bf16hi(n1[t].y);
+                n1[t] = n2[t];
+            }
+            if (i + 3 < Ps && i + 2 < i_b) z_load_row_raw<NE>(a.Z + (base + i + 3) * H, lane, n2);     // prefetch Z[i + 3]
             float row[E];
 #pragma unroll
             for (int k = 0; k < E; ++k) row[k] = carry[k];
