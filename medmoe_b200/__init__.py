@@ -8,13 +8,16 @@ from .distributed import BackpropType, concat_gather_all_gpu, gather_tensor, get
 from .losses import (ContrastiveLossOutput, FLAVAGlobalContrastiveLoss, FLAVAGlobalContrastiveLossOutput,
                      GLORIAGlobalContrastiveLoss, contrastive_loss_with_temperature, zero_shot_predict)
 from .moe import Expert, MoE
+from .checkpoint import extract_moe_state_dict, load_reference_checkpoint
+from .eval_zs import zero_shot_evaluate
 
 __version__ = "0.1.0"
 
 __all__ = [
     "MoE", "Expert", "GLORIAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLossOutput",
     "ContrastiveLossOutput", "contrastive_loss_with_temperature", "zero_shot_predict", "BackpropType", "gather_tensor",
-    "concat_gather_all_gpu", "get_rank", "activate",
+    "concat_gather_all_gpu", "get_rank", "activate", "load_reference_checkpoint", "extract_moe_state_dict",
+    "zero_shot_evaluate",
 ]
 
 

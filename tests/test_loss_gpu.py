@@ -146,3 +146,19 @@ def test_zero_shot_exact_ties_take_first_index():
     img = txt[0:1].repeat(16, 1) + 0.01 * torch.randn(16, 768)
     pred = medmoe_b200.zero_shot_predict(img.cuda(), txt.cuda())
     assert (pred.cpu() == 0).all()
+
+
+def test_zero_shot_driver_prompt_ensembles_and_accuracy():
+    from medmoe_b200 import zero_shot_evaluate
+    g = torch.Generator(device="cuda").manual_seed(5)
+    C, n_prompts, D, M = 5, 3, 768, 1024
+    prompts = torch.randn(C, n_prompts, D, device="cuda", generator=g)
+    labels = torch.randint(0, C - 1, (M,), device="cuda", generator=g)          # class C-1 has no samples
+    unit = torch.nn.functional.normalize(prompts.double(), dim=-1).mean(1)
+    img = unit[labels].float() + 0.08 * torch.randn(M, D, device="cuda", generator=g)
+    out = zero_shot_evaluate([img[:300], img[300:]], prompts, labels)
+    sim = torch.nn.functional.normalize(img.double(), dim=-1) @ torch.nn.functional.normalize(unit, dim=-1).t()
+    ref = sim.argmax(1)
+    assert torch.equal(out["pred"], ref)
+    assert abs(out["accuracy"].item() - (ref == labels).double().mean().item()) < 1e-6
+    assert torch.isnan(out["per_class_accuracy"][C - 1]) and out["per_class_accuracy"][: C - 1].min() > 0.5
