@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--topk", type=int, default=1, help="experts per image (1 = the reference; 2 = BASELINE config 4 extension)")
     ap.add_argument("--loss", default="flava", choices=["flava", "gloria"])
     ap.add_argument("--local-grad", action="store_true", help="also feed a dense synthetic cotangent into local_feat")
+    ap.add_argument("--routing", default="natural", choices=["natural", "uniform", "skew"],
+                    help="natural = the router as initialised; uniform = every expert gets B/K images; skew = all images to expert 0")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
@@ -158,7 +160,7 @@ def config_dict(args, world):
     return {"workload": f"{name}: MoE block + global InfoNCE fwd/bwd, batch {args.batch}/GPU, {args.experts} experts top-{args.topk}, "
                         f"Swin-T stage features of a {args.img}^2 image ({'/'.join(map(str, token_counts(args.img)))} tokens), bf16",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "experts": args.experts, "topk": args.topk, "img": args.img,
-            "loss": args.loss, "local_cotangent": bool(args.local_grad),
+            "loss": args.loss, "local_cotangent": bool(args.local_grad), "routing": args.routing,
             "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": "inputs+intermediates per step (> 5 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -221,6 +223,21 @@ def main():
         "txt": torch.randn(B, D, generator=g).pin_memory(),
         "labels": torch.randint(0, K, (B,), generator=g).pin_memory(),
     }
+    if args.routing != "natural":
+        # routing balance variants: the router stays the real kernel, its weights / input are chosen so that the
+        # arg-max is forced.  uniform: swin_feat carries a one-hot of (image index mod K) that the router passes through.
+        with torch.no_grad():
+            for lin in (moe.router[0], moe.router[2]):
+                lin.weight.zero_()
+                lin.bias.zero_()
+            if args.routing == "skew":
+                moe.router[2].bias[0] = 20.0
+            else:
+                idx = torch.arange(K, device=dev)
+                moe.router[0].weight[idx, idx] = 1.0
+                moe.router[2].weight[idx, idx] = 1.0
+                host["sw"].zero_()
+                host["sw"][torch.arange(B), torch.arange(B) % K] = 20.0
     h2d_bytes = sum(t.numel() * t.element_size() for t in host["feats"]) + sum(
         host[k].numel() * host[k].element_size() for k in ("sw", "txt", "labels"))
     cot_local = None
