@@ -17,8 +17,15 @@ __all__ = [
     "MoE", "Expert", "GLORIAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLossOutput",
     "ContrastiveLossOutput", "contrastive_loss_with_temperature", "zero_shot_predict", "BackpropType", "gather_tensor",
     "concat_gather_all_gpu", "get_rank", "activate", "load_reference_checkpoint", "extract_moe_state_dict",
-    "zero_shot_evaluate",
+    "zero_shot_evaluate", "SWIN",
 ]
+
+
+def __getattr__(name):
+    if name == "SWIN":            # lazy: pulls in `transformers`
+        from .swin import SWIN
+        return SWIN
+    raise AttributeError(name)
 
 
 def activate():

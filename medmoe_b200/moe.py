@@ -257,6 +257,9 @@ class MoE(nn.Module):
         feats = list(multi_scale_feats)
         if not feats[0].is_cuda:
             raise RuntimeError("medmoe_b200.MoE runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        if any(f.dtype != feats[0].dtype for f in feats):
+            # autocast hands over a mix (fp32 from LayerNorm, bf16 from Linear): the kernels compute in bf16 anyway
+            feats = [f.to(torch.bfloat16) for f in feats]
         probs, idx, w = _RouterFunction.apply(swin_feat, self.router[0].weight, self.router[0].bias,
                                               self.router[2].weight, self.router[2].bias, self.topk)
         self.last_top_expert = idx

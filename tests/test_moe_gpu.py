@@ -403,3 +403,27 @@ def test_other_output_dims_vs_oracle(D, hidden, Ps):
     moe = _module_from(params, K, hidden, D)
     grads = _check_against(moe, feats, sw, ref_out, ref_grads, cg, cl, labels)
     _check_param_grads(grads, lambda k: pgrads[k], set(ref_out["top_expert"].tolist()), TIGHT)
+
+
+def test_swin_wrapper_end_to_end_matches_oracle_on_its_own_stage_features():
+    """medmoe_b200.SWIN (random-init Swin-T, there are no weights offline): forward/backward from raw images; the MoE part
+    is checked against the oracle fed with the very stage features the backbone produced."""
+    torch.manual_seed(0)
+    net = medmoe_b200.SWIN(pretrained=False, num_experts=3).cuda().eval()      # eval: no stochastic depth, the two passes agree
+    g = torch.Generator(device="cuda").manual_seed(1)
+    imgs = (torch.rand(2, 3, 256, 240, device="cuda", generator=g) * 255).to(torch.uint8)
+    gf, lf, probs = net(imgs)
+    assert gf.shape == (2, 768) and lf.shape == (2, 768, 56, 56) and probs.shape == (2, 3)
+    (gf.float().square().mean() + lf.float().square().mean() + probs[:, 0].sum()).backward()
+    grads = [p.grad for p in net.model.parameters() if p.grad is not None]
+    assert len(grads) > 50 and all(torch.isfinite(gr).all() for gr in grads)       # the backbone is trainable (freeze_cnn: false)
+    assert net.moe.router[0].weight.grad is not None
+
+    with torch.no_grad():
+        feats, swin_feat, _ = net.stage_features(net.preprocess(imgs))
+        params = {k: v.detach().float().cpu() for k, v in net.moe.state_dict().items()}
+        (g_ref, l_ref, p_ref), idx = mo.moe_forward_sparse(params, [f.float().cpu() for f in feats], swin_feat.cpu())
+    assert torch.equal(net.moe.last_top_expert.view(-1).cpu().long(), idx.view(-1).long())
+    assert rel_err(probs.detach().cpu(), p_ref) < 1e-4
+    assert rel_err(gf.detach().float().cpu(), g_ref) < 2e-2
+    assert rel_err(lf.detach().float().cpu(), l_ref) < 2e-2
