@@ -171,6 +171,23 @@ int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, const float* 
                                      const float* dglobal, float* row_dot, float* row_coef, int32_t* row_img,
                                      float* dbeta_loc, void* dUT, float* mom_u, float* dgate, void* dZ, float* part,
                                      float* dw2_db1_db2, float* zscr, void* stream);
+/* ---- word-patch attention loss (GLORIALocalContrastiveLoss, src/losses.py:954-1026; attention_fn :698-736) ----
+ * The large products run on mm_grouped_gemm_rows / mm_grouped_gemm_wgrad; these are the passes in between.  Every [*, N]
+ * matrix has N = n_caps * Wp columns, column = caption * Wp + word; words >= cap_len[caption] are masked.
+ *   softmax_exp_fwd: E[row, n] = exp(temp1 * softmax over the caption's words of S[row, :]) (bf16), 0 where masked
+ *   softmax_exp_bwd: dE (bf16, in place) -> dS through exp, temp1 and the softmax
+ *   cos_lse_fwd    : cos[b, n] = cosine(words[n, :], wcU[b, n, :]) (eps 1e-8), sim[b, caption] = log sum_w exp(temp2 cos)
+ *                    (agg_mean: log mean); wcU fp32 [B, N, D], words fp32 [N, D]
+ *   cos_lse_bwd    : dsim [B, n_caps] -> dwcU bf16 [B, N, D] (zeros where masked) and dwords fp32 [N, D] (the direct part) */
+int mm_local_softmax_exp_fwd(const float* S, long long ld_s, void* E, long long ld_e, long long rows, int n_caps, int Wp,
+                             const int32_t* cap_len, float temp1, void* stream);
+int mm_local_softmax_exp_bwd(const void* E, long long ld_e, void* dE, long long ld_d, long long rows, int n_caps, int Wp,
+                             const int32_t* cap_len, float temp1, void* stream);
+int mm_local_cos_lse_fwd(const float* wcU, const float* words, int B, int n_caps, int Wp, int D, const int32_t* cap_len,
+                         float temp2, int agg_mean, float* cosv, float* sim, long long ld_sim, void* stream);
+int mm_local_cos_lse_bwd(const float* dsim, long long ld_dsim, const float* sim, long long ld_sim, const float* cosv,
+                         const float* wcU, const float* words, int B, int n_caps, int Wp, int D, const int32_t* cap_len,
+                         float temp2, int agg_mean, void* dwcU, float* dwords, void* stream);
 /* experimental: 1 = run eligible row GEMMs (plain bf16 epilogue, BN 192 / 256) on CTA pairs (tcgen05 cta_group::2);
  * also switched on by MEDMOE_GEMM_PAIR=1.  Needs 256-row aligned expert segments when tile_info is given. */
 void mm_debug_gemm_pair(int on);

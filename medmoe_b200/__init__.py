@@ -8,6 +8,7 @@ from .distributed import BackpropType, concat_gather_all_gpu, gather_tensor, get
 from .losses import (ContrastiveLossOutput, FLAVAGlobalContrastiveLoss, FLAVAGlobalContrastiveLossOutput,
                      GLORIAGlobalContrastiveLoss, contrastive_loss_with_temperature, zero_shot_predict)
 from .moe import Expert, MoE
+from .local_loss import GLORIALocalContrastiveLoss, GLORIALocalContrastiveLossOutput, local_similarities
 from .checkpoint import extract_moe_state_dict, load_reference_checkpoint
 from .eval_zs import zero_shot_evaluate
 
@@ -17,7 +18,7 @@ __all__ = [
     "MoE", "Expert", "GLORIAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLossOutput",
     "ContrastiveLossOutput", "contrastive_loss_with_temperature", "zero_shot_predict", "BackpropType", "gather_tensor",
     "concat_gather_all_gpu", "get_rank", "activate", "load_reference_checkpoint", "extract_moe_state_dict",
-    "zero_shot_evaluate", "SWIN",
+    "zero_shot_evaluate", "SWIN", "GLORIALocalContrastiveLoss", "GLORIALocalContrastiveLossOutput", "local_similarities",
 ]
 
 
@@ -38,6 +39,7 @@ def activate():
     swin.MoE, swin.Expert = MoE, Expert
     losses = importlib.import_module("src.losses")
     losses.GLORIAGlobalContrastiveLoss = GLORIAGlobalContrastiveLoss
+    losses.GLORIALocalContrastiveLoss = GLORIALocalContrastiveLoss
     losses.FLAVAGlobalContrastiveLoss = FLAVAGlobalContrastiveLoss
     losses.contrastive_loss_with_temperature = contrastive_loss_with_temperature
     return swin, losses

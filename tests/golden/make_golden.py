@@ -138,7 +138,7 @@ def loss_cases():
     print("losses: gloria16", out["gloria16.loss"].item(), "flava", out["flava.loss"].item())
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and os.environ.get("GOLDEN_ONLY", "") != "local":
     assert rs.available(), "needs /root/reference"
     # small-width MoE (keeps the fixture ~2 MB) incl. experts that receive no image
     moe_case("moe_small", K=3, hidden=[32, 64, 128, 256], D=256, Ps=[64, 16, 4, 1], B=6, seed=0)
@@ -150,3 +150,28 @@ if __name__ == "__main__":
     moe_case("moe_k6_bf16w", K=6, hidden=[96, 192, 384, 768], D=768, Ps=[16, 4, 1, 1], B=4, seed=2, store_params=False,
              round_bf16=True)
     loss_cases()
+
+
+def local_loss_case():
+    """GLORIALocalContrastiveLoss (src/losses.py:954-1026) on seeded inputs, ragged caption lengths."""
+    losses = rs.load_losses_module()
+    torch.manual_seed(21)
+    B, D, H, L = 5, 128, 6, 9
+    img = (0.5 * torch.randn(B, D, H, H)).requires_grad_(True)
+    words = (0.5 * torch.randn(B, D, L)).requires_grad_(True)
+    cap_lens = [9, 4, 7, 1, 6]
+    out = {}
+    for agg in ("sum", "mean"):
+        img.grad = None
+        words.grad = None
+        res = losses.GLORIALocalContrastiveLoss()(img, words, cap_lens, temp1=4.0, temp2=5.0, temp3=10.0, agg=agg)
+        (res.loss0 + res.loss1).backward()
+        out.update({f"loss0_{agg}": res.loss0, f"loss1_{agg}": res.loss1, f"d_img_{agg}": img.grad.clone(),
+                    f"d_words_{agg}": words.grad.clone(), f"att0_{agg}": res.att_maps[0], f"att3_{agg}": res.att_maps[3]})
+    out.update({"img": img, "words": words, "cap_lens": torch.tensor(cap_lens)})
+    np.savez_compressed(os.path.join(HERE, "local_loss.npz"), **npify(out))
+    print("local_loss.npz", float(out["loss0_sum"]), float(out["loss1_sum"]))
+
+
+if __name__ == "__main__":       # GOLDEN_ONLY=local regenerates just this fixture
+    local_loss_case()

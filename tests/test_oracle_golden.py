@@ -120,3 +120,20 @@ def test_zero_shot_oracle():
     pred, sim = lo.zero_shot_predict(img, txt)
     ref = torch.nn.functional.cosine_similarity(img.double()[:, None], txt.double()[None], dim=-1)
     assert torch.allclose(sim, ref, atol=1e-12) and torch.equal(pred, ref.argmax(-1))
+
+
+def test_local_loss_oracle_matches_reference_golden():
+    """oracle/local_loss_oracle.py against the committed outputs of the reference's GLORIALocalContrastiveLoss."""
+    import os
+    import numpy as np
+    from oracle import local_loss_oracle as lo
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "local_loss.npz"))
+    for agg in ("sum", "mean"):
+        img = torch.tensor(g["img"]).requires_grad_(True)
+        words = torch.tensor(g["words"]).requires_grad_(True)
+        l0, l1, att = lo.gloria_local_loss(img, words, g["cap_lens"].tolist(), agg=agg)
+        (l0 + l1).backward()
+        assert abs(l0.item() - float(g[f"loss0_{agg}"])) < 1e-5 and abs(l1.item() - float(g[f"loss1_{agg}"])) < 1e-5
+        assert torch.allclose(img.grad, torch.tensor(g[f"d_img_{agg}"]), atol=1e-6)
+        assert torch.allclose(words.grad, torch.tensor(g[f"d_words_{agg}"]), atol=1e-6)
+        assert torch.allclose(att[3], torch.tensor(g[f"att3_{agg}"]), atol=1e-6)
