@@ -26,55 +26,105 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// one thread per (row, caption): a caption's Wp scores are contiguous, neighbouring threads take neighbouring captions
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// G lanes per (row, caption), four consecutive words per lane (one 16-byte load of S, one 8-byte store of E), 32 / G captions
+// per warp; the reductions are xor-shuffles inside the G-lane group.  Work items = (row, group of 32 / G captions).
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int G>
 __global__ void __launch_bounds__(256)
 ll_softmax_exp_fwd_kernel(const float* __restrict__ S, long long ld_s, __nv_bfloat16* __restrict__ E, long long ld_e,
-                          long long rows, int n_caps, int Wp, const int* __restrict__ cap_len, float temp1) {
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= rows * n_caps) return;
-    const long long row = t / n_caps;
-    const int cap = static_cast<int>(t - row * n_caps);
-    const int len = min(cap_len[cap], Wp);
-    const float* s = S + row * ld_s + static_cast<long long>(cap) * Wp;
-    __nv_bfloat16* e = E + row * ld_e + static_cast<long long>(cap) * Wp;
-    float mx = -INFINITY;
-    for (int w = 0; w < len; ++w) mx = fmaxf(mx, s[w]);
-    float sum = 0.f;
-    for (int w = 0; w < len; ++w) sum += __expf(s[w] - mx);
-    const float inv = len > 0 ? 1.0f / sum : 0.f;
-    for (int w = 0; w < Wp; ++w) {
-        float v = 0.f;
-        if (w < len) v = __expf(temp1 * __expf(s[w] - mx) * inv);
-        e[w] = __float2bfloat16(v);
+                          unsigned rows, int n_caps, int Wp, const int* __restrict__ cap_len, float temp1) {
+    constexpr int CPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, w0 = (lane % G) * 4;
+    const unsigned gpr = (n_caps + CPW - 1) / CPW;
+    const unsigned total = rows * gpr;
+    const unsigned stride = gridDim.x * (blockDim.x >> 5);
+    for (unsigned t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += stride) {
+        const unsigned row = t / gpr;
+        const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
+        const bool on = cap < n_caps && w0 < Wp;
+        const int len = cap < n_caps ? min(__ldg(cap_len + cap), Wp) : 0;
+        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (on) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(row) * ld_s + static_cast<long long>(cap) * Wp + w0);
+        const bool m0 = w0 < len, m1 = w0 + 1 < len, m2 = w0 + 2 < len, m3 = w0 + 3 < len;
+        float mx = fmaxf(fmaxf(m0 ? v.x : -INFINITY, m1 ? v.y : -INFINITY), fmaxf(m2 ? v.z : -INFINITY, m3 ? v.w : -INFINITY));
+        mx = group_max<G>(mx);
+        const float e0 = m0 ? __expf(v.x - mx) : 0.f, e1 = m1 ? __expf(v.y - mx) : 0.f;
+        const float e2 = m2 ? __expf(v.z - mx) : 0.f, e3 = m3 ? __expf(v.w - mx) : 0.f;
+        const float sum = group_sum<G>((e0 + e1) + (e2 + e3));
+        const float sc = len > 0 ? temp1 / sum : 0.f;
+        if (on) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(m0 ? __expf(e0 * sc) : 0.f, m1 ? __expf(e1 * sc) : 0.f);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(m2 ? __expf(e2 * sc) : 0.f, m3 ? __expf(e3 * sc) : 0.f);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(E + static_cast<long long>(row) * ld_e + static_cast<long long>(cap) * Wp + w0) = pk;
+        }
     }
 }
 
 // dE (in place -> dS): a = log(E) / temp1 is the first softmax's output, g = dE * temp1 * E, dS = a (g - sum_w a g)
+template <int G>
 __global__ void __launch_bounds__(256)
 ll_softmax_exp_bwd_kernel(const __nv_bfloat16* __restrict__ E, long long ld_e, __nv_bfloat16* __restrict__ dE, long long ld_d,
-                          long long rows, int n_caps, int Wp, const int* __restrict__ cap_len, float temp1) {
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= rows * n_caps) return;
-    const long long row = t / n_caps;
-    const int cap = static_cast<int>(t - row * n_caps);
-    const int len = min(cap_len[cap], Wp);
-    const __nv_bfloat16* e = E + row * ld_e + static_cast<long long>(cap) * Wp;
-    __nv_bfloat16* d = dE + row * ld_d + static_cast<long long>(cap) * Wp;
+                          unsigned rows, int n_caps, int Wp, const int* __restrict__ cap_len, float temp1) {
+    constexpr int CPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, w0 = (lane % G) * 4;
+    const unsigned gpr = (n_caps + CPW - 1) / CPW;
+    const unsigned total = rows * gpr;
+    const unsigned stride = gridDim.x * (blockDim.x >> 5);
     const float inv_t = 1.0f / temp1;
-    float dot = 0.f;
-    for (int w = 0; w < len; ++w) {
-        const float ev = __bfloat162float(e[w]);
-        const float a = __logf(ev) * inv_t;
-        dot += a * (__bfloat162float(d[w]) * temp1 * ev);
-    }
-    for (int w = 0; w < Wp; ++w) {
-        float v = 0.f;
-        if (w < len) {
-            const float ev = __bfloat162float(e[w]);
-            const float a = __logf(ev) * inv_t;
-            v = a * (__bfloat162float(d[w]) * temp1 * ev - dot);
+    for (unsigned t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += stride) {
+        const unsigned row = t / gpr;
+        const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
+        const bool on = cap < n_caps && w0 < Wp;
+        const int len = cap < n_caps ? min(__ldg(cap_len + cap), Wp) : 0;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+        __nv_bfloat16* dp = dE + static_cast<long long>(row) * ld_d + static_cast<long long>(cap) * Wp + w0;
+        if (on) {
+            const uint2 ev = *reinterpret_cast<const uint2*>(E + static_cast<long long>(row) * ld_e + static_cast<long long>(cap) * Wp + w0);
+            const uint2 dv = *reinterpret_cast<const uint2*>(dp);
+            const float ef[4] = {__uint_as_float(ev.x << 16), __uint_as_float(ev.x & 0xffff0000u),
+                                 __uint_as_float(ev.y << 16), __uint_as_float(ev.y & 0xffff0000u)};
+            const float df[4] = {__uint_as_float(dv.x << 16), __uint_as_float(dv.x & 0xffff0000u),
+                                 __uint_as_float(dv.y << 16), __uint_as_float(dv.y & 0xffff0000u)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (w0 + k < len) {
+                    a[k] = __logf(ef[k]) * inv_t;
+                    g[k] = df[k] * temp1 * ef[k];
+                }
+            }
         }
-        d[w] = __float2bfloat16(v);
+        const float dot = group_sum<G>((a[0] * g[0] + a[1] * g[1]) + (a[2] * g[2] + a[3] * g[3]));
+        if (on) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(a[0] * (g[0] - dot), a[1] * (g[1] - dot));
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(a[2] * (g[2] - dot), a[3] * (g[3] - dot));
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dp) = pk;
+        }
     }
 }
 
@@ -191,8 +241,19 @@ extern "C" int mm_local_softmax_exp_fwd(const float* S, long long ld_s, void* E,
                "mm_local_softmax_exp_fwd: leading dimensions must cover n_caps * Wp columns");
     const long long total = rows * n_caps;
     if (total == 0) return MM_OK;
-    ll_softmax_exp_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        S, ld_s, static_cast<__nv_bfloat16*>(E), ld_e, rows, n_caps, Wp, cap_len, temp1);
+    MM_REQUIRE(Wp <= 128 && Wp % 8 == 0 && ld_s % 4 == 0 && ld_e % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(E) & 7) == 0,
+               MM_ERR_UNSUPPORTED, "mm_local_softmax_exp_fwd: Wp must be a multiple of 8 up to 128, rows 16-byte aligned");
+    MM_REQUIRE(rows * (n_caps + 1) < (1LL << 32), MM_ERR_UNSUPPORTED, "mm_local_softmax_exp_fwd: too many (row, caption) pairs");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* Eb = static_cast<__nv_bfloat16*>(E);
+    const unsigned grid = 148 * 16, r = static_cast<unsigned>(rows);
+    const int lanes = (Wp + 3) / 4;
+    if (lanes <= 2) ll_softmax_exp_fwd_kernel<2><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+    else if (lanes <= 4) ll_softmax_exp_fwd_kernel<4><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+    else if (lanes <= 8) ll_softmax_exp_fwd_kernel<8><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+    else if (lanes <= 16) ll_softmax_exp_fwd_kernel<16><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+    else ll_softmax_exp_fwd_kernel<32><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
     note_launches(1);
     return check_launch("mm_local_softmax_exp_fwd");
 }
@@ -202,8 +263,20 @@ extern "C" int mm_local_softmax_exp_bwd(const void* E, long long ld_e, void* dE,
     MM_REQUIRE(E && dE && cap_len && rows >= 0 && n_caps > 0 && Wp > 0, MM_ERR_BAD_SHAPE, "mm_local_softmax_exp_bwd: bad arguments");
     const long long total = rows * n_caps;
     if (total == 0) return MM_OK;
-    ll_softmax_exp_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(E), ld_e, static_cast<__nv_bfloat16*>(dE), ld_d, rows, n_caps, Wp, cap_len, temp1);
+    MM_REQUIRE(Wp <= 128 && Wp % 8 == 0 && ld_e % 4 == 0 && ld_d % 4 == 0 && (reinterpret_cast<uintptr_t>(E) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dE) & 7) == 0,
+               MM_ERR_UNSUPPORTED, "mm_local_softmax_exp_bwd: Wp must be a multiple of 8 up to 128, rows 8-byte aligned");
+    MM_REQUIRE(rows * (n_caps + 1) < (1LL << 32), MM_ERR_UNSUPPORTED, "mm_local_softmax_exp_bwd: too many (row, caption) pairs");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* Eb = static_cast<const __nv_bfloat16*>(E);
+    __nv_bfloat16* Db = static_cast<__nv_bfloat16*>(dE);
+    const unsigned grid = 148 * 16, r = static_cast<unsigned>(rows);
+    const int lanes = (Wp + 3) / 4;
+    if (lanes <= 2) ll_softmax_exp_bwd_kernel<2><<<grid, 256, 0, st>>>(Eb, ld_e, Db, ld_d, r, n_caps, Wp, cap_len, temp1);
+    else if (lanes <= 4) ll_softmax_exp_bwd_kernel<4><<<grid, 256, 0, st>>>(Eb, ld_e, Db, ld_d, r, n_caps, Wp, cap_len, temp1);
+    else if (lanes <= 8) ll_softmax_exp_bwd_kernel<8><<<grid, 256, 0, st>>>(Eb, ld_e, Db, ld_d, r, n_caps, Wp, cap_len, temp1);
+    else if (lanes <= 16) ll_softmax_exp_bwd_kernel<16><<<grid, 256, 0, st>>>(Eb, ld_e, Db, ld_d, r, n_caps, Wp, cap_len, temp1);
+    else ll_softmax_exp_bwd_kernel<32><<<grid, 256, 0, st>>>(Eb, ld_e, Db, ld_d, r, n_caps, Wp, cap_len, temp1);
     note_launches(1);
     return check_launch("mm_local_softmax_exp_bwd");
 }

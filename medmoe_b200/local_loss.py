@@ -10,9 +10,9 @@ streaming passes (csrc/local_loss.cu):
               cos, sim = cosine + log-sum-exp         mm_local_cos_lse_fwd
     backward  dwcU, dwords(direct)                    mm_local_cos_lse_bwd
               dE  = ctx_b dwcU_b^T                    grouped rows GEMM
-              dctx  = E dwcU_b                        grouped rows GEMM (fp32 out)
               dS                                      mm_local_softmax_exp_bwd (in place over dE)
-              dctx += dS words ;  dwords += dS^T ctx  dense rows GEMM, dense wgrad GEMM
+              dctx = [E | dS] [dwcU_b ; words]        ONE grouped rows GEMM over K = 2N (E and dS share a buffer), fp32 out
+              dwords = dS^T ctx + direct part         dense wgrad GEMM
 
 The softmax over patches is `E / colsum(E)`; the cosine that consumes the attended context is scale free, so the column sums
 are never formed (they only matter for the returned attention maps, which are computed for the B matching pairs alone).
@@ -107,26 +107,29 @@ class _LocalSimilarity(torch.autograd.Function):
         blocks = [(c0, min(caps, c0 + cb)) for c0 in range(0, caps, cb)]
 
         sim = torch.empty(B, caps, dtype=torch.float32, device=dev)
-        Es, wcUs, coss = [], [], []
+        # [E | dE]: the backward's d ctx GEMM multiplies both halves in one pass (K = 2N), so they share a buffer
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        ES = torch.empty(rows, 2 * N if need_grad else N, dtype=torch.bfloat16, device=dev)
+        wcUs, coss = [], []
         for c0, c1 in blocks:
             Nb = (c1 - c0) * Wp
             wblk = words16[c0 * Wp:c1 * Wp]
             S = torch.empty(rows, Nb, dtype=torch.float32, device=dev)
             ops.gemm_rows(ctx16, wblk, Nb, S, M=rows, tag="LL.S")
-            E = torch.empty(rows, Nb, dtype=torch.bfloat16, device=dev)
-            _lib.call("mm_local_softmax_exp_fwd", _P(S), Nb, _P(E), Nb, rows, c1 - c0, Wp, _P(cap_len[c0:c1]), float(temp1), _st(),
-                      label="LL.softmax_exp")
+            E = ES[:, c0 * Wp:c1 * Wp]
+            _lib.call("mm_local_softmax_exp_fwd", _P(S), Nb, _P(E), ES.stride(0), rows, c1 - c0, Wp, _P(cap_len[c0:c1]),
+                      float(temp1), _st(), label="LL.softmax_exp")
             del S
             wcU = torch.zeros(B, Nb, D, dtype=torch.float32, device=dev)
             ops.gemm_wgrad(E, ctx16, wcU, img_chunks, 0, n_img_chunks, 0, tag="LL.wc")
             cosv = torch.empty(B, Nb, dtype=torch.float32, device=dev)
             _lib.call("mm_local_cos_lse_fwd", _P(wcU), _P(words32[c0 * Wp:c1 * Wp]), B, c1 - c0, Wp, D, _P(cap_len[c0:c1]),
                       float(temp2), int(agg_mean), _P(cosv), _P(sim[:, c0:]), caps, _st(), label="LL.cos_lse")
-            Es.append(E); wcUs.append(wcU); coss.append(cosv)
+            wcUs.append(wcU); coss.append(cosv)
 
         ctx.geom = (B, P, D, L, Lc, Wp, caps, N, Ppad, rows, blocks, float(temp1), float(temp2), bool(agg_mean))
         ctx.tables = (img_tiles, all_chunks, n_all_chunks)
-        ctx.saved = (ctx16, words32, words16, cap_len, sim, Es, wcUs, coss)
+        ctx.saved = (ctx16, words32, words16, cap_len, sim, ES, wcUs, coss)
         ctx.in_dtypes = (tokens.dtype, words.dtype)
         return sim[:, :B].clone()
 
@@ -134,38 +137,39 @@ class _LocalSimilarity(torch.autograd.Function):
     def backward(ctx, dsim: Tensor):
         B, P, D, L, Lc, Wp, caps, N, Ppad, rows, blocks, temp1, temp2, agg_mean = ctx.geom
         img_tiles, all_chunks, n_all_chunks = ctx.tables
-        ctx16, words32, words16, cap_len, sim, Es, wcUs, coss = ctx.saved
+        ctx16, words32, words16, cap_len, sim, ES, wcUs, coss = ctx.saved
         dev = ctx16.device
         dsim_pad = torch.zeros(B, caps, dtype=torch.float32, device=dev)
         dsim_pad[:, :B].copy_(dsim)
-        dctx = torch.zeros(rows, D, dtype=torch.float32, device=dev)
-        dwords = torch.empty(N, D, dtype=torch.float32, device=dev)
+        dw_direct = torch.empty(N, D, dtype=torch.float32, device=dev)
         tiles = rows // 128
-        for (c0, c1), E, wcU, cosv in zip(blocks, Es, wcUs, coss):
+        ld = ES.stride(0)
+        # per-image weights of the d ctx GEMM: [dwcU_b^T | words^T], matching the [E | dS] columns of ES
+        Wcat = torch.empty(B, D, 2 * N, dtype=torch.bfloat16, device=dev)
+        Wcat[:, :, N:] = words16.t()
+        for (c0, c1), wcU, cosv in zip(blocks, wcUs, coss):
             nc = c1 - c0
             Nb = nc * Wp
             dwcU = torch.empty(B, Nb, D, dtype=torch.bfloat16, device=dev)
-            dw_direct = torch.empty(Nb, D, dtype=torch.float32, device=dev)
             _lib.call("mm_local_cos_lse_bwd", _P(dsim_pad[:, c0:]), caps, _P(sim[:, c0:]), caps, _P(cosv), _P(wcU),
-                      _P(words32[c0 * Wp:c1 * Wp]), B, nc, Wp, D, _P(cap_len[c0:c1]), temp2, int(agg_mean), _P(dwcU), _P(dw_direct),
-                      _st(), label="LL.cos_lse_bwd")
+                      _P(words32[c0 * Wp:c1 * Wp]), B, nc, Wp, D, _P(cap_len[c0:c1]), temp2, int(agg_mean), _P(dwcU),
+                      _P(dw_direct[c0 * Wp:c1 * Wp]), _st(), label="LL.cos_lse_bwd")
+            Wcat[:, :, c0 * Wp:c1 * Wp] = dwcU.transpose(1, 2)
             # dE[(b, p), n] = <ctx[(b, p)], dwcU[b, n]>: every image multiplies its own [Nb, D] matrix
-            dE = torch.empty(rows, Nb, dtype=torch.bfloat16, device=dev)
+            dE = ES[:, N + c0 * Wp:N + c1 * Wp]
             ops.gemm_rows(ctx16, dwcU.view(B * Nb, D), Nb, dE, plan=img_tiles, tile_begin=0, tile_count=tiles, tag="LL.dE")
-            # d ctx (through the attended context) = E dwcU_b
-            part = torch.empty(rows, D, dtype=torch.float32, device=dev)
-            dwcUT = dwcU.transpose(1, 2).contiguous().view(B * D, Nb)
-            ops.gemm_rows(E, dwcUT, D, part, plan=img_tiles, tile_begin=0, tile_count=tiles, tag="LL.dctx_wc")
-            dctx += part
-            _lib.call("mm_local_softmax_exp_bwd", _P(E), Nb, _P(dE), Nb, rows, nc, Wp, _P(cap_len[c0:c1]), temp1, _st(),
-                      label="LL.softmax_exp_bwd")
-            dS = dE
-            wT = words16[c0 * Wp:c1 * Wp].t().contiguous()                       # [D, Nb]
-            ops.gemm_rows(dS, wT, D, part, M=rows, tag="LL.dctx_S")
-            dctx += part
-            dw = torch.zeros(1, Nb, D, dtype=torch.float32, device=dev)
-            ops.gemm_wgrad(dS, ctx16, dw, all_chunks, 0, n_all_chunks, 0, tag="LL.dwords")
-            dwords[c0 * Wp:c1 * Wp] = dw[0] + dw_direct
+            _lib.call("mm_local_softmax_exp_bwd", _P(ES[:, c0 * Wp:c1 * Wp]), ld, _P(dE), ld, rows, nc, Wp, _P(cap_len[c0:c1]),
+                      temp1, _st(), label="LL.softmax_exp_bwd")
+            del dwcU
+        dS = ES[:, N:]
+        # d ctx = E dwcU_b + dS words in one grouped GEMM over K = 2N
+        dctx = torch.empty(rows, D, dtype=torch.float32, device=dev)
+        ops.gemm_rows(ES, Wcat.view(B * D, 2 * N), D, dctx, plan=img_tiles, tile_begin=0, tile_count=tiles, tag="LL.dctx")
+        del Wcat
+        # d words = dS^T ctx (+ the direct part through the cosine)
+        dwords = torch.zeros(1, N, D, dtype=torch.float32, device=dev)
+        ops.gemm_wgrad(dS, ctx16, dwords, all_chunks, 0, n_all_chunks, 0, tag="LL.dwords")
+        dwords = dwords[0] + dw_direct
         tok_dtype, word_dtype = ctx.in_dtypes
         d_tokens = dctx.view(B, Ppad, D)[:, :P].to(tok_dtype)
         d_words = torch.zeros(B, L, D, dtype=word_dtype, device=dev)

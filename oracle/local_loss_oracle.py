@@ -53,5 +53,5 @@ def gloria_local_loss(img_features: torch.Tensor, words_emb: torch.Tensor, cap_l
     """-> (loss0, loss1, att_maps)   (losses.py:1007-1021)."""
     sim, att_maps = similarities(img_features, words_emb, cap_lens, temp1, temp2, agg)
     sim = sim * temp3
-    labels = torch.arange(img_features.shape[0])
+    labels = torch.arange(img_features.shape[0], device=sim.device)
     return F.cross_entropy(sim, labels), F.cross_entropy(sim.t(), labels), att_maps
