@@ -178,7 +178,12 @@ int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, const float* 
  *   softmax_exp_bwd: dE (bf16, in place) -> dS through exp, temp1 and the softmax
  *   cos_lse_fwd    : cos[b, n] = cosine(words[n, :], wcU[b, n, :]) (eps 1e-8), sim[b, caption] = log sum_w exp(temp2 cos)
  *                    (agg_mean: log mean); wcU fp32 [B, N, D], words fp32 [N, D]
- *   cos_lse_bwd    : dsim [B, n_caps] -> dwcU bf16 [B, N, D] (zeros where masked) and dwords fp32 [N, D] (the direct part) */
+ *   cos_lse_bwd    : dsim [B, n_caps] -> dwcU bf16 [B, N, D] (zeros where masked), its transpose dwcUT[(b * D + d) * ld_t + n]
+ *                    (the K-major weight of the d ctx GEMM) and dwords fp32 [N, D] (the direct part); N % 16 == 0 */
+/* score GEMM + first softmax in one kernel for captions padded to exactly 32 word slots:
+ * E[row, 32 c + w] = exp(temp1 * softmax_w(<A[row, :], W[32 c + w, :]>)) for w < cap_len[c], 0 otherwise (bf16) */
+int mm_local_scores_softmax_exp(const void* A, long long rows, int K, long long lda, const void* W, int n_caps, long long ldw,
+                                const int32_t* cap_len, float temp1, void* E, long long ld_e, void* stream);
 int mm_local_softmax_exp_fwd(const float* S, long long ld_s, void* E, long long ld_e, long long rows, int n_caps, int Wp,
                              const int32_t* cap_len, float temp1, void* stream);
 int mm_local_softmax_exp_bwd(const void* E, long long ld_e, void* dE, long long ld_d, long long rows, int n_caps, int Wp,
@@ -187,7 +192,7 @@ int mm_local_cos_lse_fwd(const float* wcU, const float* words, int B, int n_caps
                          float temp2, int agg_mean, float* cosv, float* sim, long long ld_sim, void* stream);
 int mm_local_cos_lse_bwd(const float* dsim, long long ld_dsim, const float* sim, long long ld_sim, const float* cosv,
                          const float* wcU, const float* words, int B, int n_caps, int Wp, int D, const int32_t* cap_len,
-                         float temp2, int agg_mean, void* dwcU, float* dwords, void* stream);
+                         float temp2, int agg_mean, void* dwcU, void* dwcUT, long long ld_t, float* dwords, void* stream);
 /* experimental: 1 = run eligible row GEMMs (plain bf16 epilogue, BN 192 / 256) on CTA pairs (tcgen05 cta_group::2);
  * also switched on by MEDMOE_GEMM_PAIR=1.  Needs 256-row aligned expert segments when tile_info is given. */
 void mm_debug_gemm_pair(int on);

@@ -56,11 +56,12 @@ SIGNATURES = {
     "mm_combine_bwd_tc_supported": (c_int, [c_int, c_vp, c_int]),
     "mm_debug_force_cuda_core_dut": (None, [c_int]),
     "mm_debug_gemm_pair": (None, [c_int]),
+    "mm_local_scores_softmax_exp": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_ll, c_vp, c_f, c_vp, c_ll, c_vp]),
     "mm_local_softmax_exp_fwd": (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_f, c_vp]),
     "mm_local_softmax_exp_bwd": (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_f, c_vp]),
     "mm_local_cos_lse_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_f, c_int, c_vp, c_vp, c_ll, c_vp]),
     "mm_local_cos_lse_bwd": (c_int, [c_vp, c_ll, c_vp, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_f, c_int,
-                                     c_vp, c_vp, c_vp]),
+                                     c_vp, c_vp, c_ll, c_vp, c_vp]),
     "mm_interp_softmax_combine_bwd_tc": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_vp, c_vp,
                                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

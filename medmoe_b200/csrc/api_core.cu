@@ -283,8 +283,10 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
                           long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
                           const float* bias, const void* aux, long long ld_aux, const Rank1Aux* r1, const void* gate,
                           long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
-                          float out_scale, int flags, void* stream) {
+                          float out_scale, int flags, void* stream, const int32_t* cap_len = nullptr, float cap_temp = 0.f) {
     MM_REQUIRE(A && W && out, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: null operand");
+    MM_REQUIRE(!(flags & EPI_CAP_SOFTMAX) || (cap_len && !aux && !r1 && !gate && !out_f32 && !colsum), MM_ERR_UNSUPPORTED,
+               "mm_grouped_gemm_rows: the caption-softmax epilogue is a plain bf16 epilogue and needs cap_len");
     MM_REQUIRE(K > 0 && K % 8 == 0 && N > 0 && E > 0, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: K must be a positive multiple of 8");
     MM_REQUIRE(((aux != nullptr) || (r1 != nullptr)) == (gate != nullptr), MM_ERR_UNSUPPORTED,
                "mm_grouped_gemm_rows: aux and gate must be given together");
@@ -346,8 +348,10 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
     g.row_vec = r1 ? r1->row_vec : nullptr;
     g.vecs = r1 ? r1->vecs : nullptr;
     g.ld_vecs = r1 ? r1->ld_vecs : 0;
+    g.cap_len = cap_len;
+    g.cap_temp = cap_temp;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pair_mode() && !aux && !r1 && !gate && !out_f32 && !colsum && out_scale == 1.0f && (BN == 192 || BN == 256) &&
+    if (pair_mode() && !aux && !r1 && !gate && !out_f32 && !colsum && !cap_len && out_scale == 1.0f && (BN == 192 || BN == 256) &&
         (!tile_info || (tile_begin % 2 == 0))) {
         // each CTA of a pair stages half of the W tile
         rc = encode_tmap_bf16(&m.b, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64,
@@ -393,6 +397,17 @@ extern "C" int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K
     const Rank1Aux r1{row_coef, row_vec, vecs, ld_vecs};
     return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, nullptr, aux, ld_aux, &r1,
                           gate, ld_gate, out, ld_out, 0, colsum, 1.0f, 0, stream);
+}
+
+// E = exp(temp1 * softmax over each caption's words of A W^T): the score GEMM of the word-patch attention loss with the first
+// softmax in its epilogue, for captions padded to exactly 32 word slots (one 32-column epilogue chunk per caption).
+extern "C" int mm_local_scores_softmax_exp(const void* A, long long rows, int K, long long lda, const void* W, int n_caps,
+                                           long long ldw, const int32_t* cap_len, float temp1, void* E, long long ld_e,
+                                           void* stream) {
+    MM_REQUIRE(cap_len && n_caps > 0 && (n_caps * 32) % 128 == 0, MM_ERR_BAD_SHAPE,
+               "mm_local_scores_softmax_exp: cap_len required, 32 * n_caps must be a multiple of 128");
+    return gemm_rows_impl(A, rows, K, lda, W, 1, n_caps * 32, ldw, nullptr, 0, 0, static_cast<int>(rows), nullptr, nullptr, 0,
+                          nullptr, nullptr, 0, E, ld_e, 0, nullptr, 1.0f, EPI_CAP_SOFTMAX, stream, cap_len, temp1);
 }
 
 // dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e (+ optional column sums of A).

@@ -35,6 +35,7 @@ namespace mm {
 enum : int {
     EPI_RELU = 1,       // out = max(out, 0)
     EPI_ZERO_PAD = 2,   // kept for ABI compatibility: padding rows of an owned tile are always written as zeros
+    EPI_CAP_SOFTMAX = 4,  // every 32-column chunk is one caption: out = exp(cap_temp * softmax over its first cap_len[chunk] columns)
 };
 
 struct RowsGemmArgs {
@@ -55,6 +56,9 @@ struct RowsGemmArgs {
     const int* row_vec;      // [rows] index of the row's vector
     const float* vecs;       // [n_vecs, ld_vecs] fp32
     long long ld_vecs;
+    // EPI_CAP_SOFTMAX (word-patch attention scores, local_loss.cu): words per caption of each 32-column chunk, temperature
+    const int* cap_len;
+    float cap_temp;
 };
 
 struct WgradArgs {
@@ -333,6 +337,21 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (a.flags & EPI_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (!AUX && (a.flags & EPI_CAP_SOFTMAX)) {     // a lane holds one row's scores against the 32 word slots of a caption
+                    const int len = min(__ldg(a.cap_len + (col0 >> 5)), 32);
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < len ? f[j] : -INFINITY);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        f[j] = j < len ? __expf(f[j] - mx) : 0.f;
+                        sum += f[j];
+                    }
+                    const float sc = len > 0 ? a.cap_temp / sum : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = j < len ? __expf(f[j] * sc) : 0.f;
                 }
                 if (valid < TILE_M && !row_valid) {      // only a segment's last tile has padding rows
 #pragma unroll

@@ -164,17 +164,22 @@ ll_cos_lse_fwd_kernel(const float* __restrict__ wcU, const float* __restrict__ w
 }
 
 // one warp per column n = (caption, word), looping over the images: d cos -> d wcU[b, n, :] (bf16) and the direct part of d word_n
+// A block of 16 warps takes 16 consecutive columns, so that the transposed copy dwcUT[b, d, n] (the K-major weight of the
+// d ctx GEMM) can be written in full 32-byte sectors through a shared-memory tile.
+constexpr int LL_BWD_WARPS = 16;
 template <int DPL>   // D / 32 elements per lane kept in registers
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LL_BWD_WARPS * 32)
 ll_cos_lse_bwd_kernel(const float* __restrict__ dsim, long long ld_dsim, const float* __restrict__ sim, long long ld_sim,
                       const float* __restrict__ cosv, const float* __restrict__ wcU, const float* __restrict__ words, int B,
                       int n_caps, int Wp, const int* __restrict__ cap_len, float temp2, int agg_mean, float eps,
-                      __nv_bfloat16* __restrict__ dwcU, float* __restrict__ dwords) {
+                      __nv_bfloat16* __restrict__ dwcU, __nv_bfloat16* __restrict__ dwcUT, long long ld_t,
+                      float* __restrict__ dwords) {
     constexpr int D = DPL * 32;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    __shared__ __align__(16) __nv_bfloat16 tile[D][LL_BWD_WARPS];      // [d][n - n0]
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long N = static_cast<long long>(n_caps) * Wp;
-    if (warp >= N) return;
-    const long long n = warp;
+    const long long n0 = static_cast<long long>(blockIdx.x) * LL_BWD_WARPS;
+    const long long n = n0 + wib;                                      // N is a multiple of 16: always in range
     const int cap = static_cast<int>(n / Wp), w = static_cast<int>(n - static_cast<long long>(cap) * Wp);
     const int len = min(cap_len[cap], Wp);
     const bool live = w < len;
@@ -191,39 +196,53 @@ ll_cos_lse_bwd_kernel(const float* __restrict__ dsim, long long ld_dsim, const f
     const float log_len = agg_mean && len > 0 ? logf(static_cast<float>(len)) : 0.f;
     for (int b = 0; b < B; ++b) {
         __nv_bfloat16* out = dwcU + (static_cast<long long>(b) * N + n) * D;
-        if (!live) {
+        float o[DPL];
 #pragma unroll
-            for (int k = 0; k < DPL; ++k) out[lane + 32 * k] = __float2bfloat16(0.f);
-            continue;
+        for (int k = 0; k < DPL; ++k) o[k] = 0.f;
+        if (live) {
+            const float* yp = wcU + (static_cast<long long>(b) * N + n) * D;
+            float y[DPL];
+            float xy = 0.f, yy = 0.f;
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) {
+                y[k] = yp[lane + 32 * k];
+                xy = fmaf(x[k], y[k], xy); yy = fmaf(y[k], y[k], yy);
+            }
+            xy = warp_sum_f(xy); yy = warp_sum_f(yy);
+            const float ny = sqrtf(yy);
+            const float den = nx * ny;
+            const float c = cosv[static_cast<long long>(b) * N + n];
+            // sim = log(sum_w exp(temp2 cos)) [- log len]:  d sim / d cos = temp2 exp(temp2 cos - log sum)
+            const float logm = sim[static_cast<long long>(b) * ld_sim + cap] + log_len;
+            const float dc = dsim[static_cast<long long>(b) * ld_dsim + cap] * temp2 * __expf(temp2 * c - logm);
+            float gy_x = 0.f, gy_y = 0.f, gx_y = 0.f, gx_x = 0.f;     // d cos / d y = gy_x x + gy_y y ; d cos / d x = gx_y y + gx_x x
+            if (den > eps) {                                            // below the clamp the denominator is constant
+                const float r = 1.0f / den;
+                gy_x = r; gy_y = -c / fmaxf(yy, 1e-30f);
+                gx_y = r; gx_x = -c / fmaxf(xx, 1e-30f);
+            } else {
+                gy_x = 1.0f / eps; gx_y = 1.0f / eps;
+            }
+#pragma unroll
+            for (int k = 0; k < DPL; ++k) {
+                o[k] = dc * (gy_x * x[k] + gy_y * y[k]);
+                dx[k] = fmaf(dc, gx_y * y[k] + gx_x * x[k], dx[k]);
+            }
         }
-        const float* yp = wcU + (static_cast<long long>(b) * N + n) * D;
-        float y[DPL];
-        float xy = 0.f, yy = 0.f;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) {
-            y[k] = yp[lane + 32 * k];
-            xy = fmaf(x[k], y[k], xy); yy = fmaf(y[k], y[k], yy);
+            const __nv_bfloat16 v = __float2bfloat16(o[k]);
+            out[lane + 32 * k] = v;
+            tile[lane + 32 * k][wib] = v;
         }
-        xy = warp_sum_f(xy); yy = warp_sum_f(yy);
-        const float ny = sqrtf(yy);
-        const float den = nx * ny;
-        const float c = cosv[static_cast<long long>(b) * N + n];
-        // sim = log(sum_w exp(temp2 cos)) [- log len]:  d sim / d cos = temp2 exp(temp2 cos - log sum)
-        const float logm = sim[static_cast<long long>(b) * ld_sim + cap] + log_len;
-        const float dc = dsim[static_cast<long long>(b) * ld_dsim + cap] * temp2 * __expf(temp2 * c - logm);
-        float gy_x = 0.f, gy_y = 0.f, gx_y = 0.f, gx_x = 0.f;     // d cos / d y = gy_x x + gy_y y ; d cos / d x = gx_y y + gx_x x
-        if (den > eps) {                                            // below the clamp the denominator is constant
-            const float r = 1.0f / den;
-            gy_x = r; gy_y = -c / fmaxf(yy, 1e-30f);
-            gx_y = r; gx_x = -c / fmaxf(xx, 1e-30f);
-        } else {
-            gy_x = 1.0f / eps; gx_y = 1.0f / eps;
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += LL_BWD_WARPS * 32) {
+            const uint4* src = reinterpret_cast<const uint4*>(&tile[d][0]);
+            uint4* dst = reinterpret_cast<uint4*>(dwcUT + (static_cast<long long>(b) * D + d) * ld_t + n0);
+            dst[0] = src[0];
+            dst[1] = src[1];
         }
-#pragma unroll
-        for (int k = 0; k < DPL; ++k) {
-            out[lane + 32 * k] = __float2bfloat16(dc * (gy_x * x[k] + gy_y * y[k]));
-            dx[k] = fmaf(dc, gx_y * y[k] + gx_x * x[k], dx[k]);
-        }
+        __syncthreads();
     }
 #pragma unroll
     for (int k = 0; k < DPL; ++k) dwords[n * D + lane + 32 * k] = dx[k];
@@ -295,17 +314,20 @@ extern "C" int mm_local_cos_lse_fwd(const float* wcU, const float* words, int B,
 
 extern "C" int mm_local_cos_lse_bwd(const float* dsim, long long ld_dsim, const float* sim, long long ld_sim, const float* cosv,
                                     const float* wcU, const float* words, int B, int n_caps, int Wp, int D,
-                                    const int32_t* cap_len, float temp2, int agg_mean, void* dwcU, float* dwords,
-                                    void* stream) {
-    MM_REQUIRE(dsim && sim && cosv && wcU && words && cap_len && dwcU && dwords && B > 0 && n_caps > 0 && Wp > 0, MM_ERR_BAD_SHAPE,
-               "mm_local_cos_lse_bwd: bad arguments");
+                                    const int32_t* cap_len, float temp2, int agg_mean, void* dwcU, void* dwcUT,
+                                    long long ld_t, float* dwords, void* stream) {
+    MM_REQUIRE(dsim && sim && cosv && wcU && words && cap_len && dwcU && dwcUT && dwords && B > 0 && n_caps > 0 && Wp > 0,
+               MM_ERR_BAD_SHAPE, "mm_local_cos_lse_bwd: bad arguments");
     const long long warps = static_cast<long long>(n_caps) * Wp;
-    const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+    MM_REQUIRE(warps % LL_BWD_WARPS == 0 && ld_t % 8 == 0 && (reinterpret_cast<uintptr_t>(dwcUT) & 15) == 0, MM_ERR_BAD_SHAPE,
+               "mm_local_cos_lse_bwd: n_caps * Wp must be a multiple of 16, dwcUT rows 16-byte aligned");
+    const unsigned grid = static_cast<unsigned>(warps / LL_BWD_WARPS);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MM_LL_CASE(dpl)                                                                                                  \
     case dpl * 32:                                                                                                       \
-        ll_cos_lse_bwd_kernel<dpl><<<grid, 256, 0, st>>>(dsim, ld_dsim, sim, ld_sim, cosv, wcU, words, B, n_caps, Wp, cap_len,  \
-                                                         temp2, agg_mean, 1e-8f, static_cast<__nv_bfloat16*>(dwcU), dwords); \
+        ll_cos_lse_bwd_kernel<dpl><<<grid, LL_BWD_WARPS * 32, 0, st>>>(                                                  \
+            dsim, ld_dsim, sim, ld_sim, cosv, wcU, words, B, n_caps, Wp, cap_len, temp2, agg_mean, 1e-8f,                \
+            static_cast<__nv_bfloat16*>(dwcU), static_cast<__nv_bfloat16*>(dwcUT), ld_t, dwords);                        \
         break;
     switch (D) {
         MM_LL_CASE(24)

@@ -35,6 +35,7 @@ from . import _lib, ops
 
 _P = _lib.ptr
 SCORE_BYTES_BUDGET = 6 << 30
+FUSE_SCORE_SOFTMAX = True       # captions of at most 32 words: first softmax in the score GEMM's epilogue (tests switch it off)
 
 
 def _st():
@@ -104,6 +105,9 @@ class _LocalSimilarity(torch.autograd.Function):
         # caption blocks: 16 captions at least, as many as keep the fp32 scores of a block under the budget
         per_cap = rows * Wp * 4
         cb = max(16, min(caps, (SCORE_BYTES_BUDGET // max(per_cap, 1)) // 16 * 16))
+        fused_scores = Wp == 32 and FUSE_SCORE_SOFTMAX     # one epilogue chunk per caption: the scores never leave the SM
+        if fused_scores:
+            cb = caps
         blocks = [(c0, min(caps, c0 + cb)) for c0 in range(0, caps, cb)]
 
         sim = torch.empty(B, caps, dtype=torch.float32, device=dev)
@@ -114,12 +118,16 @@ class _LocalSimilarity(torch.autograd.Function):
         for c0, c1 in blocks:
             Nb = (c1 - c0) * Wp
             wblk = words16[c0 * Wp:c1 * Wp]
-            S = torch.empty(rows, Nb, dtype=torch.float32, device=dev)
-            ops.gemm_rows(ctx16, wblk, Nb, S, M=rows, tag="LL.S")
             E = ES[:, c0 * Wp:c1 * Wp]
-            _lib.call("mm_local_softmax_exp_fwd", _P(S), Nb, _P(E), ES.stride(0), rows, c1 - c0, Wp, _P(cap_len[c0:c1]),
-                      float(temp1), _st(), label="LL.softmax_exp")
-            del S
+            if fused_scores:
+                _lib.call("mm_local_scores_softmax_exp", _P(ctx16), rows, D, D, _P(wblk), c1 - c0, D, _P(cap_len[c0:c1]),
+                          float(temp1), _P(E), ES.stride(0), _st(), label=f"LL.S+softmax_exp:gemm_rows[K={D},N={Nb}]")
+            else:
+                S = torch.empty(rows, Nb, dtype=torch.float32, device=dev)
+                ops.gemm_rows(ctx16, wblk, Nb, S, M=rows, tag="LL.S")
+                _lib.call("mm_local_softmax_exp_fwd", _P(S), Nb, _P(E), ES.stride(0), rows, c1 - c0, Wp, _P(cap_len[c0:c1]),
+                          float(temp1), _st(), label="LL.softmax_exp")
+                del S
             wcU = torch.zeros(B, Nb, D, dtype=torch.float32, device=dev)
             ops.gemm_wgrad(E, ctx16, wcU, img_chunks, 0, n_img_chunks, 0, tag="LL.wc")
             cosv = torch.empty(B, Nb, dtype=torch.float32, device=dev)
@@ -153,8 +161,7 @@ class _LocalSimilarity(torch.autograd.Function):
             dwcU = torch.empty(B, Nb, D, dtype=torch.bfloat16, device=dev)
             _lib.call("mm_local_cos_lse_bwd", _P(dsim_pad[:, c0:]), caps, _P(sim[:, c0:]), caps, _P(cosv), _P(wcU),
                       _P(words32[c0 * Wp:c1 * Wp]), B, nc, Wp, D, _P(cap_len[c0:c1]), temp2, int(agg_mean), _P(dwcU),
-                      _P(dw_direct[c0 * Wp:c1 * Wp]), _st(), label="LL.cos_lse_bwd")
-            Wcat[:, :, c0 * Wp:c1 * Wp] = dwcU.transpose(1, 2)
+                      _P(Wcat[:, :, c0 * Wp:]), 2 * N, _P(dw_direct[c0 * Wp:c1 * Wp]), _st(), label="LL.cos_lse_bwd")
             # dE[(b, p), n] = <ctx[(b, p)], dwcU[b, n]>: every image multiplies its own [Nb, D] matrix
             dE = ES[:, N + c0 * Wp:N + c1 * Wp]
             ops.gemm_rows(ctx16, dwcU.view(B * Nb, D), Nb, dE, plan=img_tiles, tile_begin=0, tile_count=tiles, tag="LL.dE")

@@ -73,3 +73,23 @@ def test_local_similarities_take_the_moe_local_feat_view():
     sim = local_similarities(local, words, [L] * B)
     ref, _ = lo.similarities(local.float().cpu(), words.to(torch.bfloat16).float().cpu(), [L] * B)
     assert rel_err(sim.cpu(), ref) < 5e-3
+
+
+def test_fused_score_softmax_epilogue_agrees_with_the_two_pass_path(monkeypatch):
+    """Captions of <= 32 words: the first softmax runs in the score GEMM's epilogue; same result as GEMM + separate pass."""
+    from medmoe_b200 import local_loss as ll
+    B, D, H, L = 9, 768, 12, 30
+    g = torch.Generator(device="cuda").manual_seed(2)
+    img = torch.randn(B, D, H, H, device="cuda", generator=g) * 0.3
+    words = torch.randn(B, D, L, device="cuda", generator=g) * 0.3
+    cap_lens = [30, 1, 17, 25, 32, 8, 30, 29, 2]
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(ll, "FUSE_SCORE_SOFTMAX", fused)
+        x, w = img.clone().requires_grad_(True), words.clone().requires_grad_(True)
+        sim = local_similarities(x, w, cap_lens)
+        sim.square().sum().backward()
+        outs.append((sim.detach(), x.grad, w.grad))
+    assert rel_err(outs[0][0], outs[1][0]) < 1e-4
+    assert rel_err(outs[0][1], outs[1][1]) < 2e-3
+    assert rel_err(outs[0][2], outs[1][2]) < 2e-3
