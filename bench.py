@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--topk", type=int, default=1, help="experts per image (1 = the reference; 2 = BASELINE config 4 extension)")
     ap.add_argument("--loss", default="flava", choices=["flava", "gloria"])
     ap.add_argument("--local-grad", action="store_true", help="also feed a dense synthetic cotangent into local_feat")
+    ap.add_argument("--local-loss", action="store_true",
+                    help="add the word-patch attention loss (GLORIALocalContrastiveLoss) on local_feat: the reference's full objective")
+    ap.add_argument("--words", type=int, default=25, help="words per caption for --local-loss")
     ap.add_argument("--routing", default="natural", choices=["natural", "uniform", "skew"],
                     help="natural = the router as initialised; uniform = every expert gets B/K images; skew = all images to expert 0")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
@@ -161,6 +164,7 @@ def config_dict(args, world):
                         f"Swin-T stage features of a {args.img}^2 image ({'/'.join(map(str, token_counts(args.img)))} tokens), bf16",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "experts": args.experts, "topk": args.topk, "img": args.img,
             "loss": args.loss, "local_cotangent": bool(args.local_grad), "routing": args.routing,
+            "local_loss_words": args.words if args.local_loss else 0,
             "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": "inputs+intermediates per step (> 5 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -223,6 +227,11 @@ def main():
         "txt": torch.randn(B, D, generator=g).pin_memory(),
         "labels": torch.randint(0, K, (B,), generator=g).pin_memory(),
     }
+    local_mod, txt_local, cap_lens = None, None, None
+    if args.local_loss:     # synthetic word embeddings [B, 768, W] (the text tower is outside the path), full-length captions
+        local_mod = medmoe_b200.GLORIALocalContrastiveLoss(return_att_maps=False)
+        txt_local = (0.3 * torch.randn(B, D, args.words, generator=g)).to(dev)
+        cap_lens = [args.words] * B
     if args.routing != "natural":
         # routing balance variants: the router stays the real kernel, its weights / input are chosen so that the
         # arg-max is forced.  uniform: swin_feat carries a one-hot of (image index mod K) that the router passes through.
@@ -261,6 +270,9 @@ def main():
         else:
             g_loss = loss_mod(gf.float(), d["txt"], temp3=10.0)
         loss = 0.5 * g_loss + 2.0 * F.cross_entropy(probs, d["labels"])
+        if local_mod is not None:     # medmoe_module.py:220-233, 308: local_loss_weight * (loss0 + loss1)
+            l_out = local_mod(lf, txt_local, cap_lens)
+            loss = loss + 0.5 * (l_out.loss0 + l_out.loss1)
         if cot_local is not None:     # a dense synthetic cotangent for local_feat, handed straight to autograd (no glue kernels)
             torch.autograd.backward([loss, lf], [None, cot_local])
         else:

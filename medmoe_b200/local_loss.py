@@ -53,8 +53,31 @@ class GLORIALocalContrastiveLossOutput(OrderedDict):
     att_maps: List[Tensor]
 
 
+_TABLE_CACHE: dict = {}
+
+
+def _cap_len_tensor(lens, caps: int, dev) -> Tensor:
+    """int32 [caps] on the device, cached per length tuple: repeated steps (and CUDA graph capture) do no host-to-device copy."""
+    key = ("len", tuple(lens), caps, str(dev))
+    t = _TABLE_CACHE.get(key)
+    if t is None:
+        if len(_TABLE_CACHE) > 64:
+            _TABLE_CACHE.clear()
+        host = torch.zeros(caps, dtype=torch.int32)
+        host[:len(lens)] = torch.tensor(lens, dtype=torch.int32)
+        t = _TABLE_CACHE[key] = host.to(dev)
+    return t
+
+
 def _tables(B: int, tiles_per_image: int, dev):
-    """tile -> image table for the grouped row GEMMs, per-image and whole-range chunk lists for the wgrad GEMMs."""
+    """tile -> image table for the grouped row GEMMs, per-image and whole-range chunk lists for the wgrad GEMMs (cached)."""
+    key = ("tab", B, tiles_per_image, str(dev))
+    if key not in _TABLE_CACHE:
+        _TABLE_CACHE[key] = _build_tables(B, tiles_per_image, dev)
+    return _TABLE_CACHE[key]
+
+
+def _build_tables(B: int, tiles_per_image: int, dev):
     tiles = B * tiles_per_image
     t = torch.arange(tiles, dtype=torch.int32)
     tile_info = torch.stack([t // tiles_per_image, torch.full_like(t, 128)], dim=1).contiguous().to(dev)
@@ -97,9 +120,7 @@ class _LocalSimilarity(torch.autograd.Function):
         words32[:B, :Lc].copy_(words[:, :Lc])
         words32 = words32.view(N, D)
         words16 = words32.to(torch.bfloat16)
-        cap_len = torch.zeros(caps, dtype=torch.int32)
-        cap_len[:B] = torch.tensor(lens, dtype=torch.int32)
-        cap_len = cap_len.to(dev)
+        cap_len = _cap_len_tensor(lens, caps, dev)
         img_tiles, img_chunks, n_img_chunks, all_chunks, n_all_chunks = _tables(B, tpi, dev)
 
         # caption blocks: 16 captions at least, as many as keep the fp32 scores of a block under the budget
