@@ -175,7 +175,7 @@ class _LocalSimilarity(torch.autograd.Function):
         ld = ES.stride(0)
         # per-image weights of the d ctx GEMM: [dwcU_b^T | words^T], matching the [E | dS] columns of ES
         Wcat = torch.empty(B, D, 2 * N, dtype=torch.bfloat16, device=dev)
-        Wcat[:, :, N:] = words16.t()
+        Wcat[:, :, N:] = words16.t().contiguous()          # transpose the 12 MB once, then a row-contiguous broadcast
         for (c0, c1), wcU, cosv in zip(blocks, wcUs, coss):
             nc = c1 - c0
             Nb = nc * Wp
