@@ -164,7 +164,7 @@ def config_dict(args, world):
                         f"Swin-T stage features of a {args.img}^2 image ({'/'.join(map(str, token_counts(args.img)))} tokens), bf16",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "experts": args.experts, "topk": args.topk, "img": args.img,
             "loss": args.loss, "local_cotangent": bool(args.local_grad), "routing": args.routing,
-            "local_loss_words": args.words if args.local_loss else 0,
+            "local_loss_words": args.words if args.local_loss else 0,     # its word embeddings stay resident (not part of e2e H2D)
             "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": "inputs+intermediates per step (> 5 GB) exceed the 126 MB L2; no explicit flush"}
 
