@@ -47,6 +47,8 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
+constexpr int LL_ILP = 4;     // work items in flight per warp: the passes are bound by load latency, not by issue or bytes
+
 template <int G>
 __global__ void __launch_bounds__(256)
 ll_softmax_exp_fwd_kernel(const float* __restrict__ S, long long ld_s, __nv_bfloat16* __restrict__ E, long long ld_e,
@@ -57,27 +59,43 @@ ll_softmax_exp_fwd_kernel(const float* __restrict__ S, long long ld_s, __nv_bflo
     const unsigned gpr = (n_caps + CPW - 1) / CPW;
     const unsigned total = rows * gpr;
     const unsigned stride = gridDim.x * (blockDim.x >> 5);
-    for (unsigned t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += stride) {
-        const unsigned row = t / gpr;
-        const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
-        const bool on = cap < n_caps && w0 < Wp;
-        const int len = cap < n_caps ? min(__ldg(cap_len + cap), Wp) : 0;
-        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (on) v = *reinterpret_cast<const float4*>(S + static_cast<long long>(row) * ld_s + static_cast<long long>(cap) * Wp + w0);
-        const bool m0 = w0 < len, m1 = w0 + 1 < len, m2 = w0 + 2 < len, m3 = w0 + 3 < len;
-        float mx = fmaxf(fmaxf(m0 ? v.x : -INFINITY, m1 ? v.y : -INFINITY), fmaxf(m2 ? v.z : -INFINITY, m3 ? v.w : -INFINITY));
-        mx = group_max<G>(mx);
-        const float e0 = m0 ? __expf(v.x - mx) : 0.f, e1 = m1 ? __expf(v.y - mx) : 0.f;
-        const float e2 = m2 ? __expf(v.z - mx) : 0.f, e3 = m3 ? __expf(v.w - mx) : 0.f;
-        const float sum = group_sum<G>((e0 + e1) + (e2 + e3));
-        const float sc = len > 0 ? temp1 / sum : 0.f;
-        if (on) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(m0 ? __expf(e0 * sc) : 0.f, m1 ? __expf(e1 * sc) : 0.f);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(m2 ? __expf(e2 * sc) : 0.f, m3 ? __expf(e3 * sc) : 0.f);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(E + static_cast<long long>(row) * ld_e + static_cast<long long>(cap) * Wp + w0) = pk;
+    for (unsigned t0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t0 < total; t0 += LL_ILP * stride) {
+        float4 v[LL_ILP];
+        long long off[LL_ILP];
+        int len[LL_ILP];
+        bool on[LL_ILP];
+#pragma unroll
+        for (int u = 0; u < LL_ILP; ++u) {
+            const unsigned t = t0 + u * stride;
+            const unsigned row = t / gpr;
+            const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
+            on[u] = t < total && cap < n_caps && w0 < Wp;
+            len[u] = (t < total && cap < n_caps) ? min(__ldg(cap_len + cap), Wp) : 0;
+            off[u] = static_cast<long long>(cap) * Wp + w0;
+            v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (on[u]) v[u] = *reinterpret_cast<const float4*>(S + static_cast<long long>(row) * ld_s + off[u]);
+            off[u] += static_cast<long long>(row) * ld_e;
+        }
+#pragma unroll
+        for (int u = 0; u < LL_ILP; ++u) {
+            if (t0 + u * stride >= total) break;                 // warp-uniform
+            const int ln = len[u];
+            const bool m0 = w0 < ln, m1 = w0 + 1 < ln, m2 = w0 + 2 < ln, m3 = w0 + 3 < ln;
+            float mx = fmaxf(fmaxf(m0 ? v[u].x : -INFINITY, m1 ? v[u].y : -INFINITY),
+                             fmaxf(m2 ? v[u].z : -INFINITY, m3 ? v[u].w : -INFINITY));
+            mx = group_max<G>(mx);
+            const float e0 = m0 ? __expf(v[u].x - mx) : 0.f, e1 = m1 ? __expf(v[u].y - mx) : 0.f;
+            const float e2 = m2 ? __expf(v[u].z - mx) : 0.f, e3 = m3 ? __expf(v[u].w - mx) : 0.f;
+            const float sum = group_sum<G>((e0 + e1) + (e2 + e3));
+            const float sc = ln > 0 ? temp1 / sum : 0.f;
+            if (on[u]) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(m0 ? __expf(e0 * sc) : 0.f, m1 ? __expf(e1 * sc) : 0.f);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(m2 ? __expf(e2 * sc) : 0.f, m3 ? __expf(e3 * sc) : 0.f);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(E + off[u]) = pk;
+            }
         }
     }
 }
@@ -94,36 +112,49 @@ ll_softmax_exp_bwd_kernel(const __nv_bfloat16* __restrict__ E, long long ld_e, _
     const unsigned total = rows * gpr;
     const unsigned stride = gridDim.x * (blockDim.x >> 5);
     const float inv_t = 1.0f / temp1;
-    for (unsigned t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += stride) {
-        const unsigned row = t / gpr;
-        const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
-        const bool on = cap < n_caps && w0 < Wp;
-        const int len = cap < n_caps ? min(__ldg(cap_len + cap), Wp) : 0;
-        float a[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
-        __nv_bfloat16* dp = dE + static_cast<long long>(row) * ld_d + static_cast<long long>(cap) * Wp + w0;
-        if (on) {
-            const uint2 ev = *reinterpret_cast<const uint2*>(E + static_cast<long long>(row) * ld_e + static_cast<long long>(cap) * Wp + w0);
-            const uint2 dv = *reinterpret_cast<const uint2*>(dp);
-            const float ef[4] = {__uint_as_float(ev.x << 16), __uint_as_float(ev.x & 0xffff0000u),
-                                 __uint_as_float(ev.y << 16), __uint_as_float(ev.y & 0xffff0000u)};
-            const float df[4] = {__uint_as_float(dv.x << 16), __uint_as_float(dv.x & 0xffff0000u),
-                                 __uint_as_float(dv.y << 16), __uint_as_float(dv.y & 0xffff0000u)};
+    for (unsigned t0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t0 < total; t0 += LL_ILP * stride) {
+        uint2 ev[LL_ILP], dv[LL_ILP];
+        __nv_bfloat16* dp[LL_ILP];
+        int len[LL_ILP];
+        bool on[LL_ILP];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (w0 + k < len) {
-                    a[k] = __logf(ef[k]) * inv_t;
-                    g[k] = df[k] * temp1 * ef[k];
-                }
+        for (int u = 0; u < LL_ILP; ++u) {
+            const unsigned t = t0 + u * stride;
+            const unsigned row = t / gpr;
+            const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
+            on[u] = t < total && cap < n_caps && w0 < Wp;
+            len[u] = (t < total && cap < n_caps) ? min(__ldg(cap_len + cap), Wp) : 0;
+            const long long col = static_cast<long long>(cap) * Wp + w0;
+            dp[u] = dE + static_cast<long long>(row) * ld_d + col;
+            ev[u] = make_uint2(0u, 0u); dv[u] = make_uint2(0u, 0u);
+            if (on[u]) {
+                ev[u] = *reinterpret_cast<const uint2*>(E + static_cast<long long>(row) * ld_e + col);
+                dv[u] = *reinterpret_cast<const uint2*>(dp[u]);
             }
         }
-        const float dot = group_sum<G>((a[0] * g[0] + a[1] * g[1]) + (a[2] * g[2] + a[3] * g[3]));
-        if (on) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(a[0] * (g[0] - dot), a[1] * (g[1] - dot));
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(a[2] * (g[2] - dot), a[3] * (g[3] - dot));
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(dp) = pk;
+#pragma unroll
+        for (int u = 0; u < LL_ILP; ++u) {
+            if (t0 + u * stride >= total) break;                 // warp-uniform
+            const float ef[4] = {__uint_as_float(ev[u].x << 16), __uint_as_float(ev[u].x & 0xffff0000u),
+                                 __uint_as_float(ev[u].y << 16), __uint_as_float(ev[u].y & 0xffff0000u)};
+            const float df[4] = {__uint_as_float(dv[u].x << 16), __uint_as_float(dv[u].x & 0xffff0000u),
+                                 __uint_as_float(dv[u].y << 16), __uint_as_float(dv[u].y & 0xffff0000u)};
+            float a[4], g[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool m = on[u] && w0 + k < len[u];
+                a[k] = m ? __logf(ef[k]) * inv_t : 0.f;
+                g[k] = m ? df[k] * temp1 * ef[k] : 0.f;
+            }
+            const float dot = group_sum<G>((a[0] * g[0] + a[1] * g[1]) + (a[2] * g[2] + a[3] * g[3]));
+            if (on[u]) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(a[0] * (g[0] - dot), a[1] * (g[1] - dot));
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(a[2] * (g[2] - dot), a[3] * (g[3] - dot));
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dp[u]) = pk;
+            }
         }
     }
 }
