@@ -146,8 +146,15 @@ def contrastive_loss_with_temperature(
         raise RuntimeError("medmoe_b200 losses run on CUDA tensors only; there is no CPU fallback")
     B = embeddings_a.shape[0]
     if is_distributed():
-        all_a = all_gather_cat(embeddings_a, backprop_type)
-        all_b = all_gather_cat(embeddings_b, backprop_type)
+        if embeddings_a.shape == embeddings_b.shape and embeddings_a.dtype == embeddings_b.dtype:
+            # both embeddings travel in ONE all-gather (and one reduce-scatter in backward): the collectives of this loss are
+            # latency-bound (2 x 0.8 MB), so halving their number is what counts
+            D = embeddings_a.shape[1]
+            both = all_gather_cat(torch.cat([embeddings_a, embeddings_b], dim=1), backprop_type)
+            all_a, all_b = both[:, :D], both[:, D:]
+        else:
+            all_a = all_gather_cat(embeddings_a, backprop_type)
+            all_b = all_gather_cat(embeddings_b, backprop_type)
         label0 = B * get_rank()                                   # losses.py:515-518
     else:
         all_a, all_b, label0 = embeddings_a, embeddings_b, 0
