@@ -35,17 +35,20 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
 #pragma unroll
         for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < a.K; k0 += 16) {
+    // split-K: blockIdx.z takes one contiguous k range; partial results are added to a pre-zeroed C (run_sgemm)
+    const int kc = ((a.K + 15) / 16 + gridDim.z - 1) / gridDim.z * 16;
+    const int k_begin = blockIdx.z * kc, k_end = min(a.K, k_begin + kc);
+    for (int k0 = k_begin; k0 < k_end; k0 += 16) {
 #pragma unroll
         for (int j = 0; j < T; ++j) {
             int m, k;
             if (a.sak == 1) { k = t & 15; m = (t >> 4) + 16 * j; } else { m = t % TILE; k = t / TILE + (256 / TILE) * j; }
             const int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < a.M && gk < a.K) ? a.A[gm * a.sam + gk * a.sak] : 0.f;
+            As[k][m] = (gm < a.M && gk < k_end) ? a.A[gm * a.sam + gk * a.sak] : 0.f;
             int n, kb;
             if (a.sbk == 1) { kb = t & 15; n = (t >> 4) + 16 * j; } else { n = t % TILE; kb = t / TILE + (256 / TILE) * j; }
             const int gn = n0 + n, gkb = k0 + kb;
-            Bs[kb][n] = (gn < a.N && gkb < a.K) ? a.B[gkb * a.sbk + gn * a.sbn] : 0.f;
+            Bs[kb][n] = (gn < a.N && gkb < k_end) ? a.B[gkb * a.sbk + gn * a.sbn] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -72,8 +75,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs a) {
             float v = acc[i][j];
             if (a.na) v = v / fmaxf(a.na[m] * a.nb[n], a.eps);
             v *= alpha;
-            if (a.rs) v = fmaf(a.rs[m], a.X[m * a.ldx + n], v);
-            a.C[m * a.ldc + n] = v;
+            if (a.rs && blockIdx.z == 0) v = fmaf(a.rs[m], a.X[m * a.ldx + n], v);
+            if (gridDim.z == 1) a.C[m * a.ldc + n] = v;
+            else atomicAdd(a.C + m * a.ldc + n, v);
         }
     }
 }
@@ -264,10 +268,22 @@ zeroshot_kernel(const float* __restrict__ I, const float* __restrict__ T, int M,
 int run_sgemm(const SgemmArgs& a, cudaStream_t st, const char* what) {
     if (a.M <= 0 || a.N <= 0) return MM_OK;
     const int blocks64 = ((a.N + 63) / 64) * ((a.M + 63) / 64);
-    if (blocks64 >= 96) {
-        sgemm_kernel<4><<<dim3((a.N + 63) / 64, (a.M + 63) / 64), 256, 0, st>>>(a);
-    } else {      // small problem: quarter-size tiles put four times as many SMs to work
-        sgemm_kernel<2><<<dim3((a.N + 31) / 32, (a.M + 31) / 32), 256, 0, st>>>(a);
+    const bool big = blocks64 >= 96;      // small problem: quarter-size tiles put four times as many SMs to work
+    const int blocks = big ? blocks64 : ((a.N + 31) / 32) * ((a.M + 31) / 32);
+    // these GEMMs have few output tiles and a long K (logits of a 256-row batch): split K until two waves of CTAs exist
+    int splits = (2 * mm::sm_count() + blocks - 1) / blocks;
+    splits = splits < 1 ? 1 : (splits > a.K / 128 ? (a.K / 128 > 0 ? a.K / 128 : 1) : splits);
+    if (splits > 8) splits = 8;
+    if (splits > 1 && (a.X == a.C)) splits = 1;          // in-place residual: the partial sums would race with the reads of X
+    if (splits > 1) {
+        cudaError_t e = cudaMemset2DAsync(a.C, static_cast<size_t>(a.ldc) * sizeof(float), 0, static_cast<size_t>(a.N) * sizeof(float),
+                                          static_cast<size_t>(a.M), st);
+        if (e != cudaSuccess) { mm::set_error("%s: cudaMemset2DAsync failed (%s)", what, cudaGetErrorString(e)); return MM_ERR_CUDA; }
+    }
+    if (big) {
+        sgemm_kernel<4><<<dim3((a.N + 63) / 64, (a.M + 63) / 64, splits), 256, 0, st>>>(a);
+    } else {
+        sgemm_kernel<2><<<dim3((a.N + 31) / 32, (a.M + 31) / 32, splits), 256, 0, st>>>(a);
     }
     mm::note_launches(1);
     return check_launch(what);
