@@ -265,13 +265,16 @@ zeroshot_kernel(const float* __restrict__ I, const float* __restrict__ T, int M,
     if (lane == 0) pred[m] = best_c;
 }
 
+#ifndef MM_SGEMM_WAVES
+#define MM_SGEMM_WAVES 2
+#endif
 int run_sgemm(const SgemmArgs& a, cudaStream_t st, const char* what) {
     if (a.M <= 0 || a.N <= 0) return MM_OK;
     const int blocks64 = ((a.N + 63) / 64) * ((a.M + 63) / 64);
     const bool big = blocks64 >= 96;      // small problem: quarter-size tiles put four times as many SMs to work
     const int blocks = big ? blocks64 : ((a.N + 31) / 32) * ((a.M + 31) / 32);
     // these GEMMs have few output tiles and a long K (logits of a 256-row batch): split K until two waves of CTAs exist
-    int splits = (2 * mm::sm_count() + blocks - 1) / blocks;
+    int splits = (MM_SGEMM_WAVES * mm::sm_count() + blocks - 1) / blocks;
     splits = splits < 1 ? 1 : (splits > a.K / 128 ? (a.K / 128 > 0 ? a.K / 128 : 1) : splits);
     if (splits > 8) splits = 8;
     if (splits > 1 && (a.X == a.C)) splits = 1;          // in-place residual: the partial sums would race with the reads of X
