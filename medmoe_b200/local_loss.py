@@ -16,7 +16,8 @@ streaming passes (csrc/local_loss.cu):
 
 The softmax over patches is `E / colsum(E)`; the cosine that consumes the attended context is scale free, so the column sums
 are never formed (they only matter for the returned attention maps, which are computed for the B matching pairs alone).
-Captions are processed in column blocks so that the fp32 score matrix of a block stays below `SCORE_BYTES_BUDGET`.
+Captions may have up to 128 words (the reference tokenises to max_length 25, configs/model/med-moe.yaml:40; up to 32 words take
+the fused score-softmax epilogue).  Captions are processed in column blocks so that the fp32 score matrix of a block stays below `SCORE_BYTES_BUDGET`.
 The two cross-entropies over the B x B similarity matrix are ordinary torch ops (65 k elements).
 """
 from __future__ import annotations
