@@ -93,3 +93,31 @@ def test_fused_score_softmax_epilogue_agrees_with_the_two_pass_path(monkeypatch)
     assert rel_err(outs[0][0], outs[1][0]) < 1e-4
     assert rel_err(outs[0][1], outs[1][1]) < 2e-3
     assert rel_err(outs[0][2], outs[1][2]) < 2e-3
+
+
+@pytest.mark.parametrize("B,D,H,L,lens", [(1, 128, 3, 4, [4]), (2, 256, 7, 40, [1, 40]), (5, 768, 4, 128, [128, 3, 64, 65, 96])])
+def test_local_loss_edge_shapes_vs_oracle(B, D, H, L, lens):
+    """A single pair, one-word captions, the longest supported captions (128 words: four lanes groups), bf16 inputs."""
+    g = torch.Generator().manual_seed(100 + B)
+    img = (torch.randn(B, D, H, H, generator=g) * 0.3).to(torch.bfloat16)
+    words = (torch.randn(B, D, L, generator=g) * 0.3).to(torch.bfloat16)
+    ri, rw = img.float().requires_grad_(True), words.float().requires_grad_(True)
+    l0, l1, _ = lo.gloria_local_loss(ri, rw, lens, agg="mean")
+    (l0 + l1).backward()
+    di, dw = img.cuda().requires_grad_(True), words.cuda().requires_grad_(True)
+    out = GLORIALocalContrastiveLoss()(di, dw, lens, agg="mean")
+    (out.loss0 + out.loss1).backward()
+    assert di.grad.dtype == torch.bfloat16 and dw.grad.dtype == torch.bfloat16
+    assert abs(out.loss0.item() - l0.item()) < 5e-3 * max(1.0, abs(l0.item()))
+    assert abs(out.loss1.item() - l1.item()) < 5e-3 * max(1.0, abs(l1.item()))
+    if B > 1:      # B = 1: both cross-entropies are identically zero, and so are the gradients
+        assert rel_err(di.grad.float().cpu(), ri.grad) < 3e-2
+        assert rel_err(dw.grad.float().cpu(), rw.grad) < 3e-2
+    assert [m.shape[1] for m in out.att_maps] == lens
+
+
+def test_local_loss_rejects_captions_longer_than_128_words():
+    img = torch.randn(2, 128, 4, 4, device="cuda")
+    words = torch.randn(2, 128, 130, device="cuda")
+    with pytest.raises(RuntimeError, match="128"):
+        GLORIALocalContrastiveLoss()(img, words, [130, 5])
