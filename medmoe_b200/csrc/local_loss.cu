@@ -159,6 +159,72 @@ ll_softmax_exp_bwd_kernel(const __nv_bfloat16* __restrict__ E, long long ld_e, _
     }
 }
 
+// Forward pass with eight words per lane (two 16-byte loads of S, one 16-byte store of E): captions that are not a power of two
+// long waste fewer lanes (80 word slots: 10 of 16 lanes instead of 20 of 32) and the instruction count per byte halves.
+template <int G>
+__global__ void __launch_bounds__(256)
+ll_softmax_exp_fwd8_kernel(const float* __restrict__ S, long long ld_s, __nv_bfloat16* __restrict__ E, long long ld_e,
+                           unsigned rows, int n_caps, int Wp, const int* __restrict__ cap_len, float temp1) {
+    constexpr int CPW = 32 / G;
+    constexpr int ILP = 2;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, w0 = (lane % G) * 8;
+    const unsigned gpr = (n_caps + CPW - 1) / CPW;
+    const unsigned total = rows * gpr;
+    const unsigned stride = gridDim.x * (blockDim.x >> 5);
+    for (unsigned t0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t0 < total; t0 += ILP * stride) {
+        float v[ILP][8];
+        long long off[ILP];
+        int len[ILP];
+        bool on[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const unsigned t = t0 + u * stride;
+            const unsigned row = t / gpr;
+            const int cap = static_cast<int>(t - row * gpr) * CPW + sub;
+            on[u] = t < total && cap < n_caps && w0 < Wp;
+            len[u] = (t < total && cap < n_caps) ? min(__ldg(cap_len + cap), Wp) : 0;
+            off[u] = static_cast<long long>(cap) * Wp + w0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = -INFINITY;
+            if (on[u]) {
+                const float4* sp = reinterpret_cast<const float4*>(S + static_cast<long long>(row) * ld_s + off[u]);
+                const float4 lo = sp[0], hi = sp[1];
+                v[u][0] = lo.x; v[u][1] = lo.y; v[u][2] = lo.z; v[u][3] = lo.w;
+                v[u][4] = hi.x; v[u][5] = hi.y; v[u][6] = hi.z; v[u][7] = hi.w;
+            }
+            off[u] += static_cast<long long>(row) * ld_e;
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            if (t0 + u * stride >= total) break;                 // warp-uniform
+            const int ln = len[u];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx = fmaxf(mx, (w0 + k < ln) ? v[u][k] : -INFINITY);
+            mx = group_max<G>(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                v[u][k] = (w0 + k < ln) ? __expf(v[u][k] - mx) : 0.f;
+                sum += v[u][k];
+            }
+            sum = group_sum<G>(sum);
+            const float sc = ln > 0 ? temp1 / sum : 0.f;
+            if (on[u]) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 p = __floats2bfloat162_rn((w0 + 2 * k < ln) ? __expf(v[u][2 * k] * sc) : 0.f,
+                                                                   (w0 + 2 * k + 1 < ln) ? __expf(v[u][2 * k + 1] * sc) : 0.f);
+                    o[k] = *reinterpret_cast<const uint32_t*>(&p);
+                }
+                *reinterpret_cast<uint4*>(E + off[u]) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
 // Same pass with eight words per lane (one 16-byte load of E and of dE): half the instructions per byte of the 4-word version.
 template <int G>
 __global__ void __launch_bounds__(256)
@@ -362,6 +428,15 @@ extern "C" int mm_local_softmax_exp_fwd(const float* S, long long ld_s, void* E,
     __nv_bfloat16* Eb = static_cast<__nv_bfloat16*>(E);
     const unsigned grid = 148 * 16, r = static_cast<unsigned>(rows);
     const int lanes = (Wp + 3) / 4;
+    const bool vec8 = ld_s % 8 == 0 && ld_e % 8 == 0 && (reinterpret_cast<uintptr_t>(S) & 31) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0;
+    if (vec8) {      // Wp is a multiple of 8: every caption starts on a 32-byte (S) / 16-byte (E) boundary
+        const int l8 = Wp / 8;
+        if (l8 <= 1) ll_softmax_exp_fwd8_kernel<1><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+        else if (l8 <= 2) ll_softmax_exp_fwd8_kernel<2><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+        else if (l8 <= 4) ll_softmax_exp_fwd8_kernel<4><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+        else if (l8 <= 8) ll_softmax_exp_fwd8_kernel<8><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+        else ll_softmax_exp_fwd8_kernel<16><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
+    } else
     if (lanes <= 2) ll_softmax_exp_fwd_kernel<2><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
     else if (lanes <= 4) ll_softmax_exp_fwd_kernel<4><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
     else if (lanes <= 8) ll_softmax_exp_fwd_kernel<8><<<grid, 256, 0, st>>>(S, ld_s, Eb, ld_e, r, n_caps, Wp, cap_len, temp1);
