@@ -2,7 +2,7 @@
 
     python tools/local_loss_bench.py [--batch 256] [--words 25] [--img 224] [--steps 3] [--torch-batch 32]
 
-Also times the reference's algorithm as stock PyTorch ops on the same GPU (oracle restatement of losses.py:954-1026: a
+Also times the reference's algorithm as stock PyTorch ops on the same GPU (losses.py:954-1026 restated in this file: a
 Python loop over captions, fp32 bmm + softmax) at --torch-batch (its activations do not fit at 256) for a scale-free
 comparison in pairs^2 per second.  Prints one JSON line.
 """
@@ -69,7 +69,26 @@ res = {"metric": "local loss fwd+bwd", "batch": B, "words": L, "tokens": H * H, 
        "kernel_ms_sum": round(sum(v["ms"] for v in kern.values()), 2), "kernels": kern}
 
 if args.torch_batch > 0:
-    from oracle import local_loss_oracle as lo       # the reference algorithm as stock torch ops (baseline leg only)
+    import torch.nn.functional as F
+
+    def reference_algorithm(img, wrd, lens, temp1=4.0, temp2=5.0, temp3=10.0, eps=1e-8):
+        """The reference's own schedule as stock torch ops (losses.py:954-1026, attention_fn :698-736): a Python loop over the
+        captions, each repeated over the batch, two bmm + two softmax per caption.  Baseline leg of this tool only."""
+        Bn, Dn = img.shape[:2]
+        context = img.reshape(Bn, Dn, -1)
+        cols = []
+        for i in range(Bn):
+            n = lens[i]
+            word = wrd[i, :, :n].unsqueeze(0).repeat(Bn, 1, 1)
+            attn = torch.softmax(torch.bmm(context.transpose(1, 2), word), dim=-1).transpose(1, 2)
+            attn = torch.softmax(attn * temp1, dim=-1)
+            wc = torch.bmm(context, attn.transpose(1, 2))
+            cos = (word * wc).sum(1) / (word.norm(dim=1) * wc.norm(dim=1)).clamp(min=eps)
+            cols.append(torch.log(torch.exp(temp2 * cos).sum(1, keepdim=True)))
+        sim = torch.cat(cols, 1) * temp3
+        labels = torch.arange(Bn, device=sim.device)
+        return F.cross_entropy(sim, labels), F.cross_entropy(sim.t(), labels)
+
     tb = args.torch_batch
     xi = local[:tb].float().contiguous()
     wi = words[:tb].contiguous()
@@ -77,7 +96,7 @@ if args.torch_batch > 0:
     def torch_step():
         x = xi.detach().requires_grad_(True)
         w = wi.detach().requires_grad_(True)
-        l0, l1, _ = lo.gloria_local_loss(x, w, cap_lens[:tb])
+        l0, l1 = reference_algorithm(x, w, cap_lens[:tb])
         (l0 + l1).backward()
 
     torch_step()
