@@ -335,7 +335,7 @@ ll_cos_lse_bwd_kernel(const float* __restrict__ dsim, long long ld_dsim, const f
                       __nv_bfloat16* __restrict__ dwcU, __nv_bfloat16* __restrict__ dwcUT, long long ld_t,
                       float* __restrict__ dwords) {
     constexpr int D = DPL * 32;
-    __shared__ __align__(16) __nv_bfloat16 tile[D][LL_BWD_WARPS];      // [d][n - n0]
+    __shared__ __align__(16) __nv_bfloat16 tile[LL_BWD_WARPS][D];      // [n - n0][d]: a warp's stores are contiguous (no bank conflicts)
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long N = static_cast<long long>(n_caps) * Wp;
     const long long n0 = static_cast<long long>(blockIdx.x) * LL_BWD_WARPS;
@@ -393,14 +393,18 @@ ll_cos_lse_bwd_kernel(const float* __restrict__ dsim, long long ld_dsim, const f
         for (int k = 0; k < DPL; ++k) {
             const __nv_bfloat16 v = __float2bfloat16(o[k]);
             out[lane + 32 * k] = v;
-            tile[lane + 32 * k][wib] = v;
+            tile[wib][lane + 32 * k] = v;
         }
         __syncthreads();
-        for (int d = threadIdx.x; d < D; d += LL_BWD_WARPS * 32) {
-            const uint4* src = reinterpret_cast<const uint4*>(&tile[d][0]);
+        for (int d = threadIdx.x; d < D; d += LL_BWD_WARPS * 32) {     // column d of the tile -> 32 contiguous bytes of row (b, d)
+            uint32_t w[LL_BWD_WARPS / 2];
+#pragma unroll
+            for (int j = 0; j < LL_BWD_WARPS / 2; ++j)
+                w[j] = static_cast<uint32_t>(__bfloat16_as_ushort(tile[2 * j][d])) |
+                       (static_cast<uint32_t>(__bfloat16_as_ushort(tile[2 * j + 1][d])) << 16);
             uint4* dst = reinterpret_cast<uint4*>(dwcUT + (static_cast<long long>(b) * D + d) * ld_t + n0);
-            dst[0] = src[0];
-            dst[1] = src[1];
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
         __syncthreads();
     }
