@@ -72,3 +72,28 @@ def test_tensor_core_path_geometry_predicates():
     assert not sup("mm_combine_bwd_tc_supported", [96, 24, 6, 3])             # ratio 32 at the coarsest scale but P % 64 != 0
     assert sup("mm_combine_bwd_global_supported", [96, 24, 6, 3])             # the rank-1 path only needs even integer ratios
     assert not sup("mm_combine_bwd_tc_supported", swin224, D=640)             # output_dim must be one of 256/512/768/1024
+
+
+def test_local_loss_tables_cover_every_tile_once():
+    """Host tables of the word-patch attention loss: images as 'experts' of the grouped GEMMs (medmoe_b200/local_loss.py)."""
+    import torch
+    from medmoe_b200 import local_loss as ll
+    for B, tpi in [(1, 1), (5, 25), (3, 72), (37, 2)]:
+        img_tiles, img_chunks, n_img, all_chunks, n_all = ll._build_tables(B, tpi, torch.device("cpu"))
+        ti = img_tiles.tile_info
+        assert ti.shape == (B * tpi, 2) and ti.dtype == torch.int32
+        assert ti[:, 0].tolist() == [t // tpi for t in range(B * tpi)] and (ti[:, 1] == 128).all()
+        for chunks, n, per_image in ((img_chunks.chunks, n_img, True), (all_chunks.chunks, n_all, False)):
+            assert chunks.shape == (n, 4)
+            seen = []
+            for e, first, cnt, _ in chunks.tolist():
+                assert 0 < cnt <= 64
+                tiles = list(range(first, first + cnt))
+                if per_image:
+                    assert all(t // tpi == e for t in tiles)          # a chunk never straddles two images
+                else:
+                    assert e == 0
+                seen += tiles
+            assert sorted(seen) == list(range(B * tpi))
+    lens = ll._cap_len_tensor([3, 9, 1], 16, torch.device("cpu"))
+    assert lens.tolist() == [3, 9, 1] + [0] * 13 and lens.dtype == torch.int32
