@@ -50,10 +50,12 @@ int mm_trace_collect(char* buf, int len);
  * replaces src/models/components/swin.py:98-100 (router MLP, softmax, argmax).
  * x [B, D] fp32; W1 [128, D], b1 [128], W2 [K, 128], b2 [K] fp32.
  * out: hidden [B, 128] (post-ReLU, saved for backward), probs [B, K], topk_idx [B, topk] int32
- * (first maximum wins, as torch.argmax), topk_w [B, topk] (1.0 when topk == 1, else the
- * selected probs renormalised to sum 1). */
+ * (first maximum wins and NaN counts as the maximum, as torch.argmax), topk_w [B, topk] (1.0 when topk == 1,
+ * else the selected probs renormalised to sum 1); near_tie [B] int32 (may be NULL): 1 where the gap between the
+ * last selected probability and the best one left out is below tie_tol (the north star's "near-tie" report). */
 int mm_router_topk(const float* x, int B, int D, const float* W1, const float* b1, const float* W2, const float* b2,
-                   int K, int topk, float* hidden, float* probs, int32_t* topk_idx, float* topk_w, void* stream);
+                   int K, int topk, float* hidden, float* probs, int32_t* topk_idx, float* topk_w, int32_t* near_tie,
+                   float tie_tol, void* stream);
 
 /* gradient of the returned probabilities (the only gradient path into the router:
  * src/models/medmoe_module.py:235-237 applies cross-entropy to them).

@@ -23,7 +23,8 @@ SIGNATURES = {
     "mm_launch_count": (c_ll, []),
     "mm_trace_enable": (None, [c_int]),
     "mm_trace_collect": (c_int, [C.c_char_p, c_int]),
-    "mm_router_topk": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mm_router_topk": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                               c_f, c_vp]),
     "mm_router_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp]),
     "mm_dispatch_build": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -150,7 +150,8 @@ static int launch_rows(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t
     using S = GemmSmem<BN, STAGES, AUX, EW>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_rows_kernel<BN, STAGES, OUT_F32, AUX, EW>;
-    static bool configured = false;   // benign race: attribute set is idempotent
+    static bool configured_dev[64];   // per device (the attribute is per device); benign race: the set is idempotent
+    bool& configured = *per_device_flag(configured_dev);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) {
@@ -174,7 +175,8 @@ static int launch_wgrad(const CUtensorMap& tA, const CUtensorMap& tB, const Wgra
     constexpr int SMEM = S::WGRAD_TOTAL + (COLSUM ? STAGES * 8192 : 0);
     static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_wgrad_kernel<BN, STAGES, COLSUM>;
-    static bool configured = false;
+    static bool configured_dev[64];
+    bool& configured = *per_device_flag(configured_dev);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) {
@@ -199,7 +201,8 @@ static int launch_rows_pair(const RowsMaps& m, const RowsGemmArgs& args, cudaStr
     using S = PairSmem<BN, STAGES, EW>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_rows_pair_kernel<BN, STAGES, EW>;
-    static bool configured = false;
+    static bool configured_dev[64];
+    bool& configured = *per_device_flag(configured_dev);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) {

@@ -18,6 +18,12 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 int encode_tmap_bf16_swz(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride,
                          uint32_t box_inner, uint32_t box_rows, int swizzle_bytes, const char* what);
 int sm_count();
+// slot of the current device in a per-kernel `static bool[64]`: cudaFuncSetAttribute opt-ins are per device
+static inline bool* per_device_flag(bool* flags) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return &flags[dev];
+}
 // number of kernels launched through the C-ABI since load (bench.py's gpu_launches evidence)
 void note_launches(int n);
 // optional per-kernel timing inside composite entry points: one CUDA event per mark; the time between two

@@ -46,7 +46,10 @@ dispatch_build_kernel(const int* __restrict__ item_expert, DispatchPlanArgs a, i
 
     if (tid < MAX_EXPERTS) { s_cnt[tid] = 0; s_run[tid] = 0; }
     __syncthreads();
-    for (int i = tid; i < a.n_items; i += blockDim.x) atomicAdd(&s_cnt[item_expert[i]], 1);
+    // expert ids outside [0, K) (a caller's bug, or garbage from a faulted producer) are routed to expert 0 instead of
+    // indexing shared memory out of bounds: every item then still owns a slot, so no consumer reads unwritten tables
+    auto expert_of = [&](int i) { const int e = item_expert[i]; return (static_cast<unsigned>(e) < static_cast<unsigned>(K)) ? e : 0; };
+    for (int i = tid; i < a.n_items; i += blockDim.x) atomicAdd(&s_cnt[expert_of(i)], 1);
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -71,7 +74,7 @@ dispatch_build_kernel(const int* __restrict__ item_expert, DispatchPlanArgs a, i
         for (int i = tid; i < 32 * MAX_EXPERTS; i += blockDim.x) (&s_wcnt[0][0])[i] = 0;
         __syncthreads();
         const int item = base + tid;
-        const int e = item < a.n_items ? item_expert[item] : -1 - lane;   // distinct dummy keys
+        const int e = item < a.n_items ? expert_of(item) : -1 - lane;   // distinct dummy keys
         const unsigned peers = __match_any_sync(0xffffffffu, e);
         const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
         if (e >= 0 && rank_in_warp == 0) s_wcnt[warp][e] = __popc(peers);

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(ROUTER_FWD_THREADS)
 router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ W1, const float* __restrict__ b1,
                   const float* __restrict__ W2, const float* __restrict__ b2, int K, int topk,
                   float* __restrict__ hidden, float* __restrict__ probs, int* __restrict__ topk_idx,
-                  float* __restrict__ topk_w) {
+                  float* __restrict__ topk_w, int* __restrict__ near_tie, float tie_tol) {
     extern __shared__ float sm[];
     float* sx = sm;                 // [D]
     float* sh = sm + D;             // [128]
@@ -73,17 +73,31 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
             sl[e] *= inv;
             probs[static_cast<size_t>(b) * K + e] = sl[e];
         }
-        // top-k by repeated first-max selection (k is 1 or 2 in every configuration)
+        // top-k by repeated first-max selection (k is 1 or 2 in every configuration).  NaN counts as the maximum and the
+        // first one wins, exactly like torch.argmax / torch.topk: a NaN / Inf in swin_feat makes every probability NaN,
+        // the image goes to expert 0 and the NaN propagates to the outputs and the loss as in the reference (swin.py:99-100)
+        // instead of leaving the selection empty.
         unsigned long long taken = 0ull;
         float wsum = 0.f;
         for (int j = 0; j < topk; ++j) {
-            int best = -1; float bv = -1.f;
-            for (int e = 0; e < K; ++e)
-                if (!((taken >> e) & 1ull) && sl[e] > bv) { bv = sl[e]; best = e; }
+            int best = -1; float bv = 0.f;
+            for (int e = 0; e < K; ++e) {
+                if ((taken >> e) & 1ull) continue;
+                const float v = sl[e];
+                if (best < 0 || v > bv || (v != v && bv == bv)) { bv = v; best = e; }
+            }
             taken |= 1ull << best;
             topk_idx[static_cast<size_t>(b) * topk + j] = best;
             topk_w[static_cast<size_t>(b) * topk + j] = bv;
             wsum += bv;
+        }
+        if (near_tie) {
+            // near-tie report (north star: "near-tie logits documented"): the gap between the last selected probability and
+            // the best one left out; below tie_tol a bf16 / reordered evaluation of the router could pick another expert.
+            float last = topk_w[static_cast<size_t>(b) * topk + topk - 1], runner = -1.f;
+            for (int e = 0; e < K; ++e)
+                if (!((taken >> e) & 1ull) && sl[e] > runner) runner = sl[e];
+            near_tie[b] = (K > topk && !(last - runner >= tie_tol)) ? 1 : 0;
         }
         for (int j = 0; j < topk; ++j)
             topk_w[static_cast<size_t>(b) * topk + j] = (topk == 1) ? 1.0f : topk_w[static_cast<size_t>(b) * topk + j] / wsum;
@@ -143,13 +157,13 @@ using namespace mm;
 
 extern "C" int mm_router_topk(const float* x, int B, int D, const float* W1, const float* b1, const float* W2,
                               const float* b2, int K, int topk, float* hidden, float* probs, int32_t* topk_idx,
-                              float* topk_w, void* stream) {
+                              float* topk_w, int32_t* near_tie, float tie_tol, void* stream) {
     MM_REQUIRE(B >= 0 && D > 0 && K > 0 && K <= ROUTER_MAX_K && topk >= 1 && topk <= K, MM_ERR_BAD_SHAPE,
                "mm_router_topk: need 0 < K <= 64, 1 <= topk <= K");
     if (B == 0) return MM_OK;
     const size_t smem = (static_cast<size_t>(D) + ROUTER_HID + K) * sizeof(float);
     router_fwd_kernel<<<B, ROUTER_FWD_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, D, W1, b1, W2, b2, K, topk, hidden,
-                                                                          probs, topk_idx, topk_w);
+                                                                          probs, topk_idx, topk_w, near_tie, tie_tol);
     mm::note_launches(1);
     return mm_check_launch("mm_router_topk");
 }

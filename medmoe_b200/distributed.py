@@ -54,12 +54,13 @@ class _AllGatherCat(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         rank = dist.get_rank()
         grad_in = torch.empty((ctx.rows,) + tuple(grad_out.shape[1:]), dtype=grad_out.dtype, device=grad_out.device)
-        try:
-            dist.reduce_scatter_tensor(grad_in, grad_out, op=dist.ReduceOp.SUM)
-        except (RuntimeError, NotImplementedError):
-            # gloo: no reduce-scatter; all-reduce then take the local slice (same sum)
+        if dist.get_backend() == "gloo":
+            # gloo has no reduce-scatter: all-reduce then take the local slice (same sum).  The path is chosen from the
+            # backend up front, so a failing NCCL collective raises instead of silently diverging from its peers.
             dist.all_reduce(grad_out, op=dist.ReduceOp.SUM)
             grad_in = grad_out[rank * ctx.rows:(rank + 1) * ctx.rows].clone()
+        else:
+            dist.reduce_scatter_tensor(grad_in, grad_out, op=dist.ReduceOp.SUM)
         return grad_in
 
 

@@ -125,7 +125,7 @@ class _ExpertsFunction(torch.autograd.Function):
         ctx.param_needs_grad = any(p.requires_grad for p in params)
         ctx.gate_needs_grad = gate is not None and gate.requires_grad
         ctx.set_materialize_grads(False)
-        return fused, gfeat.to(in_dtype)
+        return fused, gfeat      # global_feat stays fp32 (the token mean is accumulated in fp32; only local_feat follows the input dtype)
 
     @staticmethod
     def backward(ctx, dfused, dglobal):
@@ -220,16 +220,16 @@ class _RouterFunction(torch.autograd.Function):
     def forward(ctx, x, W1, b1, W2, b2, topk):
         x32 = x.float().contiguous()
         W1c, b1c, W2c, b2c = (t.float().contiguous() for t in (W1, b1, W2, b2))
-        hidden, probs, idx, w = ops.router_topk(x32, W1c, b1c, W2c, b2c, topk)
+        hidden, probs, idx, w, near_tie = ops.router_topk(x32, W1c, b1c, W2c, b2c, topk)
         ctx.save_for_backward(x32, W1c, W2c, hidden, probs)
         ctx.x_dtype = x.dtype
         ctx.need_dx = x.requires_grad
-        ctx.mark_non_differentiable(idx, w)
+        ctx.mark_non_differentiable(idx, w, near_tie)
         ctx.set_materialize_grads(False)
-        return probs, idx, w
+        return probs, idx, w, near_tie
 
     @staticmethod
-    def backward(ctx, dprobs, _didx, _dw):
+    def backward(ctx, dprobs, _didx, _dw, _dnt):
         if dprobs is None:
             return (None,) * 6
         x32, W1c, W2c, hidden, probs = ctx.saved_tensors
@@ -250,6 +250,13 @@ class MoE(nn.Module):
         )
         self.topk = int(topk)
         self.last_top_expert = None   # int32 [B, topk] of the most recent forward (device tensor, no sync)
+        self.last_near_tie = None     # int32 [B]: 1 where the routing margin was < ops.NEAR_TIE_TOL (device tensor, no sync)
+
+    def near_tie_count(self) -> int:
+        """Images of the most recent forward whose expert choice hangs on a probability gap < 1e-6 (synchronises).
+        The reference takes `argmax` of fp32 probabilities (swin.py:99-100); the router here is fp32 too, so the
+        assignment is identical unless an image is flagged here (documented near-ties)."""
+        return 0 if self.last_near_tie is None else int(self.last_near_tie.sum().item())
 
     def forward(self, multi_scale_feats, swin_feat):
         """multi_scale_feats: list of 4 tensors [B, P_s, D_s] (finest first); swin_feat [B, router_input_dim].
@@ -260,15 +267,16 @@ class MoE(nn.Module):
         if any(f.dtype != feats[0].dtype for f in feats):
             # autocast hands over a mix (fp32 from LayerNorm, bf16 from Linear): the kernels compute in bf16 anyway
             feats = [f.to(torch.bfloat16) for f in feats]
-        probs, idx, w = _RouterFunction.apply(swin_feat, self.router[0].weight, self.router[0].bias,
-                                              self.router[2].weight, self.router[2].bias, self.topk)
-        self.last_top_expert = idx
-        gate = None
-        if self.topk > 1:
-            # extension: renormalised top-k probabilities, differentiable w.r.t. the router (tiny torch ops)
-            sel = probs.gather(1, idx.long())
-            gate = sel / sel.sum(dim=1, keepdim=True)
-        fused, global_feat = _run_experts(list(self.experts), feats, idx, gate, self.topk)
+        with torch.cuda.device(feats[0].device):     # the C-ABI launches on the current device's stream
+            probs, idx, w, near_tie = _RouterFunction.apply(swin_feat, self.router[0].weight, self.router[0].bias,
+                                                            self.router[2].weight, self.router[2].bias, self.topk)
+            self.last_top_expert, self.last_near_tie = idx, near_tie
+            gate = None
+            if self.topk > 1:
+                # extension: renormalised top-k probabilities, differentiable w.r.t. the router (tiny torch ops)
+                sel = probs.gather(1, idx.long())
+                gate = sel / sel.sum(dim=1, keepdim=True)
+            fused, global_feat = _run_experts(list(self.experts), feats, idx, gate, self.topk)
         B, P, D = fused.shape
         Hh = Ww = int(P ** 0.5)                                       # swin.py:111
         local_feat = fused.transpose(1, 2).reshape(B, D, Hh, Ww)      # a stride view, as in the reference

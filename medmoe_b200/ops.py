@@ -66,7 +66,11 @@ def run_scales(fns):
 
 
 # ---- router ---------------------------------------------------------------------------
+NEAR_TIE_TOL = 1e-6    # report |p1 - p2| < 1e-6
+
+
 def router_topk(x, W1, b1, W2, b2, topk: int):
+    """-> (hidden, probs, idx, w, near_tie): near_tie [B] int32 flags the images whose selection margin is < NEAR_TIE_TOL."""
     _need_cuda(x, W1, b1, W2, b2)
     B, D = x.shape
     K = W2.shape[0]
@@ -75,9 +79,10 @@ def router_topk(x, W1, b1, W2, b2, topk: int):
     probs = torch.empty(B, K, **f32)
     idx = torch.empty(B, topk, dtype=torch.int32, device=x.device)
     w = torch.empty(B, topk, **f32)
+    near_tie = torch.empty(B, dtype=torch.int32, device=x.device)
     _lib.call("mm_router_topk", _P(x), B, D, _P(W1), _P(b1), _P(W2), _P(b2), K, topk, _P(hidden), _P(probs), _P(idx),
-              _P(w), _st())
-    return hidden, probs, idx, w
+              _P(w), _P(near_tie), float(NEAR_TIE_TOL), _st())
+    return hidden, probs, idx, w, near_tie
 
 
 def router_bwd(dprobs, probs, hidden, x, W1, W2, need_dx: bool):

@@ -48,7 +48,7 @@ def _check_against(moe, feats_cpu, sw_cpu, ref_out, ref_grads, cot_g, cot_l, lab
     feats = [f.cuda().to(dtype).requires_grad_(True) for f in feats_cpu]
     sw = sw_cpu.cuda().requires_grad_(True)
     gf, lf, probs = moe(feats, sw)
-    assert gf.dtype == dtype and lf.dtype == dtype and probs.dtype == torch.float32
+    assert gf.dtype == torch.float32 and lf.dtype == dtype and probs.dtype == torch.float32   # global_feat is always fp32
     B, D = gf.shape
     assert lf.shape == ref_out["local_feat"].shape and not lf.is_contiguous()   # stride view like the reference
     assert torch.equal(torch.argmax(probs, -1).cpu(), ref_out["top_expert"])
@@ -266,7 +266,8 @@ def test_non_integer_scale_ratio_uses_generic_backward():
 
 def test_top2_extension_vs_generalised_oracle():
     """BASELINE config 4 routing: K = 8 experts, top-2 with renormalised gates (extension — parity is
-    against the generalised oracle, not the reference); 384^2 token geometry."""
+    against the generalised oracle, not the reference); 192^2 token geometry (2304/576/144/36) to keep
+    the CPU oracle fast — the 384^2 geometry proper is tests/test_parity_r2_gpu.py::test_cfg4_geometry_top2_k8_vs_generalised_oracle."""
     K, hidden, D, Ps, B = 8, [96, 192, 384, 768], 768, [2304, 576, 144, 36], 4
     params = mo.init_params(K, hidden, D, D, seed=41)
     params = {k: (v.to(torch.bfloat16).float() if (".proj_convs." in k or ".attn_proj.0." in k) and k.endswith("weight") else v)

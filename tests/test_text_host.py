@@ -80,3 +80,15 @@ def test_aggregate_tokens_equals_the_reference_method():
     got, _ = mmtext.aggregate_tokens(emb, ids, mmtext.continuation_table(IDX), SEP)
     assert torch.allclose(got, ref, atol=1e-6)
     assert mmtext.sentences_from_ids(ids, IDX) == sents
+
+
+def test_aggregate_tokens_equals_the_committed_reference_golden():
+    """tests/golden/text_aggregate.npz was produced by the reference method (make_golden_text.py); this runs everywhere."""
+    import numpy as np
+    from tests.util import GOLDEN
+    z = np.load(f"{GOLDEN}/text_aggregate.npz")
+    vocab = [str(w) for w in z["vocab"]]
+    got, n_words = mmtext.aggregate_tokens(torch.from_numpy(z["embeddings"]), torch.from_numpy(z["caption_ids"]),
+                                           mmtext.continuation_table(dict(enumerate(vocab))), int(z["sep_id"]))
+    assert torch.allclose(got, torch.from_numpy(z["aggregated"]), atol=1e-6)
+    assert n_words.tolist() == z["n_words"].tolist()
