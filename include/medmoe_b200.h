@@ -217,6 +217,35 @@ int mm_gloria_global_fwd(const float* img, const float* txt, int B, int D, float
                          float* loss, void* stream);
 int mm_gloria_global_bwd(const float* img, const float* txt, int B, int D, float temp, float eps, float* ws,
                          const float* gout, float* dimg, float* dtxt, void* stream);
+/* every expert's fp32 master parameters (separate storages under the reference's names, swin.py:18-30) -> the stacked
+ * operands the kernels read, in one launch: kind 0 = weight [rows, cols] -> bf16 copy dst and (dstT non-NULL) bf16
+ * transpose [cols, rows]; kind 1 = fp32 vector copy.  src / dst / dstT are HOST arrays of n_jobs DEVICE pointers. */
+int mm_pack_expert_params(const void* const* src, void* const* dst, void* const* dstT, const int32_t* rows,
+                          const int32_t* cols, const int32_t* kind, int n_jobs, void* stream);
+
+/* ---- (5) fused InfoNCE on the tensor cores (infonce_fused.cu) ---------------------------
+ * replaces src/losses.py:558-592 after the gather of :503-524, both directions at once:
+ *   logits_a = exp(logit_scale) a all_b^T, logits_b = exp(logit_scale) b all_a^T, labels label0 + r,
+ *   loss[0] = sum_r w_r CE(logits_a[r]), loss[1] likewise for logits_b (w = row_w or 1 / R; label_smoothing as in
+ *   F.cross_entropy, losses.py:579-583 cross_entropy_kwargs).
+ * fp32 in / out; the products run on tcgen05 as 3-way bf16 splits (six cross terms, fp32-exact to rounding).
+ * The logits are written only when logits_a / logits_b are non-NULL.  a, b [R, D]; all_a, all_b [N, D] (may alias a / b);
+ * lse [2, R]; workspace: mm_infonce_fused_workspace_bytes, 1 KB aligned, kept by the caller for the backward.
+ * Needs D % 192 == 0 (mm_infonce_fused_supported); other widths use mm_infonce_fwd / mm_infonce_bwd. */
+int mm_infonce_fused_supported(int R, int N, int D);
+long long mm_infonce_fused_workspace_bytes(int R, int N, int D);
+int mm_infonce_fused_fwd(const float* a, const float* b, const float* all_a, const float* all_b, int R, int N, int D,
+                         const float* logit_scale_exp, int label0, const float* row_w, float label_smoothing,
+                         void* workspace, float* logits_a, float* logits_b, float* lse, float* loss, void* stream);
+/* backward of both directions in one launch: recomputes each logits tile, forms dL in registers and feeds it back to the
+ * tensor cores from shared memory.  da, db [R, D], dall_a, dall_b [N, D] fp32 are ACCUMULATED (caller zero-fills them;
+ * dall_a may alias da and dall_b alias db when N == R); g_a, g_b: device scalars (upstream gradients), NULL = 0;
+ * dscale[0] (+)= d loss / d logit_scale. */
+int mm_infonce_fused_bwd(int R, int N, int D, const float* logit_scale_exp, int label0, const float* row_w,
+                         float label_smoothing, void* workspace, const float* lse, const float* g_a, const float* g_b,
+                         float* da, float* db, float* dall_a, float* dall_b, float* dscale, int accumulate_dscale,
+                         void* stream);
+
 /* FLAVA / CLIP semantics, one direction: replaces contrastive_loss_with_temperature,
  * src/losses.py:527-592 (the all-gather of :503-524 stays in torch.distributed).
  * logits [R, N] = *logit_scale_exp * a b_all^T; labels = label0 + row; loss = sum_r w_r (lse_r - logits[r, label]),

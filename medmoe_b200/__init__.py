@@ -4,7 +4,7 @@ Public surface mirrors the reference's operator interface for this path
 (src/models/components/swin.py `MoE`/`Expert`, src/losses.py global contrastive losses,
 src/utils/distributed.py gather helpers); see INTEGRATION.md for the drop-in recipe.
 """
-from .distributed import BackpropType, concat_gather_all_gpu, gather_tensor, get_rank
+from .distributed import BackpropType, OverlappedGradSync, concat_gather_all_gpu, gather_tensor, get_rank
 from .losses import (ContrastiveLossOutput, FLAVAGlobalContrastiveLoss, FLAVAGlobalContrastiveLossOutput,
                      GLORIAGlobalContrastiveLoss, contrastive_loss_with_temperature, zero_shot_predict)
 from .moe import Expert, MoE
@@ -18,7 +18,7 @@ __all__ = [
     "MoE", "Expert", "GLORIAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLoss", "FLAVAGlobalContrastiveLossOutput",
     "ContrastiveLossOutput", "contrastive_loss_with_temperature", "zero_shot_predict", "BackpropType", "gather_tensor",
     "concat_gather_all_gpu", "get_rank", "activate", "load_reference_checkpoint", "extract_moe_state_dict",
-    "zero_shot_evaluate", "SWIN", "GLORIALocalContrastiveLoss", "GLORIALocalContrastiveLossOutput", "local_similarities",
+    "zero_shot_evaluate", "SWIN", "OverlappedGradSync", "GLORIALocalContrastiveLoss", "GLORIALocalContrastiveLossOutput", "local_similarities",
 ]
 
 

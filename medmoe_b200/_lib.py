@@ -75,6 +75,13 @@ SIGNATURES = {
     "mm_infonce_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mm_infonce_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_f, c_vp, c_vp,
                                c_vp, c_vp, c_vp, c_int, c_vp]),
+    "mm_pack_expert_params": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "mm_infonce_fused_supported": (c_int, [c_int, c_int, c_int]),
+    "mm_infonce_fused_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
+    "mm_infonce_fused_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp]),
+    "mm_infonce_fused_bwd": (c_int, [c_int, c_int, c_int, c_vp, c_int, c_vp, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp, c_int, c_vp]),
     "mm_l2_normalize_fwd": (c_int, [c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "mm_l2_normalize_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp]),
     "mm_zeroshot_argmax": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
@@ -84,6 +91,7 @@ SIGNATURES = {
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats",
                 "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported",
+                "mm_infonce_fused_supported", "mm_infonce_fused_workspace_bytes",
                 "mm_debug_force_cuda_core_dut", "mm_debug_gemm_pair"}
 
 

@@ -354,3 +354,74 @@ extern "C" int mm_transpose_cast_f32_bf16(const float* src, void* dst, int batch
     mm::note_launches(1);
     return mm_check_launch("mm_transpose_cast_f32_bf16");
 }
+
+// ---------------------------------------------------------------------------------------
+// mm_pack_expert_params: every expert's fp32 master parameters (separate nn.Parameter storages, reference names
+// experts.{e}.proj_convs.{s}.0.{weight,bias}, experts.{e}.attn_proj.{0,2}.{weight,bias}; swin.py:18-30) -> the stacked
+// operands the kernels read, in ONE launch: bf16 weights [E, rows, cols], their bf16 transposes [E, cols, rows] (the
+// dgrad GEMMs), fp32 biases / vectors [E, n].  Replaces ~25 torch stack / cast / transpose launches per step.
+// The job table travels by value in the kernel parameters (no host -> device copy, CUDA-graph capturable).
+// ---------------------------------------------------------------------------------------
+namespace mm {
+struct PackJob {
+    const float* src;      // [rows, cols] fp32
+    void* dst;             // bf16 [rows, cols] (kind 0) or fp32 [rows * cols] (kind 1)
+    __nv_bfloat16* dstT;   // bf16 [cols, rows] or nullptr (kind 0 only)
+    int rows, cols;
+    int kind, pad;
+};
+constexpr int PACK_MAX_JOBS = 12 * 64;
+struct PackArgs { int n_jobs; PackJob job[PACK_MAX_JOBS]; };
+
+__global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant__ PackArgs a) {
+    __shared__ float tile[32][33];
+    const PackJob j = a.job[blockIdx.y];
+    if (j.kind == 1) {
+        const int n = j.rows * j.cols;
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) static_cast<float*>(j.dst)[i] = j.src[i];
+        return;
+    }
+    const int tr = (j.rows + 31) / 32, tc = (j.cols + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(j.dst);
+    for (int t = blockIdx.x; t < tr * tc; t += gridDim.x) {
+        const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty + 8 * i, c = c0 + tx;
+            float v = 0.f;
+            if (r < j.rows && c < j.cols) {
+                v = j.src[static_cast<size_t>(r) * j.cols + c];
+                dst[static_cast<size_t>(r) * j.cols + c] = __float2bfloat16_rn(v);
+            }
+            tile[ty + 8 * i][tx] = v;
+        }
+        if (j.dstT) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + ty + 8 * i, r = r0 + tx;
+                if (r < j.rows && c < j.cols) j.dstT[static_cast<size_t>(c) * j.rows + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+            }
+            __syncthreads();
+        }
+    }
+}
+}  // namespace mm
+
+// src / dst / dstT: HOST arrays of n_jobs DEVICE pointers; rows / cols / kind: host int arrays.
+extern "C" int mm_pack_expert_params(const void* const* src, void* const* dst, void* const* dstT, const int32_t* rows,
+                                     const int32_t* cols, const int32_t* kind, int n_jobs, void* stream) {
+    MM_REQUIRE(n_jobs >= 0 && n_jobs <= PACK_MAX_JOBS, MM_ERR_BAD_SHAPE, "mm_pack_expert_params: at most 768 tensors (64 experts)");
+    if (n_jobs == 0) return MM_OK;
+    static thread_local PackArgs a;      // 24 KB: kept off the stack
+    a.n_jobs = n_jobs;
+    for (int i = 0; i < n_jobs; ++i) {
+        MM_REQUIRE(src[i] && dst[i] && rows[i] > 0 && cols[i] > 0, MM_ERR_BAD_SHAPE, "mm_pack_expert_params: null tensor");
+        a.job[i] = PackJob{static_cast<const float*>(src[i]), dst[i], static_cast<__nv_bfloat16*>(dstT ? dstT[i] : nullptr), rows[i],
+                           cols[i], kind[i], 0};
+    }
+    pack_params_kernel<<<dim3(48, n_jobs), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    mm::note_launches(1);
+    return mm_check_launch("mm_pack_expert_params");
+}

@@ -48,7 +48,8 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
         for (int u = 0; u < 4; ++u) {
             const float v = warp_sum(acc[u]);
             if (lane == 0) {
-                const float h = fmaxf(v + b1[o + u], 0.f);
+                const float pre = v + b1[o + u];
+                const float h = pre < 0.f ? 0.f : pre;        // ReLU that lets NaN through like torch's (fmaxf would drop it)
                 sh[o + u] = h;
                 hidden[static_cast<size_t>(b) * ROUTER_HID + o + u] = h;
             }
@@ -65,7 +66,7 @@ router_fwd_kernel(const float* __restrict__ x, int D, const float* __restrict__ 
     __syncthreads();
     if (threadIdx.x == 0) {
         float mx = sl[0];
-        for (int e = 1; e < K; ++e) mx = fmaxf(mx, sl[e]);
+        for (int e = 1; e < K; ++e) mx = (sl[e] > mx || sl[e] != sl[e]) ? sl[e] : mx;      // NaN-propagating maximum
         float sum = 0.f;
         for (int e = 0; e < K; ++e) { const float t = expf(sl[e] - mx); sl[e] = t; sum += t; }
         const float inv = 1.0f / sum;
@@ -133,22 +134,40 @@ router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restri
     }
 }
 
-// out[r, c] = sum_b L[b, r] * R[b, c]   (dW = dOut^T * In, batch reduction, deterministic order)
-// grid = (ceil(C/256), R); optional bias out_b[r] = sum_b L[b, r].
-__global__ void __launch_bounds__(256)
-batch_outer_kernel(const float* __restrict__ L, int ldl, const float* __restrict__ R, int ldr, int B, int C,
-                   float* __restrict__ out, float* __restrict__ out_b) {
-    const int r = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    float acc = 0.f, accb = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < B; ++b) {
-        const float l = L[static_cast<size_t>(b) * ldl + r];
-        accb += l;
-        if (c < C) acc = fmaf(l, R[static_cast<size_t>(b) * ldr + c], acc);
+// dW2[e, o] = sum_b dlogit[b, e] hidden[b, o], db2[e] = sum_b dlogit[b, e]   (blocks 0 .. K-1, thread = hidden unit o)
+// db1[o]    = sum_b dhidden[b, o]                                            (block K)
+// coalesced over o, batch reduction in a fixed order (deterministic); replaces two latency-bound launches of batch_outer_kernel.
+__global__ void __launch_bounds__(ROUTER_HID)
+router_bwd_small_kernel(const float* __restrict__ dlogit, const float* __restrict__ hidden, const float* __restrict__ dhidden,
+                        int B, int K, float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ db1) {
+    const int o = threadIdx.x, e = blockIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e < K) {
+        int b = 0;
+        for (; b + 4 <= B; b += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float l = __ldg(dlogit + static_cast<size_t>(b + u) * K + e);
+                acc[u] = fmaf(l, __ldg(hidden + static_cast<size_t>(b + u) * ROUTER_HID + o), acc[u]);
+                accb[u] += l;
+            }
+        }
+        for (; b < B; ++b) {
+            const float l = __ldg(dlogit + static_cast<size_t>(b) * K + e);
+            acc[0] = fmaf(l, __ldg(hidden + static_cast<size_t>(b) * ROUTER_HID + o), acc[0]);
+            accb[0] += l;
+        }
+        dW2[e * ROUTER_HID + o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        if (o == 0) db2[e] = (accb[0] + accb[1]) + (accb[2] + accb[3]);
+    } else {
+        int b = 0;
+        for (; b + 4 <= B; b += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] += __ldg(dhidden + static_cast<size_t>(b + u) * ROUTER_HID + o);
+        }
+        for (; b < B; ++b) acc[0] += __ldg(dhidden + static_cast<size_t>(b) * ROUTER_HID + o);
+        db1[o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
-    if (c < C) out[static_cast<size_t>(r) * C + c] = acc;
-    if (out_b && c == 0) out_b[r] = accb;
 }
 
 }  // namespace mm
@@ -187,11 +206,8 @@ extern "C" int mm_router_bwd(const float* dprobs, const float* probs, const floa
         g.M = ROUTER_HID; g.N = D; g.K = B; g.alpha = 1.f;
         if (int rc = run_sgemm(g, st, "mm_router_bwd(dW1)")) return rc;
     }
-    // db1 = sum_b dh (C = 0: only the bias column of the batch reduction)
-    batch_outer_kernel<<<dim3(1, ROUTER_HID), 32, 0, st>>>(dhidden, ROUTER_HID, x, D, B, 0, dW1, db1);
-    mm::note_launches(1);
-    // dW2[K, 128] = dlogit^T h ; db2 = sum_b dlogit
-    batch_outer_kernel<<<dim3(1, K), 256, 0, st>>>(dlogit, K, hidden, ROUTER_HID, B, ROUTER_HID, dW2, db2);
+    // dW2[K, 128] = dlogit^T h, db2 = sum_b dlogit, db1 = sum_b dh: one launch
+    router_bwd_small_kernel<<<K + 1, ROUTER_HID, 0, st>>>(dlogit, hidden, dhidden, B, K, dW2, db2, db1);
     mm::note_launches(1);
     return mm_check_launch("mm_router_bwd");
 }

@@ -95,3 +95,63 @@ def concat_gather_all_gpu(tensor: torch.Tensor, backprop_type: BackpropType = Ba
     if dim == 0:
         return all_gather_cat(tensor, backprop_type)
     return torch.cat(gather_tensor(tensor, backprop_type), dim=dim)
+
+
+
+class OverlappedGradSync:
+    """DDP-style gradient averaging for a data-parallel `medmoe_b200.MoE` (experts replicated) that overlaps
+    the collective with the backward pass.
+
+    The MoE backward writes every expert-parameter gradient into ONE flat fp32 buffer and calls `grad_ready_hook` as soon as
+    the weight-gradient GEMMs are done — before the input-gradient GEMMs (dX), the un-permute and the router backward.  The
+    hook starts the NCCL all-reduce (AVG) of that bucket on a communication stream, so it travels over NVLink while those
+    kernels run; `finish()` (after `loss.backward()`) joins the stream and averages the few remaining parameters (router,
+    logit_scale: ~0.1 M values) in one more small bucket.  Everything is event-ordered and CUDA-graph capturable.
+    The reference gets the same arithmetic from Lightning's DDP (configs/trainer/ddp.yaml:4), after the whole backward.
+    """
+
+    def __init__(self, moe, other_params=(), process_group=None):
+        self.moe = moe
+        self.group = process_group
+        self.expert_params = [p for ex in moe.experts for p in ex.parameters()]
+        ids = {id(p) for p in self.expert_params}
+        self.other_params = [p for p in list(moe.parameters()) + list(other_params) if id(p) not in ids]
+        self.comm = None
+        self._flat = None
+        moe.grad_ready_hook = self._on_ready
+
+    def _on_ready(self, flat: torch.Tensor) -> None:
+        if not is_distributed():
+            return
+        if any(p.grad is not None for p in self.expert_params):
+            return                      # gradient accumulation into existing .grad: fall back to the late all-reduce in finish()
+        cur = torch.cuda.current_stream(flat.device)
+        if self.comm is None:
+            self.comm = torch.cuda.Stream(device=flat.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.comm.wait_event(ev)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        self._flat = flat
+
+    def finish(self) -> None:
+        """Call after backward: waits for the early all-reduce and averages whatever it did not cover."""
+        if not is_distributed():
+            return
+        late = list(self.other_params)
+        flat = self._flat
+        self._flat = None
+        if flat is not None:
+            torch.cuda.current_stream(flat.device).wait_stream(self.comm)
+            lo = flat.data_ptr()
+            hi = lo + flat.numel() * flat.element_size()
+            # autograd normally keeps the views of the flat buffer as .grad (no copy); anything else is averaged late
+            late += [p for p in self.expert_params if p.grad is not None and not (lo <= p.grad.data_ptr() < hi)]
+        else:
+            late += self.expert_params
+        grads = [p.grad for p in late if p.grad is not None]
+        if grads:
+            bucket = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(bucket, op=dist.ReduceOp.AVG, group=self.group)
+            torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(bucket, grads)))

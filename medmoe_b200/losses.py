@@ -28,6 +28,8 @@ from . import ops
 from .distributed import BackpropType, all_gather_cat, get_rank, is_distributed
 
 DEFAULT_LOGIT_SCALE = math.log(1 / 0.07)
+# test hook: run the fp32 CUDA-core InfoNCE kernels (csrc/loss.cu) instead of the fused tensor-core ones
+FORCE_UNFUSED_INFONCE = False
 
 
 # --------------------------------------------------------------------------------------
@@ -96,40 +98,67 @@ class _InfoNCEFunction(torch.autograd.Function):
 
     loss_a = sum_r w_r CE(exp(scale) a_r . all_b^T, label0 + r); loss_b symmetric.  Gradients are
     returned for a, b, all_a, all_b separately so that the all-gather's own backward (reduce-scatter)
-    routes the cross-rank part."""
+    routes the cross-rank part.  Widths that are multiples of 192 (768 in every configuration) run the fused
+    tensor-core kernels (csrc/infonce_fused.cu: one launch per pass for both directions, logits only written
+    when `want_logits`); other widths take the fp32 CUDA-core kernels of csrc/loss.cu."""
 
     @staticmethod
-    def forward(ctx, a, b, all_a, all_b, logit_scale, label0, row_w):
+    def forward(ctx, a, b, all_a, all_b, logit_scale, label0, row_w, smoothing=0.0, want_logits=True):
         a32, b32 = a.float().contiguous(), b.float().contiguous()
+        aliased = all_a is a and all_b is b
         alla32 = a32 if all_a is a else all_a.float().contiguous()
         allb32 = b32 if all_b is b else all_b.float().contiguous()
         scale_exp = torch.exp(logit_scale.detach().float()).reshape(1).contiguous()
+        R, D = a32.shape
+        N = allb32.shape[0]
+        ctx.fused = (not FORCE_UNFUSED_INFONCE) and a32.shape == b32.shape and alla32.shape == allb32.shape and \
+            ops.infonce_fused_supported(R, N, D)
+        ctx.cfg = (label0, row_w, a.dtype, b.dtype, all_a.dtype, all_b.dtype, logit_scale.dtype, logit_scale.shape, smoothing, aliased)
+        ctx.set_materialize_grads(False)
+        if ctx.fused:
+            loss, logits_a, logits_b, lse, ws = ops.infonce_fused_fwd(a32, b32, alla32, allb32, scale_exp, label0, row_w,
+                                                                      smoothing, want_logits)
+            ctx.save_for_backward(scale_exp, lse, ws)
+            ctx.dims = (R, N, D)
+            loss_a, loss_b = loss[0], loss[1]
+            if not want_logits:
+                return loss_a, loss_b, None, None
+            ctx.mark_non_differentiable(logits_a, logits_b)
+            return loss_a, loss_b, logits_a, logits_b
+        if smoothing:
+            raise NotImplementedError("label_smoothing needs the fused InfoNCE kernels (embedding width a multiple of 192)")
         loss_a, logits_a, lse_a = ops.infonce_fwd(a32, allb32, scale_exp, label0, row_w)
         loss_b, logits_b, lse_b = ops.infonce_fwd(b32, alla32, scale_exp, label0, row_w)
         ctx.save_for_backward(a32, b32, alla32, allb32, scale_exp, logits_a, logits_b, lse_a, lse_b)
-        ctx.cfg = (label0, row_w, a.dtype, b.dtype, all_a.dtype, all_b.dtype, logit_scale.dtype, logit_scale.shape)
         ctx.mark_non_differentiable(logits_a, logits_b)
-        ctx.set_materialize_grads(False)
         return loss_a, loss_b, logits_a, logits_b
 
     @staticmethod
     def backward(ctx, g_a, g_b, _gla, _glb):
+        label0, row_w, dt_a, dt_b, dt_alla, dt_allb, dt_s, shape_s, smoothing, aliased = ctx.cfg
+
+        def cast(t, dt):
+            return t.to(dt) if t is not None else None
+
+        def scalar(g):
+            return g.float().reshape(1).contiguous() if g is not None else None
+        if ctx.fused:
+            scale_exp, lse, ws = ctx.saved_tensors
+            R, N, D = ctx.dims
+            da, db, dall_a, dall_b, dscale = ops.infonce_fused_bwd(R, N, D, scale_exp, label0, row_w, smoothing, ws, lse,
+                                                                   scalar(g_a), scalar(g_b), aliased)
+            return (cast(da, dt_a), cast(db, dt_b), cast(dall_a, dt_alla), cast(dall_b, dt_allb),
+                    dscale.reshape(shape_s).to(dt_s), None, None, None, None)
         a32, b32, alla32, allb32, scale_exp, logits_a, logits_b, lse_a, lse_b = ctx.saved_tensors
-        label0, row_w, dt_a, dt_b, dt_alla, dt_allb, dt_s, shape_s = ctx.cfg
         dev = a32.device
         dscale = torch.zeros(1, dtype=torch.float32, device=dev)
         da = db = dall_a = dall_b = None
         if g_a is not None:
-            da, dall_b = ops.infonce_bwd(a32, allb32, scale_exp, label0, row_w, logits_a, lse_a,
-                                         g_a.float().reshape(1).contiguous(), 1.0, dscale, True)
+            da, dall_b = ops.infonce_bwd(a32, allb32, scale_exp, label0, row_w, logits_a, lse_a, scalar(g_a), 1.0, dscale, True)
         if g_b is not None:
-            db, dall_a = ops.infonce_bwd(b32, alla32, scale_exp, label0, row_w, logits_b, lse_b,
-                                         g_b.float().reshape(1).contiguous(), 1.0, dscale, True)
-
-        def cast(t, dt):
-            return t.to(dt) if t is not None else None
+            db, dall_a = ops.infonce_bwd(b32, alla32, scale_exp, label0, row_w, logits_b, lse_b, scalar(g_b), 1.0, dscale, True)
         return (cast(da, dt_a), cast(db, dt_b), cast(dall_a, dt_alla), cast(dall_b, dt_allb),
-                dscale.reshape(shape_s).to(dt_s), None, None)
+                dscale.reshape(shape_s).to(dt_s), None, None, None, None)
 
 
 def contrastive_loss_with_temperature(
@@ -139,9 +168,18 @@ def contrastive_loss_with_temperature(
     mask: Optional[Tensor] = None,
     backprop_type: BackpropType = BackpropType.GLOBAL,
     cross_entropy_kwargs: Optional[Dict[str, Any]] = None,
+    return_logits: bool = True,
 ) -> ContrastiveLossOutput:
-    if cross_entropy_kwargs:
-        raise NotImplementedError("cross_entropy_kwargs (e.g. label_smoothing) are not supported by the fused kernels")
+    """`cross_entropy_kwargs` (losses.py:579-583): `label_smoothing` is computed by the fused kernels; the other
+    F.cross_entropy options are accepted at their default values only.  `return_logits=False` (extension) skips
+    writing the two [B, N] logit matrices — the fused kernels then never materialise them (fields are None)."""
+    smoothing = 0.0
+    for k, v in (cross_entropy_kwargs or {}).items():
+        if k == "label_smoothing":
+            smoothing = float(v)
+        elif (k, v) not in (("reduction", "mean"), ("ignore_index", -100), ("weight", None), ("size_average", None),
+                            ("reduce", None)):
+            raise NotImplementedError(f"cross_entropy_kwargs[{k!r}]={v!r} is not supported by the fused InfoNCE kernels")
     if not embeddings_a.is_cuda:
         raise RuntimeError("medmoe_b200 losses run on CUDA tensors only; there is no CPU fallback")
     B = embeddings_a.shape[0]
@@ -162,9 +200,10 @@ def contrastive_loss_with_temperature(
     if mask is not None:
         m = mask.to(device=embeddings_a.device, dtype=torch.float32)
         row_w = (m / m.sum()).contiguous()                        # mean over the selected rows (losses.py:574-577)
-    loss_a, loss_b, logits_a, logits_b = _InfoNCEFunction.apply(embeddings_a, embeddings_b, all_a, all_b, logit_scale,
-                                                                label0, row_w)
-    if mask is not None:
+    with torch.cuda.device(embeddings_a.device):
+        loss_a, loss_b, logits_a, logits_b = _InfoNCEFunction.apply(embeddings_a, embeddings_b, all_a, all_b, logit_scale,
+                                                                    label0, row_w, smoothing, return_logits)
+    if mask is not None and logits_a is not None:
         logits_a, logits_b = logits_a[mask], logits_b[mask]
     return ContrastiveLossOutput(loss=(loss_a + loss_b) / 2, logits_a=logits_a, logits_b=logits_b, loss_a=loss_a,
                                  loss_b=loss_b)
@@ -204,6 +243,9 @@ class FLAVAGlobalContrastiveLoss(nn.Module):
             self.logit_scale = logit_scale
         else:
             self.logit_scale = nn.Parameter(logit_scale * torch.ones([]))
+        # extension: set to False when nothing reads image_logits / text_logits (training): the fused kernels then keep the
+        # logits on chip (the output fields are None)
+        self.return_logits = True
 
     def forward(self, image_sequence: Tensor, text_sequence: Tensor, mask: Optional[Tensor] = None) -> FLAVAGlobalContrastiveLossOutput:
         text_embedding = _L2NormalizeFunction.apply(text_sequence)
@@ -211,7 +253,7 @@ class FLAVAGlobalContrastiveLoss(nn.Module):
         self.logit_scale.data.clamp_(0, 4.6052)                  # losses.py:281
         out = contrastive_loss_with_temperature(
             embeddings_a=image_embedding, embeddings_b=text_embedding, logit_scale=self.logit_scale, mask=mask,
-            backprop_type=BackpropType.GLOBAL)
+            backprop_type=BackpropType.GLOBAL, return_logits=self.return_logits)
         return FLAVAGlobalContrastiveLossOutput(
             loss=out.loss, image_logits=out.logits_a, text_logits=out.logits_b, image_loss=out.loss_a,
             text_loss=out.loss_b, text_embedding=text_embedding, image_embedding=image_embedding,

@@ -68,7 +68,7 @@ class _ExpertsFunction(torch.autograd.Function):
     """(feats..., expert params...) -> (fused [B, P, D], global_feat [B, D]) for a given routing."""
 
     @staticmethod
-    def forward(ctx, item_expert, gate, topk, num_experts, n_scales, *tensors):
+    def forward(ctx, item_expert, gate, topk, num_experts, n_scales, owner, *tensors):
         feats = list(tensors[:n_scales])
         params = tensors[n_scales:]
         per = 2 * n_scales + 4
@@ -85,19 +85,12 @@ class _ExpertsFunction(torch.autograd.Function):
         D = params[0].shape[0]
         H = D // 2
         in_dtype = feats[0].dtype
+        feat_needs_grad = [f.requires_grad for f in feats]
+        param_needs_grad = any(p.requires_grad for p in params)
 
-        # ---- bf16 shadows of the fp32 master weights (stacked over experts) ----
-        def ex(e, i):
-            return params[e * per + i]
-        with torch.no_grad():
-            Wp32 = [torch.stack([ex(e, 2 * s).reshape(D, widths[s]) for e in range(E)]) for s in range(S)]   # [E, D, D_s]
-            bp = [torch.stack([ex(e, 2 * s + 1) for e in range(E)]).float().contiguous() for s in range(S)]    # [E, D]
-            W1_32 = torch.stack([ex(e, 2 * S) for e in range(E)])                                              # [E, H, D]
-            b1 = torch.stack([ex(e, 2 * S + 1) for e in range(E)]).float().contiguous()                         # [E, H]
-            w2 = torch.stack([ex(e, 2 * S + 2).reshape(H) for e in range(E)]).float().contiguous()              # [E, H]
-            b2 = torch.stack([ex(e, 2 * S + 3).reshape(()) for e in range(E)]).float().contiguous()             # [E]
-            Wp = [ops.cast_bf16(w.float()).view(E * D, widths[s]) for s, w in enumerate(Wp32)]
-            W1 = ops.cast_bf16(W1_32.float()).view(E * H, D)
+        # ---- bf16 shadows of the fp32 master weights, stacked over experts (+ transposes for dgrad): ONE launch ----
+        pk = ops.pack_expert_params(params, E, S, widths, D, H, need_T=param_needs_grad or any(feat_needs_grad))
+        Wp, W1, bp, b1, w2, b2 = pk["Wp"], pk["W1"], pk["bp"], pk["b1"], pk["w2"], pk["b2"]
 
         layout = make_layout(B, topk, E, P)
         plan = build_plan(item_expert.reshape(-1).contiguous(), layout)
@@ -120,10 +113,11 @@ class _ExpertsFunction(torch.autograd.Function):
 
         ctx.plan, ctx.layout = plan, layout
         ctx.dims = (B, E, S, D, H, widths, topk, per, in_dtype)
-        ctx.saved = (fs, Y, Z, beta, w2, W1_32, Wp32, gate_flat)
-        ctx.feat_needs_grad = [f.requires_grad for f in feats]
-        ctx.param_needs_grad = any(p.requires_grad for p in params)
+        ctx.saved = (fs, Y, Z, beta, w2, pk["W1T"], pk["WpT"], gate_flat)
+        ctx.feat_needs_grad = feat_needs_grad
+        ctx.param_needs_grad = param_needs_grad
         ctx.gate_needs_grad = gate is not None and gate.requires_grad
+        ctx.owner = owner
         ctx.set_materialize_grads(False)
         return fused, gfeat      # global_feat stays fp32 (the token mean is accumulated in fp32; only local_feat follows the input dtype)
 
@@ -131,9 +125,9 @@ class _ExpertsFunction(torch.autograd.Function):
     def backward(ctx, dfused, dglobal):
         plan, layout = ctx.plan, ctx.layout
         B, E, S, D, H, widths, topk, per, in_dtype = ctx.dims
-        fs, Y, Z, beta, w2, W1_32, Wp32, gate_flat = ctx.saved
+        fs, Y, Z, beta, w2, W1T, WsT, gate_flat = ctx.saved
         dev = Y.device
-        n_in = 5 + S + E * per
+        n_in = 6 + S + E * per
         if dfused is None and dglobal is None:
             return (None,) * n_in
         if dfused is not None:
@@ -142,9 +136,20 @@ class _ExpertsFunction(torch.autograd.Function):
             dfused = dfused.contiguous()
         dglobal32 = dglobal.float().contiguous() if dglobal is not None else None
 
-        W1T = ops.transpose_cast_bf16(W1_32.float()).view(E * D, H)          # [E, D, H]
-        # conv bias gradients = column sums of dPre: they come out of the dWp weight-gradient MMAs (ones block)
-        dbp = [torch.zeros(E, D, dtype=torch.float32, device=dev) for _ in range(S)]
+        # ONE fp32 buffer holds every expert-parameter gradient (one memset instead of ten fills; the per-parameter gradients
+        # handed to autograd are contiguous views of it, and a DDP-style hook can all-reduce it as a single bucket while
+        # the rest of this backward still runs):  dW1 [E,H,D] | dWp_s [E,D,D_s] | dbp_s [E,D] | red [E, D+1] = (dw2, db1, db2)
+        sizes = [E * H * D] + [E * D * w for w in widths] + [E * D] * S + [E * (D + 1)]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for n in sizes:
+            views.append(flat[off:off + n]); off += n
+        dW1 = views[0].view(E, H, D)
+        dWp = [views[1 + s].view(E, D, widths[s]) for s in range(S)]
+        dbp = [views[1 + S + s].view(E, D) for s in range(S)]      # conv bias gradients = column sums of dPre (ones block of dWp)
+        red = views[1 + 2 * S].view(E, D + 1)
+
+        need_dpre = ctx.param_needs_grad or any(ctx.feat_needs_grad)
         use_tc = not ops.FORCE_GENERIC_COMBINE_BWD and (
             ops.combine_bwd_global_supported(plan, D) if dfused is None else ops.combine_bwd_tc_supported(plan, D))
         if use_tc:
@@ -154,9 +159,11 @@ class _ExpertsFunction(torch.autograd.Function):
             if dfused is not None:
                 dlocal16 = dfused if dfused.dtype == torch.bfloat16 else ops.cast_bf16(dfused)
             row_coef, row_img, dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd_tc(Y, Z, w2, plan, D, gate_flat, beta, dlocal16,
-                                                                                  dglobal32, ctx.gate_needs_grad)
+                                                                                  dglobal32, ctx.gate_needs_grad, red=red)
             # one launch over the whole row space: every scale shares W1, and the rank-1 tables are indexed by global row
-            if dglobal32 is not None:
+            if not need_dpre:
+                dPre = None          # frozen experts and features: only the gate weights (top-k > 1) want a gradient
+            elif dglobal32 is not None:
                 dPre = dUT if dUT is not None else torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
                 ops.gemm_rows_rank1(dZ, W1T, D, dPre, plan=plan, tile_begin=0, tile_count=layout.total_tiles, row_coef=row_coef,
                                     row_vec=row_img, vecs=dglobal32, gate=Y, aux=dUT, tag="dY")
@@ -166,30 +173,17 @@ class _ExpertsFunction(torch.autograd.Function):
                 dPre = dUT
         else:
             dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
-                                                            ctx.gate_needs_grad)
+                                                            ctx.gate_needs_grad, red=red)
             # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT
-            ops.gemm_rows(dZ, W1T, D, dUT, plan=plan, tile_begin=0, tile_count=layout.total_tiles, aux=dUT, gate=Y,
-                          flags=ops.EPI_ZERO_PAD, tag="dY")
+            if need_dpre:
+                ops.gemm_rows(dZ, W1T, D, dUT, plan=plan, tile_begin=0, tile_count=layout.total_tiles, aux=dUT, gate=Y,
+                              flags=ops.EPI_ZERO_PAD, tag="dY")
             dPre = dUT
 
-        grads_feats: List = [None] * S
-        if any(ctx.feat_needs_grad):
-            WsT = [ops.transpose_cast_bf16(Wp32[s].float()).view(E * widths[s], D) for s in range(S)]   # [E, D_s, D]
-            dfs = [torch.empty(layout.region_rows[s], widths[s], dtype=torch.bfloat16, device=dev) for s in range(S)]
-
-            def dx(s):   # df_s = dPre_s W_s
-                r0, nr = layout.region_base[s], layout.region_rows[s]
-                return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfs[s], plan=plan,
-                                             tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
-            ops.run_scales([dx(s) for s in range(S)])
-            outs = ops.undispatch_rows(dfs, plan, widths, in_dtype)
-            grads_feats = [o if need else None for o, need in zip(outs, ctx.feat_needs_grad)]
-
+        # weight gradients first: once they are complete the flat bucket can travel (NCCL on a side stream) while dX runs
         grads_params: List = [None] * (E * per)
         if ctx.param_needs_grad:
-            dW1 = torch.zeros(E, H, D, dtype=torch.float32, device=dev)
             ops.gemm_wgrad(dZ, Y, dW1, plan, 0, layout.total_chunks, 0, tag="dW1")
-            dWp = [torch.zeros(E, D, widths[s], dtype=torch.float32, device=dev) for s in range(S)]
 
             def dwp(s):
                 r0, nr = layout.region_base[s], layout.region_rows[s]
@@ -204,13 +198,30 @@ class _ExpertsFunction(torch.autograd.Function):
                 grads_params[e * per + 2 * S + 1] = db1[e]
                 grads_params[e * per + 2 * S + 2] = dw2[e].unsqueeze(0)           # Linear(H, 1) weight [1, H]
                 grads_params[e * per + 2 * S + 3] = db2[e].reshape(1)
+            owner = ctx.owner
+            if owner is not None:
+                owner.last_flat_grad = flat
+                if owner.grad_ready_hook is not None:
+                    owner.grad_ready_hook(flat)
+
+        grads_feats: List = [None] * S
+        if any(ctx.feat_needs_grad):
+            dfs = [torch.empty(layout.region_rows[s], widths[s], dtype=torch.bfloat16, device=dev) for s in range(S)]
+
+            def dx(s):   # df_s = dPre_s W_s
+                r0, nr = layout.region_base[s], layout.region_rows[s]
+                return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfs[s], plan=plan,
+                                             tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
+            ops.run_scales([dx(s) for s in range(S)])
+            outs = ops.undispatch_rows(dfs, plan, widths, in_dtype)
+            grads_feats = [o if need else None for o, need in zip(outs, ctx.feat_needs_grad)]
         dgate_out = dgate.view(B, topk) if dgate is not None else None
-        return (None, dgate_out, None, None, None, *grads_feats, *grads_params)
+        return (None, dgate_out, None, None, None, None, *grads_feats, *grads_params)
 
 
-def _run_experts(experts, feats, item_expert, gate, topk):
+def _run_experts(experts, feats, item_expert, gate, topk, owner=None):
     params = _expert_param_list(experts)
-    return _ExpertsFunction.apply(item_expert, gate, topk, len(experts), len(feats), *feats, *params)
+    return _ExpertsFunction.apply(item_expert, gate, topk, len(experts), len(feats), owner, *feats, *params)
 
 
 class _RouterFunction(torch.autograd.Function):
@@ -251,6 +262,12 @@ class MoE(nn.Module):
         self.topk = int(topk)
         self.last_top_expert = None   # int32 [B, topk] of the most recent forward (device tensor, no sync)
         self.last_near_tie = None     # int32 [B]: 1 where the routing margin was < ops.NEAR_TIE_TOL (device tensor, no sync)
+        # Every expert-parameter gradient of a backward pass lives in ONE flat fp32 buffer (`last_flat_grad`; the .grad
+        # tensors are views of it).  `grad_ready_hook(flat)` is called from inside the backward as soon as that buffer is
+        # complete — before the input gradients are computed — so that data-parallel training can start its all-reduce
+        # early (medmoe_b200.distributed.OverlappedGradSync).
+        self.last_flat_grad = None
+        self.grad_ready_hook = None
 
     def near_tie_count(self) -> int:
         """Images of the most recent forward whose expert choice hangs on a probability gap < 1e-6 (synchronises).
@@ -276,7 +293,7 @@ class MoE(nn.Module):
                 # extension: renormalised top-k probabilities, differentiable w.r.t. the router (tiny torch ops)
                 sel = probs.gather(1, idx.long())
                 gate = sel / sel.sum(dim=1, keepdim=True)
-            fused, global_feat = _run_experts(list(self.experts), feats, idx, gate, self.topk)
+            fused, global_feat = _run_experts(list(self.experts), feats, idx, gate, self.topk, owner=self)
         B, P, D = fused.shape
         Hh = Ww = int(P ** 0.5)                                       # swin.py:111
         local_feat = fused.transpose(1, 2).reshape(B, D, Hh, Ww)      # a stride view, as in the reference

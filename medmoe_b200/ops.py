@@ -144,6 +144,62 @@ def transpose_cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def pack_expert_params(params: Sequence[torch.Tensor], E: int, S: int, widths: Sequence[int], D: int, H: int, need_T: bool):
+    """The experts' fp32 master parameters -> stacked kernel operands, in one launch (mm_pack_expert_params).
+    params: per expert [conv_s.weight, conv_s.bias] * S + [attn0.weight, attn0.bias, attn2.weight, attn2.bias].
+    Returns dict: Wp[s] bf16 [E*D, D_s], WpT[s] bf16 [E*D_s, D] | None, W1 bf16 [E*H, D], W1T bf16 [E*D, H] | None,
+    bp[s] fp32 [E, D], b1 [E, H], w2 [E, H], b2 [E]."""
+    per = 2 * S + 4
+    dev = params[0].device
+    keep = []                                     # fp32 / contiguous temporaries stay alive until the launch is enqueued
+
+    def f32(t):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.detach().float().contiguous()
+            keep.append(t)
+        return t
+    n_w = sum(E * D * w for w in widths) + E * H * D
+    wbuf = torch.empty(n_w * (2 if need_T else 1), dtype=torch.bfloat16, device=dev)
+    vbuf = torch.empty(S * E * D + 2 * E * H + E, dtype=torch.float32, device=dev)
+    out = {"Wp": [], "WpT": [], "bp": []}
+    off = 0
+    for s in range(S):
+        out["Wp"].append(wbuf[off:off + E * D * widths[s]].view(E * D, widths[s])); off += E * D * widths[s]
+    out["W1"] = wbuf[off:off + E * H * D].view(E * H, D); off += E * H * D
+    if need_T:
+        for s in range(S):
+            out["WpT"].append(wbuf[off:off + E * D * widths[s]].view(E * widths[s], D)); off += E * D * widths[s]
+        out["W1T"] = wbuf[off:off + E * H * D].view(E * D, H); off += E * H * D
+    else:
+        out["WpT"], out["W1T"] = [None] * S, None
+    voff = 0
+    for s in range(S):
+        out["bp"].append(vbuf[voff:voff + E * D].view(E, D)); voff += E * D
+    out["b1"] = vbuf[voff:voff + E * H].view(E, H); voff += E * H
+    out["w2"] = vbuf[voff:voff + E * H].view(E, H); voff += E * H
+    out["b2"] = vbuf[voff:voff + E]
+    src, dst, dstT, rows, cols, kind = [], [], [], [], [], []
+
+    def job(t, d, dT, r, c, k):
+        src.append(f32(t).data_ptr()); dst.append(d.data_ptr()); dstT.append(dT.data_ptr() if dT is not None else 0)
+        rows.append(r); cols.append(c); kind.append(k)
+    for e in range(E):
+        base = e * per
+        for s in range(S):
+            w = widths[s]
+            job(params[base + 2 * s], out["Wp"][s][e * D:(e + 1) * D], out["WpT"][s][e * w:(e + 1) * w] if need_T else None, D, w, 0)
+            job(params[base + 2 * s + 1], out["bp"][s][e], None, 1, D, 1)
+        job(params[base + 2 * S], out["W1"][e * H:(e + 1) * H], out["W1T"][e * D:(e + 1) * D] if need_T else None, H, D, 0)
+        job(params[base + 2 * S + 1], out["b1"][e], None, 1, H, 1)
+        job(params[base + 2 * S + 2], out["w2"][e], None, 1, H, 1)
+        job(params[base + 2 * S + 3], out["b2"][e:e + 1], None, 1, 1, 1)
+    n = len(src)
+    _lib.call("mm_pack_expert_params", (_lib.C.c_void_p * n)(*src), (_lib.C.c_void_p * n)(*dst), (_lib.C.c_void_p * n)(*dstT),
+              _lib.host_i32(rows), _lib.host_i32(cols), _lib.host_i32(kind), n, _st())
+    del keep
+    return out
+
+
 # ---- grouped GEMMs --------------------------------------------------------------------
 def gemm_rows(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, plan: Optional[DispatchPlan] = None,
               tile_begin: int = 0, tile_count: int = 0, M: int = 0, bias=None, aux=None, gate=None, colsum=None,
@@ -210,7 +266,7 @@ def combine_fwd(Y, Z, w2, b2, plan: DispatchPlan, D: int, gate, out_dtype):
 
 
 def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool,
-                force_generic: bool = False):
+                force_generic: bool = False, red=None):
     lay = plan.layout
     _need_cuda(Y, Z, w2, beta, dlocal, dglobal)
     B, P, K = lay.n_images, lay.P[0], lay.num_experts
@@ -225,7 +281,8 @@ def combine_bwd(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dgloba
     dUT = torch.empty(lay.total_rows, D, dtype=torch.bfloat16, device=dev)
     dZ = torch.empty(lay.total_rows, D // 2, dtype=torch.bfloat16, device=dev)
     part = torch.empty(lay.n_items, nrb, D + 1, **f32)
-    red = torch.empty(K, D + 1, **f32)
+    if red is None:
+        red = torch.empty(K, D + 1, **f32)
     dl_f32 = dlocal is not None and dlocal.dtype == torch.float32
     _lib.call("mm_interp_softmax_combine_bwd", _P(Y), _P(Z), _P(w2), B, lay.topk, P, _lib.host_i32(lay.P), D, K,
               _P(plan.perm), _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(plan.counts),
@@ -246,7 +303,7 @@ def combine_bwd_tc_supported(plan: DispatchPlan, D: int) -> bool:
     return bool(_lib.call("mm_combine_bwd_tc_supported", lay.P[0], _lib.host_i32(lay.P), D))
 
 
-def combine_bwd_tc(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool):
+def combine_bwd_tc(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dglobal, need_dgate: bool, red=None):
     """Backward of the combine on the tensor-core / rank-1 path.  dlocal: bf16 [B, P, D] or None; dglobal: fp32 [B, D] or None.
     Returns (row_coef, row_img, dUT, dZ, dw2, db1, db2, dgate): d fused / d Y = dUT (local part, None without dlocal)
     + row_coef[row] * dglobal[row_img[row]] (rebuilt inside the dY GEMM, None without dglobal)."""
@@ -271,7 +328,8 @@ def combine_bwd_tc(Y, Z, w2, plan: DispatchPlan, D: int, gate, beta, dlocal, dgl
     dgate = torch.zeros(lay.n_items, **f32) if need_dgate else None
     dZ = torch.empty(lay.total_rows, D // 2, dtype=torch.bfloat16, device=dev)
     part = torch.empty(lay.n_items, nrb, D + 1, **f32)
-    red = torch.empty(K, D + 1, **f32)
+    if red is None:
+        red = torch.empty(K, D + 1, **f32)
     tile0 = plan.tile_info[lay.tile_base[0]:lay.tile_base[0] + lay.region_tiles[0]]
     _lib.call("mm_interp_softmax_combine_bwd_tc", _P(Y), _P(Z), _P(w2), B, lay.topk, P, _lib.host_i32(lay.P), D, K,
               _P(plan.perm), _P(plan.inv_perm), _P(plan.slot_expert), _P(plan.slot_row), _P(plan.counts),
@@ -323,6 +381,44 @@ def infonce_bwd(a, b_all, scale_exp, label0: int, row_w, logits, lse, gout, gmul
               _P(gout), float(gmul), _P(dlogits), _P(row_tmp), _P(da), _P(db_all), _P(dscale), int(accumulate_dscale),
               _st())
     return da, db_all
+
+
+def infonce_fused_supported(R: int, N: int, D: int) -> bool:
+    return bool(_lib.call("mm_infonce_fused_supported", R, N, D))
+
+
+def infonce_fused_fwd(a, b, all_a, all_b, scale_exp, label0: int, row_w, smoothing: float, want_logits: bool):
+    """Both directions of the InfoNCE in one fused tcgen05 kernel (+ the bf16 split pre-pass).
+    Returns (loss [2], logits_a | None, logits_b | None, lse [2, R], workspace)."""
+    _need_cuda(a, b, all_a, all_b, scale_exp, row_w)
+    R, D = a.shape
+    N = all_b.shape[0]
+    dev = a.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    ws = torch.empty(_lib.call("mm_infonce_fused_workspace_bytes", R, N, D) + 1024, dtype=torch.uint8, device=dev)
+    ws = ws[(-ws.data_ptr()) % 1024:]                       # 1 KB aligned view (torch allocations are 512 B aligned)
+    logits_a = torch.empty(R, N, **f32) if want_logits else None
+    logits_b = torch.empty(R, N, **f32) if want_logits else None
+    lse = torch.empty(2, R, **f32)
+    loss = torch.empty(2, **f32)
+    _lib.call("mm_infonce_fused_fwd", _P(a), _P(b), _P(all_a), _P(all_b), R, N, D, _P(scale_exp), label0, _P(row_w),
+              float(smoothing), _P(ws), _P(logits_a), _P(logits_b), _P(lse), _P(loss), _st())
+    return loss, logits_a, logits_b, lse, ws
+
+
+def infonce_fused_bwd(R: int, N: int, D: int, scale_exp, label0: int, row_w, smoothing: float, ws, lse, g_a, g_b, aliased: bool):
+    """-> (da, db, dall_a | None, dall_b | None, dscale [1]).  `aliased` (single rank: all_a is a): the column-side gradients are
+    accumulated into da / db in place."""
+    dev = lse.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    rows = 2 * R if aliased else 2 * R + 2 * N
+    buf = torch.zeros(rows, D, **f32)                      # one memset for all four gradient buffers
+    da, db = buf[:R], buf[R:2 * R]
+    dall_a, dall_b = (da, db) if aliased else (buf[2 * R:2 * R + N], buf[2 * R + N:])
+    dscale = torch.empty(1, **f32)
+    _lib.call("mm_infonce_fused_bwd", R, N, D, _P(scale_exp), label0, _P(row_w), float(smoothing), _P(ws), _P(lse), _P(g_a),
+              _P(g_b), _P(da), _P(db), _P(dall_a), _P(dall_b), _P(dscale), 0, _st())
+    return da, db, (None if aliased else dall_a), (None if aliased else dall_b), dscale
 
 
 def l2_normalize_fwd(x, eps: float = 1e-12):

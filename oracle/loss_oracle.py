@@ -37,9 +37,10 @@ def gloria_global_loss(cnn_code: torch.Tensor, rnn_code: torch.Tensor, temp3: fl
 
 def contrastive_loss_with_temperature(emb_a: torch.Tensor, emb_b: torch.Tensor, logit_scale: torch.Tensor,
                                       all_a: Optional[torch.Tensor] = None, all_b: Optional[torch.Tensor] = None,
-                                      rank: int = 0, mask: Optional[torch.Tensor] = None):
+                                      rank: int = 0, mask: Optional[torch.Tensor] = None, label_smoothing: float = 0.0):
     """One rank's view of losses.py:527-592.  all_a / all_b are the concatenated embeddings of
-    every rank (None = single process); labels are local_batch * rank + arange (losses.py:516)."""
+    every rank (None = single process); labels are local_batch * rank + arange (losses.py:516);
+    `label_smoothing` is the one `cross_entropy_kwargs` entry restated (losses.py:579-583)."""
     temperature = torch.exp(logit_scale)
     if all_a is None:
         all_a, all_b = emb_a, emb_b
@@ -49,8 +50,8 @@ def contrastive_loss_with_temperature(emb_a: torch.Tensor, emb_b: torch.Tensor, 
     logits_b = emb_b @ all_a.t() * temperature
     if mask is not None:
         logits_a, logits_b, labels = logits_a[mask], logits_b[mask], labels[mask]
-    loss_a = F.cross_entropy(logits_a, labels)
-    loss_b = F.cross_entropy(logits_b, labels)
+    loss_a = F.cross_entropy(logits_a, labels, label_smoothing=label_smoothing)
+    loss_b = F.cross_entropy(logits_b, labels, label_smoothing=label_smoothing)
     return (loss_a + loss_b) / 2, logits_a, logits_b, loss_a, loss_b
 
 

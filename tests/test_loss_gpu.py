@@ -162,3 +162,74 @@ def test_zero_shot_driver_prompt_ensembles_and_accuracy():
     assert torch.equal(out["pred"], ref)
     assert abs(out["accuracy"].item() - (ref == labels).double().mean().item()) < 1e-6
     assert torch.isnan(out["per_class_accuracy"][C - 1]) and out["per_class_accuracy"][: C - 1].min() > 0.5
+
+
+# ---- fused tensor-core InfoNCE (csrc/infonce_fused.cu) ----------------------------------------------------------------
+def test_fused_infonce_label_smoothing_matches_reference_golden():
+    """cross_entropy_kwargs={"label_smoothing": 0.1} (losses.py:579-583) against the reference function's own output."""
+    g = load_golden("losses_smoothing")
+    for tag, m in (("", None), ("mask.", g["mask"].cuda())):
+        a = g["a"].cuda().requires_grad_(True); b = g["b"].cuda().requires_grad_(True); s = g["scale"].cuda().requires_grad_(True)
+        out = medmoe_b200.contrastive_loss_with_temperature(a, b, s, mask=m, cross_entropy_kwargs={"label_smoothing": 0.1})
+        assert abs(out.loss.item() - g[tag + "loss"].item()) < 1e-5
+        assert abs(out.loss_a.item() - g[tag + "loss_a"].item()) < 1e-5 and abs(out.loss_b.item() - g[tag + "loss_b"].item()) < 1e-5
+        out.loss.backward()
+        assert rel_err(a.grad.cpu(), g[tag + "da"]) < 1e-4 and rel_err(b.grad.cpu(), g[tag + "db"]) < 1e-4
+        assert abs(s.grad.item() - g[tag + "dscale"].item()) < 1e-4 * max(1.0, abs(g[tag + "dscale"].item()))
+    with pytest.raises(NotImplementedError):
+        medmoe_b200.contrastive_loss_with_temperature(a, b, s, cross_entropy_kwargs={"reduction": "sum"})
+
+
+@pytest.mark.parametrize("R,N,r", [(256, 256, 0), (256, 2048, 5), (100, 300, 2), (37, 37, 0)])
+def test_fused_and_unfused_infonce_agree_and_match_oracle(R, N, r):
+    """The tcgen05 kernels (3-way bf16 split, fp32-exact to rounding) against the fp32 CUDA-core kernels and the oracle: ragged
+    row / column tiles, label offsets, logits on request only."""
+    from medmoe_b200 import losses as L
+    torch.manual_seed(R + N)
+    all_a = torch.nn.functional.normalize(torch.randn(N, 768), dim=-1)
+    all_b = torch.nn.functional.normalize(torch.randn(N, 768), dim=-1)
+    s = torch.tensor(lo.DEFAULT_LOGIT_SCALE)
+    aliased = R == N
+    label0 = 0 if aliased else min(r * R, N - R)
+    ar = all_a.clone().requires_grad_(True); br = all_b.clone().requires_grad_(True); sr = s.clone().requires_grad_(True)
+    temperature = torch.exp(sr)
+    la_ref = torch.nn.functional.cross_entropy(ar[label0:label0 + R] @ br.t() * temperature, label0 + torch.arange(R))
+    lb_ref = torch.nn.functional.cross_entropy(br[label0:label0 + R] @ ar.t() * temperature, label0 + torch.arange(R))
+    ((la_ref + lb_ref) / 2).backward()
+    res = {}
+    for force in (False, True):
+        L.FORCE_UNFUSED_INFONCE = force
+        try:
+            ag = all_a.cuda().requires_grad_(True); bg = all_b.cuda().requires_grad_(True); sg = s.cuda().requires_grad_(True)
+            a_loc, b_loc = (ag, bg) if aliased else (ag[label0:label0 + R], bg[label0:label0 + R])
+            n0 = medmoe_b200._lib.load().mm_launch_count()
+            la, lb, logits_a, logits_b = _InfoNCEFunction.apply(a_loc, b_loc, ag, bg, sg, label0, None, 0.0, not force and R == 37)
+            ((la + lb) / 2).backward()
+            res[force] = (la.item(), lb.item(), ag.grad.clone(), bg.grad.clone(), sg.grad.item(),
+                          medmoe_b200._lib.load().mm_launch_count() - n0, logits_a)
+        finally:
+            L.FORCE_UNFUSED_INFONCE = False
+    for force in (False, True):
+        la, lb, da, db, ds, _, _ = res[force]
+        assert abs(la - la_ref.item()) < 1e-5 * abs(la_ref.item()) and abs(lb - lb_ref.item()) < 1e-5 * abs(lb_ref.item())
+        assert rel_err(da.cpu(), ar.grad) < 1e-4 and rel_err(db.cpu(), br.grad) < 1e-4
+        assert abs(ds - sr.grad.item()) < 1e-4 * max(1.0, abs(sr.grad.item()))
+    assert res[False][5] == 3 and res[True][5] > 10          # split + fused forward + fused backward vs the unfused chain
+    if R == 37:
+        ref_logits = (ar[:R] @ br.t() * temperature).detach()
+        assert (res[False][6].cpu() - ref_logits).abs().max().item() < 2e-5
+    else:
+        assert res[False][6] is None                              # logits stay on chip unless asked for
+
+
+def test_flava_module_without_logits():
+    g = load_golden("losses")
+    I = g["flava.img"].cuda().requires_grad_(True)
+    T = g["flava.txt"].cuda().requires_grad_(True)
+    mod = medmoe_b200.FLAVAGlobalContrastiveLoss().cuda()
+    mod.return_logits = False
+    out = mod(I, T)
+    assert out.image_logits is None and out.text_logits is None
+    assert abs(out.loss.item() - g["flava.loss"].item()) < 1e-5
+    out.loss.backward()
+    assert rel_err(I.grad.cpu(), g["flava.dimg"]) < 1e-4 and rel_err(T.grad.cpu(), g["flava.dtxt"]) < 1e-4

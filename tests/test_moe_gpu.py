@@ -205,7 +205,10 @@ def test_full_batch_properties():
         perm = torch.randperm(B, device="cuda", generator=g)
         gfp, lfp, probsp = moe([f[perm] for f in feats], sw[perm])
         assert torch.equal(probsp, probs[perm]) and torch.equal(moe.last_top_expert, top[perm])
-        assert torch.equal(lfp, lf[perm]) and torch.equal(gfp, gf[perm])
+        assert torch.equal(lfp, lf[perm])
+        # global_feat is returned in fp32: an image that lands at another offset inside its 128-token tile has its 7-term
+        # sums accumulated in another order by the MMA, so the token mean agrees to fp32 reassociation, not bit for bit
+        assert (gfp - gf[perm]).abs().max().item() <= 2e-6 * gf.abs().max().item()
     assert torch.isfinite(lf.float()).all() and torch.isfinite(gf.float()).all()
     # (3) global_feat is the token mean of local_feat
     assert rel_err(gf.float(), lf.float().flatten(2).mean(-1)) < 5e-3

@@ -137,3 +137,16 @@ def test_local_loss_oracle_matches_reference_golden():
         assert torch.allclose(img.grad, torch.tensor(g[f"d_img_{agg}"]), atol=1e-6)
         assert torch.allclose(words.grad, torch.tensor(g[f"d_words_{agg}"]), atol=1e-6)
         assert torch.allclose(att[3], torch.tensor(g[f"att3_{agg}"]), atol=1e-6)
+
+
+def test_flava_label_smoothing_oracle_matches_reference_golden():
+    """cross_entropy_kwargs={"label_smoothing": 0.1} through the reference function (make_golden_smoothing.py), incl. the mask."""
+    from oracle import loss_oracle as lo
+    g = load_golden("losses_smoothing")
+    for tag, m in (("", None), ("mask.", g["mask"])):
+        a = g["a"].clone().requires_grad_(True); b = g["b"].clone().requires_grad_(True); s = g["scale"].clone().requires_grad_(True)
+        loss, _, _, la, lb = lo.contrastive_loss_with_temperature(a, b, s, mask=m, label_smoothing=0.1)
+        loss.backward()
+        assert abs(loss.item() - g[tag + "loss"].item()) < 1e-6 and abs(la.item() - g[tag + "loss_a"].item()) < 1e-6
+        assert torch.allclose(a.grad, g[tag + "da"], atol=1e-7) and torch.allclose(b.grad, g[tag + "db"], atol=1e-7)
+        assert abs(s.grad.item() - g[tag + "dscale"].item()) < 1e-5
