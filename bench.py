@@ -406,7 +406,7 @@ def main():
                 loss.backward()
             if sync is not None:          # DDP gradient averaging; the experts' bucket already travels since mid-backward
                 sync.finish()
-            step.last = (gf, probs)
+            step.last = (gf.detach(), probs.detach())      # detached: nothing may keep this step's autograd graph alive
             return loss
         return step
 
@@ -458,6 +458,9 @@ def main():
         if i == 0:
             first_loss = l0.detach().clone()
             first_gf, first_probs = step.last[0].detach().clone(), step.last[1].detach().clone()
+        # nothing may keep an eager step's autograd graph alive: its AccumulateGrad nodes belong to the default stream and would
+        # make the capture below depend on it (cudaErrorStreamCaptureImplicit)
+        del l0
     barrier()
 
     # ---------------- N > 1: first-step loss against a single-process recomputation on gathered inputs ----------------
