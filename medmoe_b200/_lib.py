@@ -42,6 +42,9 @@ SIGNATURES = {
                                       c_vp, c_vp]),
     "mm_grouped_gemm_wgrad_colsum": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                              c_vp, c_vp, c_vp]),
+    "mm_expert_b2b_fwd_supported": (c_int, [c_int, c_int, c_int]),
+    "mm_expert_b2b_fwd": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_int, c_ll, c_vp, c_vp, c_int,
+                                  c_int, c_vp, c_ll, c_vp, c_ll, c_vp]),
     "mm_combine_num_token_blocks": (c_int, [c_int]),
     "mm_combine_num_row_blocks": (c_int, [c_vp]),
     "mm_combine_num_runs": (c_int, [c_int]),
@@ -91,7 +94,7 @@ SIGNATURES = {
 _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_version", "mm_device_sm_count", "mm_launch_count", "mm_combine_num_token_blocks",
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats",
                 "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported",
-                "mm_infonce_fused_supported", "mm_infonce_fused_workspace_bytes",
+                "mm_infonce_fused_supported", "mm_infonce_fused_workspace_bytes", "mm_expert_b2b_fwd_supported",
                 "mm_debug_force_cuda_core_dut", "mm_debug_gemm_pair"}
 
 

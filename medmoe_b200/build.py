@@ -19,7 +19,7 @@ LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libmedmoe_b200.so"
 OBJ_DIR = PKG / "build"
 
-SOURCES = ["api_core.cu", "router.cu", "dispatch.cu", "combine.cu", "loss.cu", "infonce_fused.cu", "local_loss.cu"]
+SOURCES = ["api_core.cu", "b2b.cu", "router.cu", "dispatch.cu", "combine.cu", "loss.cu", "infonce_fused.cu", "local_loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -64,8 +64,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         return obj
 
+    # MEDMOE_BUILD_ONLY="b2b.cu,..." (tuning experiments): recompile just these, reuse the other objects of the last build
+    only = [x for x in os.environ.get("MEDMOE_BUILD_ONLY", "").split(",") if x]
+
+    def compile_or_reuse(src: str) -> Path:
+        obj = OBJ_DIR / (src + ".o")
+        return obj if only and src not in only and obj.exists() else compile_one(src)
+
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+        objs = list(ex.map(compile_or_reuse, SOURCES))
     # static cudart: the library must load (and export its symbols) on a box without a driver
     link = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static",
             "-gencode", "arch=compute_100a,code=sm_100a"]

@@ -1,0 +1,79 @@
+// medmoe_b200 — C-ABI of the back-to-back expert GEMM kernels (b2b.cuh).  Contract: include/medmoe_b200.h.
+#include "api_internal.h"
+#include "b2b.cuh"
+
+using namespace mm;
+
+namespace {
+
+template <int NKB1>
+int launch_b2b_fwd(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtensorMap& tB2, const CUtensorMap& tY,
+                   const CUtensorMap& tZ, const B2BFwdArgs& args, cudaStream_t st) {
+    using S = B2BSmem<NKB1>;
+    static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = b2b_fwd_kernel<NKB1>;
+    static bool configured_dev[64];
+    bool& configured = *per_device_flag(configured_dev);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("expert_b2b_fwd: cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            return MM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int grid = args.tile_count < sm_count() ? args.tile_count : sm_count();
+    if (grid <= 0) return MM_OK;
+    kern<<<grid, B2B_THREADS, S::TOTAL, st>>>(tA1, tB1, tB2, tY, tZ, args);
+    note_launches(1);
+    return check_launch("expert_b2b_fwd");
+}
+
+}  // namespace
+
+// 1 when mm_expert_b2b_fwd covers this shape (otherwise run the two GEMMs separately through mm_grouped_gemm_rows)
+extern "C" int mm_expert_b2b_fwd_supported(int K1, int D, int H) {
+    return (D == B2B_D && H == B2B_H && K1 > 0 && K1 % 16 == 0 && K1 <= 128) ? 1 : 0;
+}
+
+// Y = ReLU(f Wp_e^T + bp_e) (bf16, written once) and Z = Y W1_e^T + b1_e (bf16) over the 128-row tiles
+// [tile_begin, tile_begin + tile_count) of one scale region; f / Y / Z point at the region's first row.
+extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
+                                 long long ldwp, const float* bias1, const void* W1, int H, long long ldw1,
+                                 const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
+                                 long long ld_y, void* Z, long long ld_z, void* stream) {
+    MM_REQUIRE(f && Wp && W1 && bias1 && bias2 && tile_info && Y && Z, MM_ERR_BAD_SHAPE, "mm_expert_b2b_fwd: null operand");
+    MM_REQUIRE(mm_expert_b2b_fwd_supported(K1, D, H), MM_ERR_UNSUPPORTED,
+               "mm_expert_b2b_fwd: needs D = 768, H = 384 and K1 a multiple of 16 up to 128");
+    if (tile_count <= 0) return MM_OK;
+    const uint64_t io_rows = static_cast<uint64_t>(tile_count) * TILE_M;
+    CUtensorMap tA1, tB1, tB2, tY, tZ;
+    int rc = encode_tmap_bf16(&tA1, f, static_cast<uint64_t>(K1), static_cast<uint64_t>(f_rows), static_cast<uint64_t>(ldf), 64,
+                              TILE_M, "mm_expert_b2b_fwd(f)");
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tB1, Wp, static_cast<uint64_t>(K1), static_cast<uint64_t>(E) * D, static_cast<uint64_t>(ldwp), 64,
+                          B2B_NC, "mm_expert_b2b_fwd(Wp)");
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tB2, W1, static_cast<uint64_t>(D), static_cast<uint64_t>(E) * H, static_cast<uint64_t>(ldw1), 64,
+                          B2B_H / 2, "mm_expert_b2b_fwd(W1)");
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tY, Y, static_cast<uint64_t>(D), io_rows, static_cast<uint64_t>(ld_y), 64, TILE_M,
+                          "mm_expert_b2b_fwd(Y)");
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tZ, Z, static_cast<uint64_t>(H), io_rows, static_cast<uint64_t>(ld_z), 64, TILE_M,
+                          "mm_expert_b2b_fwd(Z)");
+    if (rc) return rc;
+    B2BFwdArgs g;
+    g.tile_info = reinterpret_cast<const int2*>(tile_info);
+    g.tile_begin = tile_begin;
+    g.tile_count = tile_count;
+    g.K1 = K1;
+    g.bias1 = bias1;
+    g.bias2 = bias2;
+    g.y = static_cast<__nv_bfloat16*>(Y);
+    g.ld_y = ld_y;
+    g.z = static_cast<__nv_bfloat16*>(Z);
+    g.ld_z = ld_z;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return K1 <= 64 ? launch_b2b_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st) : launch_b2b_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st);
+}

@@ -118,6 +118,20 @@ MM_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (mbarrier.test_wait): for roles that poll several barriers in turn
+MM_DEVINL bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug must become a trap (reported as a CUDA error by the
 // C-ABI), never a hung GPU box.
 MM_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -99,15 +99,29 @@ class _ExpertsFunction(torch.autograd.Function):
 
         Y = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
         Z = torch.empty(layout.total_rows, H, dtype=torch.bfloat16, device=dev)
-        def e1(s):   # E1: Y_s = ReLU(f_s W_s^T + b_s)
+        # E1: Y_s = ReLU(f_s W_s^T + b_s);  E4 at native resolution: Z = Y W1^T + b1 (the lerp commutes with the affine map).
+        # Narrow scales run both in ONE back-to-back kernel (Y never re-read); the others as two grouped GEMMs, with E4
+        # as a single launch over the contiguous tile range the fused kernel did not cover.
+        fused_s = [s for s in range(S) if ops.expert_b2b_supported(widths[s], D, H)]
+        n_fused = 0
+        while n_fused < S and n_fused in fused_s:      # a prefix of the regions, so that the rest stays one tile range
+            n_fused += 1
+        for s in range(n_fused):
+            r0, nr = layout.region_base[s], layout.region_rows[s]
+            ops.expert_b2b_fwd(fs[s], Wp[s], bp[s], W1, b1, Y[r0:r0 + nr], Z[r0:r0 + nr], plan=plan,
+                               tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"E1E4.s{s}")
+
+        def e1(s):
             r0 = layout.region_base[s]
             return lambda: ops.gemm_rows(fs[s], Wp[s], D, Y[r0:r0 + layout.region_rows[s]], plan=plan,
                                          tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], bias=bp[s],
                                          flags=ops.EPI_RELU | ops.EPI_ZERO_PAD, tag=f"E1.s{s}")
-        ops.run_scales([e1(s) for s in range(S)])
-        # E4 at native resolution: Z = Y W1^T + b1 (the lerp commutes with the affine map)
-        ops.gemm_rows(Y, W1, H, Z, plan=plan, tile_begin=0, tile_count=layout.total_tiles, bias=b1, flags=ops.EPI_ZERO_PAD,
-                      tag="E4")
+        ops.run_scales([e1(s) for s in range(n_fused, S)])
+        if n_fused < S:
+            t0 = layout.tile_base[n_fused]
+            r0 = layout.region_base[n_fused]
+            ops.gemm_rows(Y[r0:], W1, H, Z[r0:], plan=plan, tile_begin=t0, tile_count=layout.total_tiles - t0, bias=b1,
+                          flags=ops.EPI_ZERO_PAD, tag="E4")
         gate_flat = gate.reshape(-1).float().contiguous() if gate is not None else None
         fused, gfeat, beta = ops.combine_fwd(Y, Z, w2, b2, plan, D, gate_flat, in_dtype)
 

@@ -279,3 +279,73 @@ def test_pair_rows_gemm_grouped_256_row_segments(pair_mode):
         ref = torch.relu(A[t * 128: t * 128 + v].float() @ Wf[e].t() + bias[e])
         assert (blk[v:] == 0).all()
         assert (blk[:v] - ref).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
+
+
+# ---- back-to-back expert GEMMs (csrc/b2b.cuh): E1 -> E4 in one kernel -------------------------------------------------
+def _b2b_case(n_items, E, P, K1, seed, idle_expert=False):
+    from medmoe_b200 import ops
+    D, H = 768, 384
+    g = torch.Generator().manual_seed(seed)
+    item_expert = torch.randint(1 if idle_expert else 0, E, (n_items,), generator=g, dtype=torch.int32)
+    layout = mmplan.make_layout(n_items, 1, E, P, target_chunks=4)
+    plan = mmplan.build_plan(item_expert.cuda(), layout)
+    rows = layout.total_rows
+    row_e = _row_expert(layout, plan)
+    f = _bf16(rows, K1, seed=seed + 1)
+    f[row_e < 0] = 0
+    Wp = _bf16(E * D, K1, scale=K1 ** -0.5, seed=seed + 2)
+    W1 = _bf16(E * H, D, scale=D ** -0.5, seed=seed + 3)
+    bp = torch.randn(E, D, device="cuda")
+    b1 = torch.randn(E, H, device="cuda")
+    Y = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    Z = torch.full((rows, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    assert _lib.call("mm_expert_b2b_fwd_supported", K1, D, H) == 1
+    ops.expert_b2b_fwd(f, Wp, bp, W1, b1, Y, Z, plan=plan, tile_begin=0, tile_count=layout.total_tiles)
+    torch.cuda.synchronize()
+    return layout, plan, row_e, f, Wp, W1, bp, b1, Y, Z
+
+
+@pytest.mark.parametrize("K1", [96, 64, 128, 32])
+@pytest.mark.parametrize("idle", [False, True])
+def test_b2b_forward_bit_identical_to_the_two_gemms(K1, idle):
+    """The fused kernel runs the same MMAs in the same k order on the same bf16-rounded Y: Y and Z must be bit-identical
+    to mm_grouped_gemm_rows(E1) followed by mm_grouped_gemm_rows(E4), including zeroed padding rows and unowned tiles."""
+    D, H = 768, 384
+    layout, plan, row_e, f, Wp, W1, bp, b1, Y, Z = _b2b_case(41, 4, [196, 49], K1, seed=30 + K1, idle_expert=idle)
+    rows = layout.total_rows
+    Y2 = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    Z2 = torch.full((rows, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm_rows(f, Wp, D, tile_info=plan.tile_info, tile_begin=0, tile_count=layout.total_tiles, bias=bp, out=Y2,
+              flags=EPI_RELU | EPI_ZERO_PAD)
+    gemm_rows(Y2, W1, H, tile_info=plan.tile_info, tile_begin=0, tile_count=layout.total_tiles, bias=b1, out=Z2,
+              flags=EPI_ZERO_PAD)
+    assert torch.isfinite(Y.float()).all() and torch.isfinite(Z.float()).all()      # every tile written, owned or not
+    assert torch.equal(Y.view(torch.int16), Y2.view(torch.int16))
+    assert torch.equal(Z.view(torch.int16), Z2.view(torch.int16))
+    assert (Y[row_e < 0] == 0).all() and (Z[row_e < 0] == 0).all()
+
+
+def test_b2b_forward_vs_fp32_matmul():
+    D, H, E, K1 = 768, 384, 3, 96
+    layout, plan, row_e, f, Wp, W1, bp, b1, Y, Z = _b2b_case(23, E, [784, 196], K1, seed=77)
+    Wpf, W1f = Wp.float().view(E, D, K1), W1.float().view(E, H, D)
+    for e in range(E):
+        m = row_e == e
+        y_ref = torch.relu(f[m].float() @ Wpf[e].t() + bp[e])
+        assert (Y[m].float() - y_ref).abs().max().item() <= 2 ** -7 * max(1.0, y_ref.abs().max().item())
+        z_ref = Y[m].float() @ W1f[e].t() + b1[e]            # GEMM 2 consumes the bf16-rounded Y, like the unfused path
+        assert (Z[m].float() - z_ref).abs().max().item() <= 2 ** -7 * max(1.0, z_ref.abs().max().item())
+
+
+def test_b2b_forward_many_tiles_per_cta():
+    """More tiles than SMs: every CTA walks several tiles, so the barrier phases wrap many times."""
+    layout, plan, row_e, f, Wp, W1, bp, b1, Y, Z = _b2b_case(24, 4, [3136], 96, seed=5)
+    assert layout.total_tiles >= 4 * 148
+    E, D, H, K1 = 4, 768, 384, 96
+    Wpf, W1f = Wp.float().view(E, D, K1), W1.float().view(E, H, D)
+    for e in range(E):
+        m = row_e == e
+        y_ref = torch.relu(f[m].float() @ Wpf[e].t() + bp[e])
+        assert (Y[m].float() - y_ref).abs().max().item() <= 2 ** -7 * max(1.0, y_ref.abs().max().item())
+        z_ref = Y[m].float() @ W1f[e].t() + b1[e]
+        assert (Z[m].float() - z_ref).abs().max().item() <= 2 ** -7 * max(1.0, z_ref.abs().max().item())
