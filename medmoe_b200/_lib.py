@@ -99,6 +99,9 @@ _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_
 
 
 def library_path() -> Path:
+    import os
+    if os.environ.get("MEDMOE_LIB"):      # tuning experiments only: a variant built with MEDMOE_LIB_OUT (medmoe_b200/build.py)
+        return Path(os.environ["MEDMOE_LIB"]).resolve()
     return Path(__file__).resolve().parent / "lib" / "libmedmoe_b200.so"
 
 

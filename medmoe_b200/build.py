@@ -54,8 +54,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     nvcc = _nvcc()
 
+    variant = bool(os.environ.get("MEDMOE_LIB_OUT"))
+
     def compile_one(src: str) -> Path:
-        obj = OBJ_DIR / (src + ".o")
+        obj = OBJ_DIR / (src + (".variant.o" if variant else ".o"))      # a variant never overwrites the product's objects
         cmd = [nvcc, *NVCC_FLAGS, "-I", str(CSRC), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
@@ -74,13 +76,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_or_reuse, SOURCES))
     # static cudart: the library must load (and export its symbols) on a box without a driver
-    link = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-cudart", "static",
+    # MEDMOE_LIB_OUT=path (tuning experiments): link a variant library next to the product one; load it with MEDMOE_LIB=path
+    out = Path(os.environ["MEDMOE_LIB_OUT"]).resolve() if os.environ.get("MEDMOE_LIB_OUT") else LIB_PATH
+    out.parent.mkdir(parents=True, exist_ok=True)
+    link = [nvcc, "-shared", "-o", str(out), *map(str, objs), "-cudart", "static",
             "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    stamp.write_text(digest)
-    return LIB_PATH
+    if out == LIB_PATH:
+        stamp.write_text(digest)
+    return out
 
 
 if __name__ == "__main__":
