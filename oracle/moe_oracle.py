@@ -133,6 +133,34 @@ def expert_forward_as_written(params: Params, e: int, feats: List[torch.Tensor])
     return (stacked * beta.unsqueeze(-1)).sum(dim=2)                                       # [B, P, D]
 
 
+def _stored(x: torch.Tensor, dtype) -> torch.Tensor:
+    """Value as it reads back from a `dtype` buffer; the rounding is invisible to autograd (straight-through)."""
+    return x if dtype is None else x + (x.to(dtype).to(x.dtype) - x).detach()
+
+
+def expert_forward_storage_aware(params: Params, e: int, feats: List[torch.Tensor], storage=torch.bfloat16) -> torch.Tensor:
+    """The closed form below with the two HBM storage points of the CUDA path made explicit: Y = ReLU(conv) and
+    Z = Y W1^T + b1 (first attention Linear, evaluated at native resolution because the lerp commutes with the affine map)
+    are rounded to `storage` before they are interpolated.  The ReLU gate of the attention hidden layer is then decided on
+    the same values the kernels see, which is what the gradient of attn_proj.0 is sensitive to (tests/test_moe_gpu.py:
+    a unit within bf16 rounding of zero flips its gate, a 100 % error on that entry).  Mathematically identical to
+    `expert_forward_closed_form` for storage=None."""
+    P = max(f.shape[1] for f in feats)
+    W1, b1 = params[f"experts.{e}.attn_proj.0.weight"], params[f"experts.{e}.attn_proj.0.bias"]
+    us, hs = [], []
+    for s, f in enumerate(feats):
+        w = params[f"experts.{e}.proj_convs.{s}.0.weight"].squeeze(-1)
+        y = _stored(torch.relu(f @ w.t() + params[f"experts.{e}.proj_convs.{s}.0.bias"]), storage)   # [B, P_s, D]
+        z = _stored(y @ W1.t() + b1, storage)                                                       # [B, P_s, H]
+        us.append(lerp_rows(y, P))
+        hs.append(torch.relu(lerp_rows(z, P)))
+    U = torch.stack(us, dim=2)                                                             # [B, P, S, D]
+    h = torch.stack(hs, dim=2)                                                             # [B, P, S, H]
+    logit = (h @ params[f"experts.{e}.attn_proj.2.weight"].t()).squeeze(-1) + params[f"experts.{e}.attn_proj.2.bias"]
+    beta = torch.softmax(logit, dim=-1)
+    return (U * beta.unsqueeze(-1)).sum(dim=2)
+
+
 def expert_forward_closed_form(params: Params, e: int, feats: List[torch.Tensor]) -> torch.Tensor:
     """Same expert with the projection as a matmul and the interpolation in closed form
     (token-major throughout, no [B, D, P] transposes) — the schedule the CUDA path restates."""
@@ -170,9 +198,10 @@ def moe_forward_dense(params: Params, feats: List[torch.Tensor], swin_feat: torc
 
 
 def moe_forward_sparse(params: Params, feats: List[torch.Tensor], swin_feat: torch.Tensor, topk: int = 1,
-                       closed_form: bool = True):
+                       closed_form: bool = True, storage=None):
     """Route first, run only the selected experts on their images.  topk > 1 is the documented
-    extension: fused = sum_j g_j * expert_{idx_j}(x), g = renormalised top-k probabilities."""
+    extension: fused = sum_j g_j * expert_{idx_j}(x), g = renormalised top-k probabilities.
+    `storage=torch.bfloat16` evaluates the experts with the CUDA path's storage points (expert_forward_storage_aware)."""
     probs = router_probs(params, swin_feat)
     idx, gate = topk_gate(probs, topk)
     if topk > 1:
@@ -183,6 +212,8 @@ def moe_forward_sparse(params: Params, feats: List[torch.Tensor], swin_feat: tor
     D = params["experts.0.attn_proj.0.weight"].shape[1]
     fused = torch.zeros(B, P, D, dtype=feats[0].dtype)
     run = expert_forward_closed_form if closed_form else expert_forward_as_written
+    if storage is not None:
+        run = lambda p_, e_, f_: expert_forward_storage_aware(p_, e_, f_, storage)      # noqa: E731
     for e in range(num_experts_of(params)):
         for j in range(topk):
             rows = (idx[:, j] == e).nonzero().flatten()

@@ -184,3 +184,36 @@ def test_aggregate_tokens_on_cuda_matches_reference_golden():
     # the aggregated word embeddings feed the local loss as [B, D, L]: sum of the last layers, like text_encoder.py:119-127
     words = got.sum(1).permute(0, 2, 1).contiguous()
     assert words.shape == (emb.shape[0], emb.shape[3], emb.shape[2])
+
+
+def test_attn_proj0_gradient_against_storage_aware_oracle():
+    """the 1e-1 bound on the attn_proj.0 (W1, b1) gradients.  The whole gap to the fp32 oracle is the ReLU
+    gate of the attention hidden layer being decided on bf16-STORED Z (and bf16-stored Y feeding it): against the oracle that
+    rounds at the same two storage points (`expert_forward_storage_aware`; rounding is straight-through for autograd) the same
+    gradients agree ten times tighter.  Both errors are printed (`pytest -s`) and recorded in DESIGN.md §2."""
+    K, Ps, B = 4, [3136, 784, 196, 49], 6
+    params = _bf16_params(K, seed=131)
+    torch.manual_seed(132)
+    feats = [torch.randn(B, p, d).to(torch.bfloat16).float() for p, d in zip(Ps, HID)]
+    sw, cg = torch.randn(B, D), torch.randn(B, D)
+    cl = torch.randn(B, D, 56, 56) / 3136
+    ref = {}
+    for name, storage in (("fp32", None), ("stored", torch.bfloat16)):
+        pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        (gf, lf, _), idx = mo.moe_forward_sparse(pr, [f.clone() for f in feats], sw.clone(), storage=storage)
+        ((gf * cg).sum() + (lf * cl).sum()).backward()
+        ref[name] = {k: v.grad for k, v in pr.items()}
+    moe = _module_from(params, K, HID, D)
+    gf2, lf2, _ = moe([f.cuda() for f in feats], sw.cuda())
+    ((gf2 * cg.cuda()).sum() + (lf2 * cl.cuda()).sum()).backward()
+    used = set(idx.flatten().tolist())
+    worst = {"fp32": 0.0, "stored": 0.0}
+    for k, p in moe.named_parameters():
+        if ".attn_proj.0." not in k or int(k.split(".")[1]) not in used:
+            continue
+        for name in worst:
+            worst[name] = max(worst[name], rel_err(p.grad.cpu(), ref[name][k]))
+    print(f"\nattn_proj.0 gradient, worst norm-wise error over experts: vs fp32 oracle {worst['fp32']:.4f}, "
+          f"vs storage-aware oracle {worst['stored']:.4f}")
+    assert worst["fp32"] < TIGHT["attn0"]
+    assert worst["stored"] < 2e-2
