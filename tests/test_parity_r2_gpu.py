@@ -216,4 +216,4 @@ def test_attn_proj0_gradient_against_storage_aware_oracle():
     print(f"\nattn_proj.0 gradient, worst norm-wise error over experts: vs fp32 oracle {worst['fp32']:.4f}, "
           f"vs storage-aware oracle {worst['stored']:.4f}")
     assert worst["fp32"] < TIGHT["attn0"]
-    assert worst["stored"] < 2e-2
+    assert worst["stored"] < 1e-2      # measured 1.5e-3 (vs 1.9e-2 against the fp32 oracle)
