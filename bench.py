@@ -268,10 +268,19 @@ def load_traffic_table():
         except OSError:
             continue
         seen = {}
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+        def col_bytes(r, prefix):      # ncu picks the unit per column: "dram_read [Mbyte]" / "[Gbyte]" ...
+            for k, v in r.items():
+                m = re.match(re.escape(prefix) + r" \[(\w+)\]$", k)
+                if m:
+                    return float(v) * unit[m.group(1)]
+            raise KeyError(prefix)
+
         for r in rows:
             try:
                 name = r["kernel"]
-                byts = (float(r["dram_read [Gbyte]"]) + float(r["dram_write [Gbyte]"])) * 1e9
+                byts = col_bytes(r, "dram_read") + col_bytes(r, "dram_write")
             except (KeyError, ValueError):
                 continue
             key = re.sub(r"\s+", "", name.replace("void ", "").replace("mm::", ""))
@@ -340,7 +349,10 @@ def main():
     if args.loss == "flava":
         loss_mod.return_logits = False       # nothing in a training step reads the logit matrices: they stay on chip
     params = [p for p in list(moe.parameters()) + list(loss_mod.parameters())]
-    sync = medmoe_b200.OverlappedGradSync(moe, other_params=list(loss_mod.parameters())) if world > 1 else None
+    # MEDMOE_BENCH_NO_GRADSYNC=1 (diagnostic only, never a bench number: the step is then not data-parallel training) leaves the
+    # gradient all-reduce out, to see what it costs
+    sync = medmoe_b200.OverlappedGradSync(moe, other_params=list(loss_mod.parameters())) \
+        if world > 1 and not os.environ.get("MEDMOE_BENCH_NO_GRADSYNC") else None
 
     # synthetic batch (seed 12345 + rank, the reference's seed, pretraining_medmoe.yaml:18), pinned on the host
     g = torch.Generator().manual_seed(12345 + rank)
@@ -776,6 +788,10 @@ def main():
             "hbm_bytes_per_step": bytes_per_step,
             "kernels": kernels, "kernel_ms_per_step": total_kernel_ms / args.steps, "loss": float(loss.detach()),
             "first_step_loss": float(first_loss), "multi_rank_loss_check": loss_check, "also": also,
+            # how the ranks exchanged data: embeddings of the InfoNCE ("p2p" = the library's NVLink peer-memory kernels,
+            # csrc/p2p.cu; "nccl"; "none" at N = 1), parameter gradients (NCCL all-reduce overlapped with the backward)
+            "exchange": {"embeddings": medmoe_b200.distributed.PeerExchange.last_backend,
+                         "grad_sync": "overlapped_nccl_all_reduce" if sync is not None else "none"},
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu

@@ -278,6 +278,28 @@ int mm_l2_normalize_bwd(const float* dy, const float* y, const float* norms, int
 int mm_zeroshot_argmax(const float* img, const float* txt, int M, int C, int D, float eps, long long* pred, float* sim,
                        void* stream);
 
+/* ---- embedding exchange over NVLink peer memory (csrc/p2p.cu): the all-gather / reduce-scatter pair of
+ * reference src/utils/distributed.py:28-58 (torch.distributed.nn.functional.all_gather and its backward) as used by
+ * src/losses.py:503-524, for the ranks of ONE node (world <= 8), without NCCL: peer stores / peer loads + system-scope
+ * flags.  Every rank allocates one workspace of mm_p2p_workspace_bytes(world, bytes_per_rank) with mm_p2p_alloc, ships
+ * the 64-byte CUDA IPC handle to its peers (any host channel) and maps theirs with mm_p2p_open; peer_bufs is a HOST
+ * array of `world` device pointers (entry `rank` = the own workspace).  Calls must be made by all ranks in the same
+ * order; step counters live in the workspace and are advanced on the device (CUDA-graph replay safe).
+ *   mm_p2p_all_gather:          src [bytes_per_rank] -> dst [world * bytes_per_rank], block q = rank q's src
+ *   mm_p2p_reduce_scatter_f32:  grad fp32 [world * bytes_per_rank] -> out [bytes_per_rank] = sum_q grad_q[block rank]
+ *                               (ranks summed in ascending order: deterministic)
+ * bytes_per_rank must be a multiple of 16 and the same in every call on a workspace.  A rank that waits ~10 s for a
+ * peer traps (sticky CUDA error) instead of hanging. */
+long long mm_p2p_workspace_bytes(int world, long long bytes_per_rank);
+int mm_p2p_alloc(long long bytes, void** ptr_out, void* handle_out);
+int mm_p2p_open(const void* handle, void** ptr_out);
+int mm_p2p_close(void* ptr);
+int mm_p2p_free(void* ptr);
+int mm_p2p_all_gather(const void* src, void* dst, long long bytes_per_rank, void* const* peer_bufs, int rank, int world,
+                      void* stream);
+int mm_p2p_reduce_scatter_f32(const void* grad, void* out, long long bytes_per_rank, void* const* peer_bufs, int rank,
+                              int world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,13 @@ SIGNATURES = {
     "mm_l2_normalize_fwd": (c_int, [c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "mm_l2_normalize_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp]),
     "mm_zeroshot_argmax": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
+    "mm_p2p_workspace_bytes": (c_ll, [c_int, c_ll]),
+    "mm_p2p_alloc": (c_int, [c_ll, c_vp, c_vp]),
+    "mm_p2p_open": (c_int, [c_vp, c_vp]),
+    "mm_p2p_close": (c_int, [c_vp]),
+    "mm_p2p_free": (c_int, [c_vp]),
+    "mm_p2p_all_gather": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_vp]),
+    "mm_p2p_reduce_scatter_f32": (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_vp]),
 }
 
 # entry points that return a plain value, not an mm_status
@@ -95,7 +102,7 @@ _VALUE_FUNCS = {"mm_trace_enable", "mm_trace_collect", "mm_last_error", "mm_abi_
                 "mm_combine_num_row_blocks", "mm_combine_num_runs", "mm_combine_num_part_blocks", "mm_combine_bwd_z_scratch_floats", "mm_gloria_workspace_floats",
                 "mm_combine_bwd_global_supported", "mm_combine_bwd_tc_supported",
                 "mm_infonce_fused_supported", "mm_infonce_fused_workspace_bytes", "mm_expert_b2b_fwd_supported",
-                "mm_debug_force_cuda_core_dut", "mm_debug_gemm_pair"}
+                "mm_debug_force_cuda_core_dut", "mm_debug_gemm_pair", "mm_p2p_workspace_bytes"}
 
 
 def library_path() -> Path:

@@ -19,7 +19,7 @@ LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libmedmoe_b200.so"
 OBJ_DIR = PKG / "build"
 
-SOURCES = ["api_core.cu", "b2b.cu", "router.cu", "dispatch.cu", "combine.cu", "loss.cu", "infonce_fused.cu", "local_loss.cu"]
+SOURCES = ["api_core.cu", "b2b.cu", "router.cu", "dispatch.cu", "combine.cu", "loss.cu", "infonce_fused.cu", "local_loss.cu", "p2p.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

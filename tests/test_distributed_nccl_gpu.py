@@ -60,6 +60,51 @@ def _worker(rank, port, out_dir):
         assert rel(t_loc.grad, tr.grad[rank * B:(rank + 1) * B]) < 1e-4
         assert abs(mod.logit_scale.grad.item() - sr.grad.item()) < 1e-4 * max(1.0, abs(sr.grad.item()))
 
+        # ---- the exchange ran over NVLink peer memory (csrc/p2p.cu), and that path equals the NCCL collectives bit for bit
+        #      (two ranks: the sum of two floats has one order), eagerly and under CUDA-graph replay ----
+        from medmoe_b200 import distributed as mmd
+        assert mmd.PeerExchange.last_backend == "p2p", mmd.PeerExchange._disabled_reason
+        xs = torch.zeros(B, 2 * D, device=dev, requires_grad=True)
+        gs = torch.zeros(WORLD * B, 2 * D, device=dev)
+
+        def exchange():
+            y = mmd.all_gather_cat(xs)
+            (dx,) = torch.autograd.grad(y, xs, gs)
+            return y, dx
+
+        def fill(it):
+            gx = torch.Generator().manual_seed(1000 + 10 * it + rank)
+            xs.data.copy_(torch.randn(B, 2 * D, generator=gx))
+            gs.copy_(torch.randn(WORLD * B, 2 * D, generator=gx))
+
+        def check(y, dx, what):
+            ref_y = torch.empty_like(gs)
+            dist.all_gather_into_tensor(ref_y, xs.detach())
+            ref_dx = torch.empty(B, 2 * D, device=dev)
+            dist.reduce_scatter_tensor(ref_dx, gs.clone(), op=dist.ReduceOp.SUM)
+            assert torch.equal(y, ref_y), what
+            assert torch.equal(dx, ref_dx), what
+        for it in range(3):
+            fill(it)
+            check(*exchange(), f"eager {it}")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            exchange()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y_s, dx_s = exchange()
+        for it in range(5):                        # the device-side step counters keep the parity right across replays
+            fill(100 + it)
+            graph.replay()
+            check(y_s, dx_s, f"replay {it}")
+        os.environ["MEDMOE_P2P_EXCHANGE"] = "0"   # same call through NCCL
+        fill(7)
+        check(*exchange(), "nccl")
+        assert mmd.PeerExchange.last_backend == "nccl"
+        os.environ["MEDMOE_P2P_EXCHANGE"] = "1"
+
         # ---- mask path over NCCL: mean over the selected local rows (losses.py:574-577) ----
         m_loc = mask_all[rank * B:(rank + 1) * B]
         ref_m = lo.contrastive_loss_with_temperature(ia[rank * B:(rank + 1) * B].detach(), tb[rank * B:(rank + 1) * B].detach(),
