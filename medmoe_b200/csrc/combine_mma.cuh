@@ -435,28 +435,32 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_bytes = c.HB * 256;                          // 128 rows x HB columns of bf16
     const int ac_bytes = ((c.kc + 63) / 64) * 16384;
-    uint8_t* sAc = smem;                                         // [2 tile parities] coarse lerp weights, 128 x kc
-    uint8_t* sB = sAc + 2 * ac_bytes;
+    uint8_t* sAi = smem;                                         // identity, 128 x 128 (two 64-wide k blocks)
+    uint8_t* sAc = sAi + 32768;                                  // coarse lerp weights, 128 x kc
+    uint8_t* sB = sAc + ac_bytes;
     float* s_w2 = reinterpret_cast<float*>(sB + c.stages * stage_bytes);          // [H] of the current expert
     float4* s_x = reinterpret_cast<float4*>(s_w2 + c.H);                           // [2 tile parities][128 tokens]
     uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * TILE_M);
     uint64_t* empty = full + CL_STAGES;
     uint64_t* tfull = empty + CL_STAGES;
     uint64_t* tempty = tfull + CL_MAX_ACC;
-    uint64_t* a_full = tempty + CL_MAX_ACC;      // [2]
-    uint64_t* a_empty = a_full + 2;              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+    uint64_t* a_full = tempty + CL_MAX_ACC;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { tma_prefetch_desc(&tmZ0); tma_prefetch_desc(&tmZ1); tma_prefetch_desc(&tmZ2); tma_prefetch_desc(&tmZ3); }
     if (threadIdx.x == 32) {
         for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < CL_MAX_ACC; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], CM_EPI_WARPS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], CM_COEF_WARPS); mbar_init(&a_empty[s], 1); }
+        mbar_init(a_full, CM_COEF_WARPS);
+        mbar_init(a_empty, 1);
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-    for (int i = threadIdx.x * 16; i < 2 * ac_bytes; i += CM_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x * 16; i < 32768 + ac_bytes; i += CM_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < TILE_M) *reinterpret_cast<__nv_bfloat16*>(sAi + cm_a_off(threadIdx.x, threadIdx.x)) = __float2bfloat16_rn(1.0f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -503,19 +507,32 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
         const uint32_t idesc = make_idesc_bf16(TILE_M, c.HB, 0, 1);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        int it = 0;                            // tiles done by this CTA: coefficient buffer = it & 1
-        const uint64_t dac_base = make_smem_desc(smem_u32(sAc), 16, 1024);
+        uint32_t a_phase = 0;
+        const uint64_t dai = make_smem_desc(smem_u32(sAi), 16, 1024);
+        const uint64_t dac = make_smem_desc(smem_u32(sAc), 16, 1024);
+        const uint64_t db0_base = make_smem_desc(smem_u32(sB), TILE_M * 128, 1024);                         // finest-scale stage: chunks 16 KB apart
         const uint64_t dbc_base = make_smem_desc(smem_u32(sB), static_cast<uint32_t>(c.kc) * 128u, 1024);    // coarse stage: chunks kc rows apart
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
             if (c.tile_info[t].x < 0) continue;
-            const int buf = it & 1;
-            const uint64_t dac = smem_desc_advance(dac_base, buf * ac_bytes);
             for (int h = 0; h < c.n_half; ++h) {
-                // ---- finest scale: no interpolation, so no MMA — the epilogue warps read that stage straight from shared
-                //      memory (and release it); this role only steps over the ring position ----
+                // ---- finest scale: identity x Z_0 tile (the identity block is static: no need to wait for this tile's
+                //      lerp weights yet, so their rebuild hides behind these MMAs) ----
+                mbar_wait(&full[stage], phase);
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                {
+                    const uint32_t d_tmem = tmem_base + acc * c.HB;
+                    cm_issue_mmas(d_tmem, dai, smem_desc_advance(db0_base, stage * stage_bytes), idesc, TILE_M / 16, false);
+                    umma_commit(&empty[stage]);
+                    umma_commit(&tfull[acc]);
+                }
                 if (++stage == c.stages) { stage = 0; phase ^= 1; }
+                if (++acc == c.n_acc) { acc = 0; acc_phase ^= 1; }
                 // ---- coarse scales ----
-                if (h == 0) mbar_wait(&a_full[buf], (it >> 1) & 1);
+                if (h == 0) {
+                    mbar_wait(a_full, a_phase);
+                    a_phase ^= 1;
+                }
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint64_t dbc = smem_desc_advance(dbc_base, stage * stage_bytes);
@@ -533,13 +550,12 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                 }
                 if (++stage == c.stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&a_empty[buf]);
-            ++it;
+            umma_commit(a_empty);
         }
     } else if (warp >= 4 && warp < 4 + CM_COEF_WARPS) {
         // ===================== lerp-weight builders: thread = token m of the tile =====================
         const int m = (warp - 4) * 32 + lane;
-        int it = 0;
+        uint32_t a_phase = 0;
         uint32_t offa[4], offb[4];
         int q0[4];
 #pragma unroll
@@ -570,19 +586,16 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
                     vb[s] = (qa == q0[s] + 1 ? 1.0f - L.lam : 0.f) + (qb == q0[s] + 1 ? L.lam : 0.f);
                 }
             }
-            // two coefficient buffers: the weights of tile i + 1 are built while the MMAs of tile i still read theirs
-            const int buf = it & 1;
-            mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
-            uint8_t* sa = sAc + buf * ac_bytes;
+            mbar_wait(a_empty, a_phase ^ 1);
+            a_phase ^= 1;
 #pragma unroll
             for (int s = 1; s < 4; ++s) {
-                *reinterpret_cast<__nv_bfloat16*>(sa + offa[s]) = __float2bfloat16_rn(va[s]);
-                *reinterpret_cast<__nv_bfloat16*>(sa + offb[s]) = __float2bfloat16_rn(vb[s]);
+                *reinterpret_cast<__nv_bfloat16*>(sAc + offa[s]) = __float2bfloat16_rn(va[s]);
+                *reinterpret_cast<__nv_bfloat16*>(sAc + offb[s]) = __float2bfloat16_rn(vb[s]);
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[buf]);
-            ++it;
+            if (lane == 0) mbar_arrive(a_full);
         }
     } else if (warp >= 4 + CM_COEF_WARPS) {
         // ===================== epilogue: row-wise w2 . ReLU(.) over the accumulator, then the softmax over scales =====================
@@ -592,11 +605,8 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
         const int n_ch = c.HB / 32;
         const int epi_tid = threadIdx.x - (4 + CM_COEF_WARPS) * 32;
         int acc = 0; uint32_t acc_phase = 0;
-        int stage = 0; uint32_t phase = 0;          // this role's view of the operand ring (it consumes the finest-scale stages)
         int cur_e = -1;
         uint32_t parity = 0;
-        const int r_tile = q * 32 + lane;           // this lane's token row of the tile
-        const int units_half = c.HB / 16;           // 16-byte units (8 columns) of a pass that this warp reduces
         for (int t = blockIdx.x; t < c.n_tiles; t += gridDim.x) {
             const int2 ti = c.tile_info[t];
             const int e = ti.x;
@@ -609,32 +619,8 @@ cm_logits_kernel(const __grid_constant__ CUtensorMap tmZ0, const __grid_constant
             }
             float lg[4] = {0.f, 0.f, 0.f, 0.f};
             for (int h = 0; h < c.n_half; ++h) {
-                // ---- finest scale: w2 . ReLU(Z_0[row]) straight from the TMA-staged tile (128-byte rows, SW128: a quarter
-                //      warp reads eight different 16-byte units of eight consecutive rows = all 32 banks, no conflicts) ----
-                {
-                    mbar_wait(&full[stage], phase);
-                    const uint8_t* st = sB + stage * stage_bytes + r_tile * 128;
-                    const float* w2h = s_w2 + h * c.HB;
-                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-                    const int u0 = hsel * units_half;
-#pragma unroll 4
-                    for (int u = u0; u < u0 + units_half; ++u) {
-                        const uint4 z = *reinterpret_cast<const uint4*>(st + (u >> 3) * (TILE_M * 128) + (((u & 7) ^ (r_tile & 7)) << 4));
-                        const float4 wa = *reinterpret_cast<const float4*>(w2h + u * 8);
-                        const float4 wb = *reinterpret_cast<const float4*>(w2h + u * 8 + 4);
-                        p0 = fmaf(fmaxf(bf16lo(z.x), 0.f), wa.x, p0); p1 = fmaf(fmaxf(bf16hi(z.x), 0.f), wa.y, p1);
-                        p2 = fmaf(fmaxf(bf16lo(z.y), 0.f), wa.z, p2); p3 = fmaf(fmaxf(bf16hi(z.y), 0.f), wa.w, p3);
-                        p0 = fmaf(fmaxf(bf16lo(z.z), 0.f), wb.x, p0); p1 = fmaf(fmaxf(bf16hi(z.z), 0.f), wb.y, p1);
-                        p2 = fmaf(fmaxf(bf16lo(z.w), 0.f), wb.z, p2); p3 = fmaf(fmaxf(bf16hi(z.w), 0.f), wb.w, p3);
-                    }
-                    lg[0] += (p0 + p1) + (p2 + p3);
-                    named_bar_sync(2, CM_EPI_WARPS * 32);           // every epilogue warp has read the stage
-                    if (epi_tid == 0) mbar_arrive(&empty[stage]);
-                    if (++stage == c.stages) { stage = 0; phase ^= 1; }
-                    if (++stage == c.stages) { stage = 0; phase ^= 1; }      // the coarse stage belongs to the MMA role
-                }
 #pragma unroll
-                for (int s = 1; s < 4; ++s) {
+                for (int s = 0; s < 4; ++s) {
                     mbar_wait(&tfull[acc], acc_phase);
                     tc_fence_after();
                     const uint32_t t_row = tmem_base + acc * c.HB + (static_cast<uint32_t>(q * 32) << 16);
@@ -715,8 +701,8 @@ static inline bool cl_geometry(const CombineArgs& a, int D, ClArgs& c) {
 }
 
 static inline size_t cl_smem_bytes(const ClArgs& c) {
-    return 2 * static_cast<size_t>((c.kc + 63) / 64) * 16384 + static_cast<size_t>(c.stages) * c.HB * 256 +
-           static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 2 * CL_MAX_ACC + 4) * 8 + 16 + 1024;
+    return 32768 + static_cast<size_t>((c.kc + 63) / 64) * 16384 + static_cast<size_t>(c.stages) * c.HB * 256 +
+           static_cast<size_t>(c.H) * 4 + 2 * TILE_M * 16 + (2 * CL_STAGES + 2 * CL_MAX_ACC + 2) * 8 + 16 + 1024;
 }
 
 // =======================================================================================
