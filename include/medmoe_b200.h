@@ -127,12 +127,14 @@ int mm_grouped_gemm_wgrad_colsum(const void* A, long long a_rows, int N1, long l
  *   Y[rows, D] = ReLU(f[rows, K1] Wp_e[D, K1]^T + bias1_e)      Z[rows, H] = Y W1_e[H, D]^T + bias2_e      (bf16 out)
  * f / Y / Z point at the region's first row; tiles are tile_info[tile_begin .. tile_begin + tile_count).
  * Supported: D = 768, H = 384, K1 % 16 == 0, K1 <= 128 (mm_expert_b2b_fwd_supported); results are bit-identical to the
- * two mm_grouped_gemm_rows launches it replaces. */
+ * two mm_grouped_gemm_rows launches it replaces.
+ * flags & 1: the tiles (2j, 2j + 1) of the launch never belong to two experts (the 256-row segment alignment that
+ * mm_dispatch_build produces) -> CTA pairs (tcgen05 cta_group::2) share every weight tile; same results. */
 int mm_expert_b2b_fwd_supported(int K1, int D, int H);
 int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
                       long long ldwp, const float* bias1, const void* W1, int H, long long ldw1, const float* bias2,
                       const int32_t* tile_info, int tile_begin, int tile_count, void* Y, long long ld_y, void* Z,
-                      long long ld_z, void* stream);
+                      long long ld_z, int flags, void* stream);
 
 /* ---- (4) interpolate + scale-softmax + weighted combine / scatter-back ------------------
  * replaces swin.py:42-80 (F.interpolate, stack/permute, attn_proj[1:], softmax over scales,

@@ -44,7 +44,7 @@ SIGNATURES = {
                                              c_vp, c_vp, c_vp]),
     "mm_expert_b2b_fwd_supported": (c_int, [c_int, c_int, c_int]),
     "mm_expert_b2b_fwd": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_int, c_ll, c_vp, c_vp, c_int,
-                                  c_int, c_vp, c_ll, c_vp, c_ll, c_vp]),
+                                  c_int, c_vp, c_ll, c_vp, c_ll, c_int, c_vp]),
     "mm_combine_num_token_blocks": (c_int, [c_int]),
     "mm_combine_num_row_blocks": (c_int, [c_vp]),
     "mm_combine_num_runs": (c_int, [c_int]),

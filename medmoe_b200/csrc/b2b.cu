@@ -1,10 +1,17 @@
 // medmoe_b200 — C-ABI of the back-to-back expert GEMM kernels (b2b.cuh).  Contract: include/medmoe_b200.h.
+#include <cstdlib>
 #include "api_internal.h"
 #include "b2b.cuh"
 
 using namespace mm;
 
 namespace {
+
+// MEDMOE_B2B_DEBUG (tuning / A-B runs): bit 0 = never use CTA pairs
+int b2b_debug_flags() {
+    static const int v = [] { const char* e = getenv("MEDMOE_B2B_DEBUG"); return e ? atoi(e) : 0; }();
+    return v;
+}
 
 template <int NKB1>
 int launch_b2b_fwd(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtensorMap& tB2, const CUtensorMap& tY,
@@ -29,6 +36,30 @@ int launch_b2b_fwd(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtenso
     return check_launch("expert_b2b_fwd");
 }
 
+template <int NKB1>
+int launch_b2b_pair_fwd(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtensorMap& tB2, const CUtensorMap& tY,
+                        const CUtensorMap& tZ, const B2BFwdArgs& args, cudaStream_t st) {
+    using S = B2BPairSmem<NKB1>;
+    static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = b2b_pair_fwd_kernel<NKB1>;
+    static bool configured_dev[64];
+    bool& configured = *per_device_flag(configured_dev);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("expert_b2b_fwd(pair): cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            return MM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int n_pairs = (args.tile_count + 1) / 2;
+    const int clusters = n_pairs < sm_count() / 2 ? n_pairs : sm_count() / 2;
+    if (clusters <= 0) return MM_OK;
+    kern<<<2 * clusters, B2B_THREADS, S::TOTAL, st>>>(tA1, tB1, tB2, tY, tZ, args);      // __cluster_dims__(2, 1, 1)
+    note_launches(1);
+    return check_launch("expert_b2b_fwd(pair)");
+}
+
 }  // namespace
 
 // 1 when mm_expert_b2b_fwd covers this shape (otherwise run the two GEMMs separately through mm_grouped_gemm_rows)
@@ -41,21 +72,24 @@ extern "C" int mm_expert_b2b_fwd_supported(int K1, int D, int H) {
 extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
                                  long long ldwp, const float* bias1, const void* W1, int H, long long ldw1,
                                  const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
-                                 long long ld_y, void* Z, long long ld_z, void* stream) {
+                                 long long ld_y, void* Z, long long ld_z, int flags, void* stream) {
     MM_REQUIRE(f && Wp && W1 && bias1 && bias2 && tile_info && Y && Z, MM_ERR_BAD_SHAPE, "mm_expert_b2b_fwd: null operand");
     MM_REQUIRE(mm_expert_b2b_fwd_supported(K1, D, H), MM_ERR_UNSUPPORTED,
                "mm_expert_b2b_fwd: needs D = 768, H = 384 and K1 a multiple of 16 up to 128");
     if (tile_count <= 0) return MM_OK;
     const uint64_t io_rows = static_cast<uint64_t>(tile_count) * TILE_M;
+    // flags & 1: the caller guarantees that the tiles (2j, 2j + 1) of this launch never belong to two experts (SEG_ALIGN row
+    // layout) -> CTA pairs (cta_group::2) share every weight tile: each CTA stages half of its rows
+    const bool pairs = (flags & 1) && !(b2b_debug_flags() & 1) && tile_count >= 2;
     CUtensorMap tA1, tB1, tB2, tY, tZ;
     int rc = encode_tmap_bf16(&tA1, f, static_cast<uint64_t>(K1), static_cast<uint64_t>(f_rows), static_cast<uint64_t>(ldf), 64,
                               TILE_M, "mm_expert_b2b_fwd(f)");
     if (rc) return rc;
     rc = encode_tmap_bf16(&tB1, Wp, static_cast<uint64_t>(K1), static_cast<uint64_t>(E) * D, static_cast<uint64_t>(ldwp), 64,
-                          B2B_NC, "mm_expert_b2b_fwd(Wp)");
+                          pairs ? B2B_NC / 2 : B2B_NC, "mm_expert_b2b_fwd(Wp)");
     if (rc) return rc;
     rc = encode_tmap_bf16(&tB2, W1, static_cast<uint64_t>(D), static_cast<uint64_t>(E) * H, static_cast<uint64_t>(ldw1), 64,
-                          B2B_H / 2, "mm_expert_b2b_fwd(W1)");
+                          pairs ? B2B_H / 4 : B2B_H / 2, "mm_expert_b2b_fwd(W1)");
     if (rc) return rc;
     rc = encode_tmap_bf16(&tY, Y, static_cast<uint64_t>(D), io_rows, static_cast<uint64_t>(ld_y), 64, TILE_M,
                           "mm_expert_b2b_fwd(Y)");
@@ -75,5 +109,6 @@ extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long l
     g.z = static_cast<__nv_bfloat16*>(Z);
     g.ld_z = ld_z;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pairs) return K1 <= 64 ? launch_b2b_pair_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st) : launch_b2b_pair_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st);
     return K1 <= 64 ? launch_b2b_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st) : launch_b2b_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st);
 }

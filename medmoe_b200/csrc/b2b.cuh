@@ -22,7 +22,7 @@
 // its two accumulators allow (they are released as soon as the epilogue has read them into registers), so the tensor
 // pipe works on G2(c-1), G2(c-2) while the epilogue converts chunk c.
 #pragma once
-#include "gemm.cuh"
+#include "gemm_pair.cuh"
 
 #ifndef MM_B2B_DBG
 #define MM_B2B_DBG 0      // tuning experiments ("switch parts off"): 1 no Y store, 2 no Z store, 4 no W1 loads, 8 no Wp loads, 16 no f loads,
@@ -424,6 +424,384 @@ b2b_fwd_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+
+// =====================================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster (the two SMs of a TPC) work on the tiles (2j, 2j + 1)
+// of the region — always one expert's (SEG_ALIGN) — and SHARE the weight tiles: each CTA stages half of every Wp chunk
+// (32 of 64 rows) and half of every W1 half chunk (96 of 192 rows), the leader issues one M = 256 MMA per k step that reads
+// both halves, and each CTA keeps the accumulators of its own 128 rows in its own TMEM.  Per SM this halves the bytes that
+// come out of L2 for the weights (the single-CTA kernel re-fetches 0.72 MB of weights per tile) and, with the same shared
+// memory, doubles the latency the operand rings cover (6 Wp chunks and 3 W1 chunks in flight instead of 2 and 2).
+//
+// Barriers (same shared-memory offsets in both CTAs; "L." = the leader's instance, the only one used):
+//   L.a1full, L.b1full[], L.b2full[]   TMA bytes of BOTH CTAs (the leader's producer expects 2x, gemm_pair.cuh)
+//   a1empty, b1empty[], b2empty[]      multicast commits -> each CTA's producer
+//   acc1full[2], acc2full              multicast commits -> each CTA's epilogue
+//   L.acc1empty[2] (2 x 8 warps), L.acc2empty (2 x 16 warps), L.a2pair[] (2 x 8 warps: a Y chunk is in shared memory in both
+//                                      CTAs)   epilogue warps arrive locally (leader) or remotely (peer, default .release.cta form)
+//   a2full[] (8 warps)                 own epilogue -> own store warp;   a2empty[] (2)   multicast commit of GEMM 2 + own store warp
+// A tile no expert owns (second tile of a segment's last pair) runs the protocol with zero valid rows: its epilogue writes zeros.
+// =====================================================================================================================
+constexpr int B2BP_S1 = 6, B2BP_S2 = 6, B2BP_SA2 = 3;
+static_assert(B2B_NCH % B2BP_S1 == 0 && (B2B_NCH / B2BP_S1) % 2 == 0 && (2 * B2B_NCH) % B2BP_S2 == 0 &&
+                  ((2 * B2B_NCH) / B2BP_S2) % 2 == 0 && B2B_NRING % B2BP_SA2 == 0 && (B2B_NRING / B2BP_SA2) % 2 == 0 &&
+                  (B2B_NCH / B2BP_SA2) % 2 == 0,
+              "ring stages and phases are compile-time functions of the chunk index: every ring must wrap an even number of times per tile");
+
+template <int NKB1>
+struct B2BPairSmem {
+    static constexpr int A1_BYTES = NKB1 * 16384;                  // own f tile
+    static constexpr int B1_STAGE = NKB1 * 4096;                   // half of a Wp chunk: 32 rows x 64 k per k block
+    static constexpr int B2_STAGE = (B2B_H / 4) * 128;             // half of a W1 half chunk: 96 rows x 64 k = 12 KB
+    static constexpr int A2_BYTES = 16384;
+    static constexpr int OFF_B1 = A1_BYTES;
+    static constexpr int OFF_B2 = OFF_B1 + B2BP_S1 * B1_STAGE;
+    static constexpr int OFF_A2 = OFF_B2 + B2BP_S2 * B2_STAGE;
+    static constexpr int OFF_BAR = OFF_A2 + B2BP_SA2 * A2_BYTES;
+    static constexpr int N_BARS = 2 + 2 * B2BP_S1 + 2 * B2BP_S2 + 4 + 3 * B2BP_SA2 + 2;
+    static constexpr int TOTAL = OFF_BAR + N_BARS * 8 + 16 + 1024;
+};
+
+template <int NKB1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(B2B_THREADS, 1)
+b2b_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY,
+                    const __grid_constant__ CUtensorMap tmZ, const B2BFwdArgs a) {
+    using S = B2BPairSmem<NKB1>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA1 = smem;
+    uint8_t* sB1 = smem + S::OFF_B1;
+    uint8_t* sB2 = smem + S::OFF_B2;
+    uint8_t* sA2 = smem + S::OFF_A2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+    uint64_t* a1full = bars;
+    uint64_t* a1empty = bars + 1;
+    uint64_t* b1full = bars + 2;               // [S1]
+    uint64_t* b1empty = b1full + B2BP_S1;
+    uint64_t* b2full = b1empty + B2BP_S1;      // [S2]
+    uint64_t* b2empty = b2full + B2BP_S2;
+    uint64_t* acc1full = b2empty + B2BP_S2;    // [2]
+    uint64_t* acc1empty = acc1full + 2;        // [2]
+    uint64_t* a2full = acc1empty + 2;          // [SA2] own epilogue -> own store warp
+    uint64_t* a2pair = a2full + B2BP_SA2;      // [SA2] both CTAs' epilogues -> leader's GEMM-2 issuer
+    uint64_t* a2empty = a2pair + B2BP_SA2;     // [SA2]
+    uint64_t* acc2full = a2empty + B2BP_SA2;
+    uint64_t* acc2empty = acc2full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2empty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+    const int n_pairs = (a.tile_count + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2);
+        tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmZ);
+    }
+    if (threadIdx.x == 32) {
+        mbar_init(a1full, 1); mbar_init(a1empty, 1);
+        for (int s = 0; s < B2BP_S1; ++s) { mbar_init(&b1full[s], 1); mbar_init(&b1empty[s], 1); }
+        for (int s = 0; s < B2BP_S2; ++s) { mbar_init(&b2full[s], 1); mbar_init(&b2empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc1full[s], 1); mbar_init(&acc1empty[s], B2B_EPI_WARPS); }      // 2 CTAs x 8 warps
+        for (int s = 0; s < B2BP_SA2; ++s) {
+            mbar_init(&a2full[s], B2B_EPI_WARPS / 2); mbar_init(&a2pair[s], B2B_EPI_WARPS); mbar_init(&a2empty[s], 2);
+        }
+        mbar_init(acc2full, 1); mbar_init(acc2empty, 2 * B2B_EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    tc_fence_before();
+    cluster_sync_all();                        // both CTAs' barriers exist before anyone signals across
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc2 = tmem_base + 2 * B2B_NC;
+
+    // expert of a pair = expert of its first owned tile; -1 when neither tile is owned
+    auto pair_expert = [&](int pj) {
+        const int t0 = 2 * pj, t1 = 2 * pj + 1;
+        const int e0 = a.tile_info[a.tile_begin + t0].x;
+        if (e0 >= 0) return e0;
+        return t1 < a.tile_count ? a.tile_info[a.tile_begin + t1].x : -1;
+    };
+    auto next_owned = [&](int pj) {
+        while (pj < n_pairs && pair_expert(pj) < 0) pj += pair_step;
+        return pj;
+    };
+    // arrive on the LEADER's instance of a barrier
+    auto arrive_leader = [&](uint64_t* bar) {
+        if (rank == 0) mbar_arrive(bar);
+        else mbar_arrive_cluster(mapa_u32(bar, 0));
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs: own f tile, own halves of the weight chunks) =====================
+        if (elect_one()) {
+            int p1 = next_owned(pair0), c1 = -1;
+            int p2 = p1, i2 = 0;
+            int e1 = p1 < n_pairs ? pair_expert(p1) : 0, e2 = e1;
+            uint32_t a1ph = 0;
+            uint32_t idle = 0;
+            const uint32_t bar_a1 = mapa_u32(a1full, 0);
+            while (p1 < n_pairs || p2 < n_pairs) {
+                bool progressed = false;
+                if (p1 < n_pairs) {
+                    if (c1 < 0) {
+                        if (mbar_test_wait(a1empty, a1ph ^ 1)) {
+                            a1ph ^= 1;
+                            if (rank == 0) mbar_expect_tx(a1full, 2 * NKB1 * 16384);
+                            const int lt = min(2 * p1 + static_cast<int>(rank), a.tile_count - 1);
+#pragma unroll
+                            for (int kb = 0; kb < NKB1; ++kb) tma_load_2d_pair(sA1 + kb * 16384, &tmA1, bar_a1, kb * 64, lt * TILE_M);
+                            c1 = 0; progressed = true;
+                        }
+                    } else {
+                        const int b = c1 % B2BP_S1;
+                        if (mbar_test_wait(&b1empty[b], ((c1 / B2BP_S1) & 1) ^ 1)) {
+                            if (rank == 0) mbar_expect_tx(&b1full[b], 2 * S::B1_STAGE);
+                            const uint32_t bar = mapa_u32(&b1full[b], 0);
+#pragma unroll
+                            for (int kb = 0; kb < NKB1; ++kb)
+                                tma_load_2d_pair(sB1 + b * S::B1_STAGE + kb * 4096, &tmB1, bar, kb * 64,
+                                                 e1 * B2B_D + c1 * B2B_NC + static_cast<int>(rank) * (B2B_NC / 2));
+                            progressed = true;
+                            if (++c1 == B2B_NCH) {
+                                c1 = -1;
+                                p1 = next_owned(p1 + pair_step);
+                                if (p1 < n_pairs) e1 = pair_expert(p1);
+                            }
+                        }
+                    }
+                }
+                if (p2 < n_pairs) {
+                    const int s2 = i2 % B2BP_S2;
+                    if (mbar_test_wait(&b2empty[s2], ((i2 / B2BP_S2) & 1) ^ 1)) {
+                        if (rank == 0) mbar_expect_tx(&b2full[s2], 2 * S::B2_STAGE);
+                        tma_load_2d_pair(sB2 + s2 * S::B2_STAGE, &tmB2, mapa_u32(&b2full[s2], 0), (i2 >> 1) * B2B_NC,
+                                         e2 * B2B_H + (i2 & 1) * (B2B_H / 2) + static_cast<int>(rank) * (B2B_H / 4));
+                        progressed = true;
+                        if (++i2 == 2 * B2B_NCH) {
+                            i2 = 0;
+                            p2 = next_owned(p2 + pair_step);
+                            if (p2 < n_pairs) e2 = pair_expert(p2);
+                        }
+                    }
+                }
+                if (progressed) idle = 0;
+                else if (++idle > (1u << 27)) __trap();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer, GEMM 2 (leader CTA only): Z += Y_chunk W1_chunk^T on both CTAs' rows =====================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc2 = make_idesc_bf16(2 * TILE_M, B2B_H / 2, 0, 0);
+            const uint64_t db2 = make_smem_desc(smem_u32(sB2), 16, 1024);
+            const uint64_t da2 = make_smem_desc(smem_u32(sA2), 16, 1024);
+            uint32_t acc2e_ph = 0;
+            for (int pj = pair0; pj < n_pairs; pj += pair_step) {
+                if (pair_expert(pj) < 0) continue;
+                mbar_wait(acc2empty, acc2e_ph ^ 1); acc2e_ph ^= 1;
+#pragma unroll
+                for (int c = 0; c < B2B_NCH; ++c) {
+                    const int b = c % B2BP_SA2;
+                    mbar_wait(&a2pair[b], (c / B2BP_SA2) & 1);
+                    tc_fence_after();
+                    const uint64_t da = smem_desc_advance(da2, b * S::A2_BYTES);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int idx = 2 * c + hf, s2 = idx % B2BP_S2;
+                        mbar_wait(&b2full[s2], (idx / B2BP_S2) & 1);
+                        tc_fence_after();
+                        const uint64_t db = smem_desc_advance(db2, s2 * S::B2_STAGE);
+                        const uint32_t d = tmem_acc2 + hf * (B2B_H / 2);
+                        umma_bf16_pair(d, da, db, idesc2, c != 0);
+                        umma_bf16_pair(d, smem_desc_advance(da, 32), smem_desc_advance(db, 32), idesc2, 1);
+                        umma_bf16_pair(d, smem_desc_advance(da, 64), smem_desc_advance(db, 64), idesc2, 1);
+                        umma_bf16_pair(d, smem_desc_advance(da, 96), smem_desc_advance(db, 96), idesc2, 1);
+                        umma_commit_pair(&b2empty[s2]);
+                    }
+                    umma_commit_pair(&a2empty[b]);
+                    if (c == B2B_NCH - 1) umma_commit_pair(acc2full);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== MMA issuer, GEMM 1 (leader CTA only): acc1[c & 1] = f_tile Wp_chunk^T =====================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc1 = make_idesc_bf16(2 * TILE_M, B2B_NC, 0, 0);
+            const uint64_t da1 = make_smem_desc(smem_u32(sA1), 16, 1024);
+            const uint64_t db1 = make_smem_desc(smem_u32(sB1), 16, 1024);
+            const int ks_last = (a.K1 - (NKB1 - 1) * 64 + 15) / 16;
+            uint32_t a1ph = 0;
+            for (int pj = pair0; pj < n_pairs; pj += pair_step) {
+                if (pair_expert(pj) < 0) continue;
+                mbar_wait(a1full, a1ph); a1ph ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < B2B_NCH; ++c) {
+                    const int b = c & 1, sb = c % B2BP_S1;
+                    mbar_wait(&acc1empty[b], ((c >> 1) & 1) ^ 1);
+                    mbar_wait(&b1full[sb], (c / B2BP_S1) & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + b * B2B_NC;
+#pragma unroll
+                    for (int kb = 0; kb < NKB1; ++kb) {
+                        const uint64_t da = smem_desc_advance(da1, kb * 16384);
+                        const uint64_t db = smem_desc_advance(db1, sb * S::B1_STAGE + kb * 4096);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (kb < NKB1 - 1 || k < ks_last)
+                                umma_bf16_pair(d, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc1, (kb | k) != 0);
+                    }
+                    umma_commit_pair(&b1empty[sb]);
+                    umma_commit_pair(&acc1full[b]);
+                    if (c == B2B_NCH - 1) umma_commit_pair(a1empty);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== Y / Z store of the own tile (zero fill when the whole pair is unowned) =====================
+        for (int pj = pair0; pj < n_pairs; pj += pair_step) {
+            const int lt = 2 * pj + static_cast<int>(rank);
+            if (pair_expert(pj) < 0) {
+                if (lt < a.tile_count) {
+                    __nv_bfloat16* yb = a.y + static_cast<long long>(lt) * TILE_M * a.ld_y;
+                    __nv_bfloat16* zb = a.z + static_cast<long long>(lt) * TILE_M * a.ld_z;
+                    for (int r = 0; r < TILE_M; ++r) {
+                        for (int cidx = lane * 8; cidx < B2B_D; cidx += 256) stg_v4(yb + r * a.ld_y + cidx, make_uint4(0, 0, 0, 0));
+                        for (int cidx = lane * 8; cidx < B2B_H; cidx += 256) stg_v4(zb + r * a.ld_z + cidx, make_uint4(0, 0, 0, 0));
+                    }
+                }
+                continue;
+            }
+            const bool store = lt < a.tile_count;
+#pragma unroll
+            for (int c = 0; c < B2B_NRING; ++c) {
+                const int b = c % B2BP_SA2;
+                mbar_wait(&a2full[b], (c / B2BP_SA2) & 1);
+                if (lane == 0) {
+                    if (store) {
+                        if (c < B2B_NCH) tma_store_2d(&tmY, sA2 + b * S::A2_BYTES, c * B2B_NC, lt * TILE_M);
+                        else tma_store_2d(&tmZ, sA2 + b * S::A2_BYTES, (c - B2B_NCH) * B2B_NC, lt * TILE_M);
+                    }
+                    tma_store_commit();
+                    if (c > 0) {
+                        tma_store_wait_read<1>();
+                        mbar_arrive(&a2empty[(c - 1) % B2BP_SA2]);
+                        if (c - 1 >= B2B_NCH) mbar_arrive(&a2empty[(c - 1) % B2BP_SA2]);
+                    }
+                    if (c == B2B_NRING - 1) { tma_store_wait_read<0>(); mbar_arrive(&a2empty[b]); mbar_arrive(&a2empty[b]); }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    } else if (warp >= 4) {
+        // ===================== epilogue (each CTA: its own 128 rows) =====================
+        const int q = warp & 3;
+        const int ew = warp - 4;
+        const int g = ew >> 2;
+        const int p = g >> 1;
+        const int hh = g & 1;
+        uint32_t acc1f_ph = 0, acc2f_ph = 0;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const int r = q * 32 + lane;
+        for (int pj = pair0; pj < n_pairs; pj += pair_step) {
+            const int e = pair_expert(pj);
+            if (e < 0) continue;
+            const int lt = 2 * pj + static_cast<int>(rank);
+            int valid = 0;
+            if (lt < a.tile_count) {
+                const int2 ti = a.tile_info[a.tile_begin + lt];
+                valid = ti.x >= 0 ? ti.y : 0;
+            }
+            const bool row_valid = r < valid;
+            const float* b1p = a.bias1 + static_cast<size_t>(e) * B2B_D + hh * 32;
+#pragma unroll 1
+            for (int c = p; c < B2B_NCH; c += 2) {
+                float4 bv[8];
+                const float4* bp = reinterpret_cast<const float4*>(b1p + c * B2B_NC);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+                mbar_wait(&acc1full[p], acc1f_ph); acc1f_ph ^= 1;
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + lane_off + p * B2B_NC + hh * 32, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_leader(&acc1empty[p]);
+                const int b2 = c % B2BP_SA2;
+                const uint32_t a2e_par = ((c / B2BP_SA2) & 1) ^ 1;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float f0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bv[j].x, 0.f);
+                    const float f1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bv[j].y, 0.f);
+                    const float f2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bv[j].z, 0.f);
+                    const float f3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bv[j].w, 0.f);
+                    pk[2 * j] = row_valid ? pack_bf16x2(f0, f1) : 0u;
+                    pk[2 * j + 1] = row_valid ? pack_bf16x2(f2, f3) : 0u;
+                }
+                mbar_wait(&a2empty[b2], a2e_par);
+                uint8_t* a2row = sA2 + b2 * S::A2_BYTES + r * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = hh * 4 + j;
+                    *reinterpret_cast<uint4*>(a2row + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&a2full[b2]); arrive_leader(&a2pair[b2]); }
+            }
+            mbar_wait(acc2full, acc2f_ph); acc2f_ph ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int zc = p; zc < B2B_NZB; zc += 2) {
+                const int col0 = zc * B2B_NC + hh * 32;
+                float4 bv[8];
+                const float4* bp = reinterpret_cast<const float4*>(a.bias2 + static_cast<size_t>(e) * B2B_H + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc2 + lane_off + col0, v);
+                tmem_ld_wait();
+                if (zc + 2 >= B2B_NZB) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader(acc2empty);
+                }
+                const int c = B2B_NCH + zc;
+                const int b2 = c % B2BP_SA2;
+                const uint32_t a2e_par = ((c / B2BP_SA2) & 1) ^ 1;
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float f0 = __uint_as_float(v[4 * j + 0]) + bv[j].x, f1 = __uint_as_float(v[4 * j + 1]) + bv[j].y;
+                    const float f2 = __uint_as_float(v[4 * j + 2]) + bv[j].z, f3 = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+                    pk[2 * j] = row_valid ? pack_bf16x2(f0, f1) : 0u;
+                    pk[2 * j + 1] = row_valid ? pack_bf16x2(f2, f3) : 0u;
+                }
+                mbar_wait(&a2empty[b2], a2e_par);
+                uint8_t* a2row = sA2 + b2 * S::A2_BYTES + r * 128;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = hh * 4 + j;
+                    *reinterpret_cast<uint4*>(a2row + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a2full[b2]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                        // the peer may still read this CTA's shared memory / signal its barriers
+    if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }
 
 }  // namespace mm

@@ -61,7 +61,7 @@ dispatch_build_kernel(const int* __restrict__ item_expert, DispatchPlanArgs a, i
         int r = a.region_base[s];
         for (int e = 0; e < K; ++e) {
             s_seg[s][e] = r;
-            r += (s_cnt[e] * a.P[s] + TILE_M - 1) / TILE_M * TILE_M;
+            r += (s_cnt[e] * a.P[s] + SEG_ALIGN - 1) / SEG_ALIGN * SEG_ALIGN;
         }
     }
     __syncthreads();

@@ -31,7 +31,9 @@ enum : int {
     MM_ERR_WORKSPACE = -6,
 };
 
-constexpr int TILE_M = 128;   // rows per GEMM tile == TMEM lanes == padding granule of a segment
+constexpr int TILE_M = 128;   // rows per GEMM tile == TMEM lanes
+constexpr int SEG_ALIGN = 256;  // an expert's segment starts on a multiple of 256 rows in every region: the tiles (2j, 2j + 1) of a
+                              // region never belong to two experts, so a CTA pair (tcgen05 cta_group::2) can share one weight tile
 
 // ------------------------------------------------------------------------------------
 // Small math helpers

@@ -224,15 +224,17 @@ def expert_b2b_supported(K1: int, D: int, H: int) -> bool:
 
 
 def expert_b2b_fwd(f: torch.Tensor, Wp: torch.Tensor, bias1: torch.Tensor, W1: torch.Tensor, bias2: torch.Tensor,
-                   Y: torch.Tensor, Z: torch.Tensor, *, plan: DispatchPlan, tile_begin: int, tile_count: int, tag: str = ""):
+                   Y: torch.Tensor, Z: torch.Tensor, *, plan: DispatchPlan, tile_begin: int, tile_count: int, tag: str = "",
+                   pairs: bool = True):
     """Y = ReLU(f Wp_e^T + bias1_e), Z = Y W1_e^T + bias2_e over the tiles of one scale region, in one kernel (Y is not
-    re-read).  Wp: stacked [E * D, K1] bf16, W1: stacked [E * H, D] bf16; f / Y / Z start at the region's first row."""
+    re-read).  Wp: stacked [E * D, K1] bf16, W1: stacked [E * H, D] bf16; f / Y / Z start at the region's first row.
+    `pairs`: the plan's 256-row segment alignment (plan.SEG_ALIGN) lets CTA pairs share the weight tiles (same results)."""
     _need_cuda(f, Wp, bias1, W1, bias2, Y, Z)
     D, H = Y.shape[1], Z.shape[1]
     E = Wp.shape[0] // D
     _lib.call("mm_expert_b2b_fwd", _P(f), f.shape[0], f.shape[1], f.stride(0), _P(Wp), E, D, Wp.stride(0), _P(bias1), _P(W1),
               H, W1.stride(0), _P(bias2), _P(plan.tile_info), tile_begin, tile_count, _P(Y), Y.stride(0), _P(Z), Z.stride(0),
-              _st(), label=f"{tag}:expert_b2b[K1={f.shape[1]}]")
+              int(pairs and tile_begin % 2 == 0), _st(), label=f"{tag}:expert_b2b[K1={f.shape[1]}]")
     return Y, Z
 
 

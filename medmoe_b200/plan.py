@@ -2,9 +2,9 @@
 
 Layout: every activation that is indexed by "token row" lives in one row
 space made of S scale regions.  Region s holds, for every expert e in order, the
-`count[e] * P_s` native rows of the images routed to e, padded to a multiple of 128 rows so
-that a 128-row GEMM tile never straddles two experts.  Region capacities are static
-(`n_items * P_s` rounded up + 128 rows per expert), so buffers and launch grids do not
+`count[e] * P_s` native rows of the images routed to e, padded to a multiple of 256 rows so
+that a 128-row GEMM tile never straddles two experts and neither does a CTA pair's two tiles.  Region capacities are static
+(`n_items * P_s` rounded up + 256 rows per expert), so buffers and launch grids do not
 depend on the routing and no host<->device sync is needed; only the small int tables
 written by `mm_dispatch_build` change per step.
 """
@@ -18,6 +18,7 @@ import torch
 from . import _lib
 
 TILE_M = 128
+SEG_ALIGN = 256      # csrc/mm_common.cuh: expert segments start on multiples of 256 rows (two tiles), see there
 
 
 def _round_up(x: int, m: int) -> int:
@@ -56,7 +57,7 @@ def make_layout(n_images: int, topk: int, num_experts: int, P: Sequence[int], ta
     chunk_tiles, chunk_cap, chunk_base = [], [], []
     row = tile = chunk = 0
     for p in P:
-        rows = _round_up(n_items * p, TILE_M) + num_experts * TILE_M
+        rows = _round_up(n_items * p, SEG_ALIGN) + num_experts * SEG_ALIGN
         tiles = rows // TILE_M
         # wgrad chunks: enough of them to fill the SMs, few enough that the fp32 red.add traffic of their partial
         # results stays small (small regions get proportionally fewer chunks)
@@ -121,7 +122,7 @@ def reference_plan(item_expert: Sequence[int], layout: RowLayout) -> dict:
         r = layout.region_base[s]
         for e in range(K):
             seg_start[s][e] = r
-            r += _round_up(counts[e] * layout.P[s], TILE_M)
+            r += _round_up(counts[e] * layout.P[s], SEG_ALIGN)
     perm, inv_perm, slot_expert = [0] * n, [0] * n, [0] * n
     slot_row = [[0] * n for _ in range(S)]
     seen = [0] * K
