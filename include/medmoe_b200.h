@@ -34,7 +34,13 @@ enum mm_status {
     MM_ERR_WORKSPACE = -6
 };
 
-enum mm_epilogue_flags { MM_EPI_RELU = 1, MM_EPI_ZERO_PAD = 2 };
+enum mm_epilogue_flags {
+    MM_EPI_RELU = 1, MM_EPI_ZERO_PAD = 2, MM_EPI_CAP_SOFTMAX = 4,
+    /* the caller guarantees that the tiles (2j, 2j + 1) of the launch never belong to two experts (the 256-row segment
+     * alignment mm_dispatch_build produces; always true without tile_info): CTA pairs (tcgen05 cta_group::2) may then
+     * share the weight tiles — each CTA stages half.  Results are bit-identical. */
+    MM_EPI_PAIR_OK = 8
+};
 
 const char* mm_last_error(void);
 int mm_abi_version(void);
@@ -105,12 +111,14 @@ int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long long lda, 
 /* the same product with a rank-1 aux that is never materialised (backward of E4 + ReLU of E1; the rank-1 term is the
  * per-image constant part of d fused / d Y, see mm_interp_softmax_combine_bwd_tc), plus an optional tensor aux:
  *   out[row, :] = (A[row, :] W_e^T + row_coef[row] * vecs[row_vec[row], :] + aux[row, :]) masked by gate > 0
- * row_coef fp32 [rows], row_vec int32 [rows], vecs fp32 [n_vecs, ld_vecs]; aux bf16 or NULL; colsum as above. */
+ * row_coef fp32 [rows], row_vec int32 [rows], vecs fp32 [n_vecs, ld_vecs]; aux bf16 or NULL; colsum as above.
+ * flags: MM_EPI_PAIR_OK (8) only — the tiles (2j, 2j + 1) of the launch never belong to two experts (mm_dispatch_build's
+ * 256-row segment alignment), so CTA pairs (tcgen05 cta_group::2) may share the weight tiles; same results. */
 int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
                                long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
                                const float* row_coef, const int32_t* row_vec, const float* vecs, long long ld_vecs,
                                const void* aux, long long ld_aux, const void* gate, long long ld_gate, void* out,
-                               long long ld_out, float* colsum, void* stream);
+                               long long ld_out, float* colsum, int flags, void* stream);
 /* dW[e][N1, N2] += sum_{rows of expert e} A[row, N1]^T B[row, N2]  (fp32 red.add; caller zeroes dW). */
 int mm_grouped_gemm_wgrad(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
                           int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,

@@ -37,7 +37,7 @@ SIGNATURES = {
     "mm_grouped_gemm_rows": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                      c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_int, c_vp, c_f, c_int, c_vp]),
     "mm_grouped_gemm_rows_rank1": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int,
-                                           c_vp, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_vp]),
+                                           c_vp, c_vp, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_int, c_vp]),
     "mm_grouped_gemm_wgrad": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,
                                       c_vp, c_vp]),
     "mm_grouped_gemm_wgrad_colsum": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,

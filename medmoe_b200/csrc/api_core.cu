@@ -219,14 +219,42 @@ static int launch_rows_pair(const RowsMaps& m, const RowsGemmArgs& args, cudaStr
     return check_launch("gemm_rows_pair");
 }
 
-static int g_pair_mode = -1;      // -1: read MEDMOE_GEMM_PAIR on first use; 0 off; 1 on
+// rank-1 aux + gate epilogue on CTA pairs (the dY GEMM)
+template <int BN>
+static int launch_rows_pair_r1(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
+    constexpr int EW = MM_EPI_WARPS_RANK1;
+    constexpr int STAGES = 4;
+    using S = PairR1Smem<BN, STAGES, EW>;
+    static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_rows_pair_r1_kernel<BN, STAGES, EW>;
+    static bool configured_dev[64];
+    bool& configured = *per_device_flag(configured_dev);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("gemm_rows_pair_r1: cannot opt in to %d B of shared memory (%s)", S::TOTAL, cudaGetErrorString(e));
+            return MM_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int work = ((args.tile_count + 1) / 2) * args.n_tiles;
+    int grid = 2 * work < sm_count() ? 2 * work : (sm_count() & ~1);
+    if (grid <= 0) return MM_OK;
+    kern<<<grid, rows_threads(EW), S::TOTAL, st>>>(m.a, m.b, m.out, m.gate, args);
+    note_launches(1);
+    return check_launch("gemm_rows_pair_r1");
+}
+
+// CTA pairs are used wherever the caller vouches for the row layout (EPI_PAIR_OK); MEDMOE_GEMM_PAIR=0 / mm_debug_gemm_pair(0)
+// switch them off for A/B measurements (bit 0: plain epilogue GEMMs, bit 1: the rank-1 dY GEMM; default 3 = both)
+static int g_pair_mode = -1;
 extern "C" void mm_debug_gemm_pair(int on) { g_pair_mode = on; }
-static bool pair_mode() {
+static int pair_mode() {
     if (g_pair_mode < 0) {
         const char* v = getenv("MEDMOE_GEMM_PAIR");
-        g_pair_mode = (v && v[0] == '1') ? 1 : 0;
+        g_pair_mode = v ? atoi(v) : 3;
     }
-    return g_pair_mode == 1;
+    return g_pair_mode;
 }
 
 static int pick_bn_rows(int N) {
@@ -354,8 +382,15 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
     g.cap_len = cap_len;
     g.cap_temp = cap_temp;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pair_mode() && !aux && !r1 && !gate && !out_f32 && !colsum && !cap_len && out_scale == 1.0f && (BN == 192 || BN == 256) &&
-        (!tile_info || (tile_begin % 2 == 0))) {
+    const bool pair_ok = (flags & EPI_PAIR_OK) && (tile_info ? (tile_begin % 2 == 0 && tile_count >= 2) : M > TILE_M);
+    if (pair_ok && (pair_mode() & 2) && tile_info && r1 && !aux && gate && !colsum && out_scale == 1.0f && !bias && BN == 256) {
+        rc = encode_tmap_bf16(&m.b, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64,
+                              BN / 2, "mm_grouped_gemm_rows_rank1(W, pair)");
+        if (rc) return rc;
+        return launch_rows_pair_r1<256>(m, g, st);
+    }
+    if (pair_ok && (pair_mode() & 1) && !aux && !r1 && !gate && !out_f32 && !colsum && !cap_len && out_scale == 1.0f &&
+        (BN == 192 || BN == 256)) {
         // each CTA of a pair stages half of the W tile
         rc = encode_tmap_bf16(&m.b, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64,
                               BN / 2, "mm_grouped_gemm_rows(W, pair)");
@@ -395,11 +430,12 @@ extern "C" int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K
                                           long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
                                           const float* row_coef, const int32_t* row_vec, const float* vecs,
                                           long long ld_vecs, const void* aux, long long ld_aux, const void* gate,
-                                          long long ld_gate, void* out, long long ld_out, float* colsum, void* stream) {
+                                          long long ld_gate, void* out, long long ld_out, float* colsum, int flags,
+                                          void* stream) {
     MM_REQUIRE(tile_info, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows_rank1: tile_info required");
     const Rank1Aux r1{row_coef, row_vec, vecs, ld_vecs};
     return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, nullptr, aux, ld_aux, &r1,
-                          gate, ld_gate, out, ld_out, 0, colsum, 1.0f, 0, stream);
+                          gate, ld_gate, out, ld_out, 0, colsum, 1.0f, flags & EPI_PAIR_OK, stream);
 }
 
 // E = exp(temp1 * softmax over each caption's words of A W^T): the score GEMM of the word-patch attention loss with the first

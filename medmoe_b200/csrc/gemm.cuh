@@ -36,6 +36,8 @@ enum : int {
     EPI_RELU = 1,       // out = max(out, 0)
     EPI_ZERO_PAD = 2,   // kept for ABI compatibility: padding rows of an owned tile are always written as zeros
     EPI_CAP_SOFTMAX = 4,  // every 32-column chunk is one caption: out = exp(cap_temp * softmax over its first cap_len[chunk] columns)
+    EPI_PAIR_OK = 8,      // the caller guarantees that tiles (2j, 2j + 1) of the launch never belong to two experts (SEG_ALIGN row
+                          // layout of mm_dispatch_build): CTA pairs (tcgen05 cta_group::2) may share the weight tiles
 };
 
 struct RowsGemmArgs {

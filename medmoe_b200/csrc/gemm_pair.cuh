@@ -261,4 +261,260 @@ gemm_rows_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair row GEMM with the rank-1 aux + gate epilogue (gemm_rows_kernel's AUX = 2): the dY GEMM of the backward,
+//   out = (A W_e^T + row_coef[row] * vecs[row_vec[row], :]) * [gate > 0]
+// Same pair plumbing as above; the epilogue is gemm_rows_kernel's (gate tiles TMA-prefetched one chunk ahead into two
+// slots per warp, rank-1 vector loaded before the TMEM wait, packed gate mask, swizzled staging, TMA store), with TWO
+// output staging slots per warp: the halved W stages leave the room, and the per-chunk wait for the previous TMA store
+// to have read its slot was the longest link of the single-CTA kernel's per-warp chain.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int EPI_WARPS>
+struct PairR1Smem {
+    static constexpr int A_BYTES = TILE_M * 128;
+    static constexpr int B_BYTES = (BN / 2) * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int OUT_SLOTS = 2;
+    static constexpr int EPI_OUT_BYTES = EPI_WARPS * OUT_SLOTS * EPI_SLOT_BYTES;
+    static constexpr int EPI_IN_BYTES = EPI_WARPS * 2 * EPI_SLOT_BYTES;          // gate tiles, double-buffered
+    static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_OUT_BYTES + EPI_IN_BYTES + BAR_BYTES + 1024;
+};
+
+template <int BN, int STAGES, int EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(rows_threads(EPI_WARPS), 1)
+gemm_rows_pair_r1_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmGate,
+                         const RowsGemmArgs a) {
+    using S = PairR1Smem<BN, STAGES, EPI_WARPS>;
+    static_assert(BN % 64 == 0 && BN <= 256, "BN / 2 must be a multiple of 32 rows");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * S::A_BYTES;
+    uint8_t* sOut = smem + STAGES * S::STAGE_BYTES;
+    uint8_t* sIn = sOut + S::EPI_OUT_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sIn + S::EPI_IN_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* inbar = tempty + 2;              // [EPI_WARPS][2 slots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 2 * EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmGate); }
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 2 * EPI_WARPS); }
+        for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&inbar[s], 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_kb = (a.K + 63) / 64;
+    const int n_pairs = (a.tile_count + 1) >> 1;
+    const int total_work = n_pairs * a.n_tiles;
+
+    auto pair_expert = [&](int pt) {
+        const int t0 = 2 * pt, t1 = 2 * pt + 1;
+        const int e0 = a.tile_info[a.tile_begin + t0].x;
+        if (e0 >= 0) return e0;
+        return t1 < a.tile_count ? a.tile_info[a.tile_begin + t1].x : -1;
+    };
+    // valid rows of this CTA's tile of pair pt (0: not owned / past the end)
+    auto own_valid = [&](int pt) {
+        const int lt = 2 * pt + static_cast<int>(rank);
+        if (lt >= a.tile_count) return 0;
+        const int2 ti = a.tile_info[a.tile_begin + lt];
+        return ti.x >= 0 ? ti.y : 0;
+    };
+
+    if (warp == 0 && elect_one()) {
+        // ===================== TMA producer (both CTAs: own A rows, own half of W) =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int w = pair; w < total_work; w += n_pairs_grid) {
+            const int pt = w / a.n_tiles, nt = w - pt * a.n_tiles;
+            const int e = pair_expert(pt);
+            if (e < 0) continue;
+            const int row_a = min(2 * pt + static_cast<int>(rank), a.tile_count - 1) * TILE_M;
+            const int row_b = e * a.N + nt * BN + static_cast<int>(rank) * (BN / 2);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (rank == 0) mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+                const uint32_t bar = mapa_u32(&full[stage], 0);
+                tma_load_2d_pair(sA + stage * S::A_BYTES, &tmA, bar, kb * 64, row_a);
+                tma_load_2d_pair(sB + stage * S::B_BYTES, &tmB, bar, kb * 64, row_b);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && rank == 0 && elect_one()) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        constexpr uint32_t idesc = make_idesc_bf16(2 * TILE_M, BN, 0, 0);
+        const uint64_t da_base = make_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t db_base = make_smem_desc(smem_u32(sB), 16, 1024);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = pair; w < total_work; w += n_pairs_grid) {
+            if (pair_expert(w / a.n_tiles) < 0) continue;
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint64_t da = smem_desc_advance(da_base, stage * S::A_BYTES);
+                const uint64_t db = smem_desc_advance(db_base, stage * S::B_BYTES);
+                const int ksteps = min(4, (a.K - kb * 64 + 15) / 16);
+                if (ksteps == 4) {
+                    umma_bf16_pair(d_tmem, da, db, idesc, kb != 0);
+                    umma_bf16_pair(d_tmem, smem_desc_advance(da, 32), smem_desc_advance(db, 32), idesc, 1);
+                    umma_bf16_pair(d_tmem, smem_desc_advance(da, 64), smem_desc_advance(db, 64), idesc, 1);
+                    umma_bf16_pair(d_tmem, smem_desc_advance(da, 96), smem_desc_advance(db, 96), idesc, 1);
+                } else {
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16_pair(d_tmem, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc, (kb | k) != 0);
+                }
+                umma_commit_pair(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit_pair(&tfull[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp == 3) {
+        // ===================== own tiles that are not owned by an expert: zero fill =====================
+        for (int w = pair; w < total_work; w += n_pairs_grid) {
+            const int pt = w / a.n_tiles, nt = w - pt * a.n_tiles;
+            const int lt = 2 * pt + static_cast<int>(rank);
+            if (lt >= a.tile_count || a.tile_info[a.tile_begin + lt].x >= 0) continue;
+            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(lt) * TILE_M * a.ld_out + nt * BN;
+            for (int r = 0; r < TILE_M; ++r)
+                for (int cidx = lane * 8; cidx < BN; cidx += 256) stg_v4(base + r * a.ld_out + cidx, make_uint4(0, 0, 0, 0));
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (each CTA: its own 128 rows) =====================
+        const int q = warp & 3;
+        const int ew = warp - 4;
+        const int h = ew >> 2;
+        constexpr int NCH = BN / 32;
+        constexpr int CSTEP = EPI_WARPS / 4;
+        uint8_t* my_out = sOut + ew * S::OUT_SLOTS * EPI_SLOT_BYTES;
+        uint8_t* my_in = sIn + ew * 2 * EPI_SLOT_BYTES;
+        uint64_t* my_bar = inbar + ew * 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        int oslot = 0;
+        int islot = 0; uint32_t iphase[2] = {0, 0};
+
+        // next work item of this pair sequence in which this CTA's own tile is owned (gate prefetch chain)
+        auto next_active = [&](int w) {
+            for (; w < total_work; w += n_pairs_grid)
+                if (own_valid(w / a.n_tiles) > 0) break;
+            return w;
+        };
+        auto issue_in = [&](int w, int c, int slot) {   // lane 0 only
+            const int pt = w / a.n_tiles, nt = w - pt * a.n_tiles;
+            const int row0 = (2 * pt + static_cast<int>(rank)) * TILE_M + q * 32, col0 = nt * BN + c * 32;
+            mbar_expect_tx(&my_bar[slot], EPI_SLOT_BYTES);
+            tma_load_2d(my_in + slot * EPI_SLOT_BYTES, &tmGate, &my_bar[slot], col0, row0);
+        };
+
+        int w_act = next_active(pair);            // the work item whose gate tiles are (being) prefetched
+        if (w_act < total_work && lane == 0 && h < NCH) issue_in(w_act, h, 0);
+        for (int w = pair; w < total_work; w += n_pairs_grid) {
+            const int pt = w / a.n_tiles, nt = w - pt * a.n_tiles;
+            if (pair_expert(pt) < 0) continue;
+            const int lt = 2 * pt + static_cast<int>(rank);
+            const int valid = own_valid(pt);
+            const int r_in_tile = q * 32 + lane;
+            const long long row = static_cast<long long>(lt) * TILE_M + r_in_tile;
+            const bool row_valid = r_in_tile < valid;
+            float r1_coef = 0.f;
+            const float* r1_vec = a.vecs;
+            if (row_valid) {
+                r1_coef = __ldg(a.row_coef + row);
+                r1_vec = a.vecs + static_cast<long long>(__ldg(a.row_vec + row)) * a.ld_vecs;
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            if (valid > 0) {          // w == w_act: this warp's first gate tile of the item is in flight in slot `islot`
+                const int w_next = next_active(w + n_pairs_grid);
+                const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+                for (int c = h; c < NCH; c += CSTEP) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c * 32, v);
+                    if (lane == 0) {
+                        if (c + CSTEP < NCH) issue_in(w, c + CSTEP, islot ^ 1);
+                        else if (w_next < total_work) issue_in(w_next, h, islot ^ 1);
+                    }
+                    const int col0 = nt * BN + c * 32;
+                    float4 xv[8];
+                    const float4* vp = reinterpret_cast<const float4*>(r1_vec + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] = __ldg(vp + j);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f[4 * j + 0] = fmaf(r1_coef, xv[j].x, __uint_as_float(v[4 * j + 0]));
+                        f[4 * j + 1] = fmaf(r1_coef, xv[j].y, __uint_as_float(v[4 * j + 1]));
+                        f[4 * j + 2] = fmaf(r1_coef, xv[j].z, __uint_as_float(v[4 * j + 2]));
+                        f[4 * j + 3] = fmaf(r1_coef, xv[j].w, __uint_as_float(v[4 * j + 3]));
+                    }
+                    mbar_wait(&my_bar[islot], iphase[islot]);
+                    iphase[islot] ^= 1;
+                    const uint8_t* gt = my_in + islot * EPI_SLOT_BYTES;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 g = *reinterpret_cast<const uint4*>(gt + epi_slot_off(lane, j));
+                        pk[4 * j + 0] = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]) & bf16x2_pos_mask(g.x);
+                        pk[4 * j + 1] = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]) & bf16x2_pos_mask(g.y);
+                        pk[4 * j + 2] = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]) & bf16x2_pos_mask(g.z);
+                        pk[4 * j + 3] = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]) & bf16x2_pos_mask(g.w);
+                    }
+                    __syncwarp();       // every lane is done with gate slot `islot` before lane 0 refills it next iteration
+                    islot ^= 1;
+                    if (!row_valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    }
+                    if (lane == 0) tma_store_wait_read<S::OUT_SLOTS - 1>();
+                    __syncwarp();
+                    uint8_t* so = my_out + oslot * EPI_SLOT_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(so + epi_slot_off(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmOut, so, col0, lt * TILE_M + q * 32);
+                        tma_store_commit();
+                    }
+                    oslot ^= 1;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty[acc]);
+                else mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc2(tmem_base, 512);
+}
+
 }  // namespace mm

@@ -115,13 +115,13 @@ class _ExpertsFunction(torch.autograd.Function):
             r0 = layout.region_base[s]
             return lambda: ops.gemm_rows(fs[s], Wp[s], D, Y[r0:r0 + layout.region_rows[s]], plan=plan,
                                          tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], bias=bp[s],
-                                         flags=ops.EPI_RELU | ops.EPI_ZERO_PAD, tag=f"E1.s{s}")
+                                         flags=ops.EPI_RELU | ops.EPI_ZERO_PAD | ops.EPI_PAIR_OK, tag=f"E1.s{s}")
         ops.run_scales([e1(s) for s in range(n_fused, S)])
         if n_fused < S:
             t0 = layout.tile_base[n_fused]
             r0 = layout.region_base[n_fused]
             ops.gemm_rows(Y[r0:], W1, H, Z[r0:], plan=plan, tile_begin=t0, tile_count=layout.total_tiles - t0, bias=b1,
-                          flags=ops.EPI_ZERO_PAD, tag="E4")
+                          flags=ops.EPI_ZERO_PAD | ops.EPI_PAIR_OK, tag="E4")
         gate_flat = gate.reshape(-1).float().contiguous() if gate is not None else None
         fused, gfeat, beta = ops.combine_fwd(Y, Z, w2, b2, plan, D, gate_flat, in_dtype)
 
@@ -183,7 +183,7 @@ class _ExpertsFunction(torch.autograd.Function):
                                     row_vec=row_img, vecs=dglobal32, gate=Y, aux=dUT, tag="dY")
             else:
                 ops.gemm_rows(dZ, W1T, D, dUT, plan=plan, tile_begin=0, tile_count=layout.total_tiles, aux=dUT, gate=Y,
-                              flags=ops.EPI_ZERO_PAD, tag="dY")
+                              flags=ops.EPI_ZERO_PAD | ops.EPI_PAIR_OK, tag="dY")
                 dPre = dUT
         else:
             dUT, dZ, dw2, db1, db2, dgate = ops.combine_bwd(Y, Z, w2, plan, D, gate_flat, beta, dfused, dglobal32,
@@ -191,7 +191,7 @@ class _ExpertsFunction(torch.autograd.Function):
             # dPre = (dUT + dZ W1) * [Y > 0], in place over dUT
             if need_dpre:
                 ops.gemm_rows(dZ, W1T, D, dUT, plan=plan, tile_begin=0, tile_count=layout.total_tiles, aux=dUT, gate=Y,
-                              flags=ops.EPI_ZERO_PAD, tag="dY")
+                              flags=ops.EPI_ZERO_PAD | ops.EPI_PAIR_OK, tag="dY")
             dPre = dUT
 
         # weight gradients first: once they are complete the flat bucket can travel (NCCL on a side stream) while dX runs
@@ -224,7 +224,7 @@ class _ExpertsFunction(torch.autograd.Function):
 
             def dx(s):   # df_s = dPre_s W_s
                 r0, nr = layout.region_base[s], layout.region_rows[s]
-                return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfs[s], plan=plan,
+                return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfs[s], plan=plan, flags=ops.EPI_PAIR_OK,
                                              tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
             ops.run_scales([dx(s) for s in range(S)])
             outs = ops.undispatch_rows(dfs, plan, widths, in_dtype)

@@ -14,6 +14,7 @@ from . import _lib
 from .plan import DispatchPlan, RowLayout
 
 EPI_RELU, EPI_ZERO_PAD = 1, 2
+EPI_PAIR_OK = 8      # plan-based launches: tiles (2j, 2j + 1) share an expert (plan.SEG_ALIGN), CTA pairs may share weight tiles
 _P = _lib.ptr
 # test hook: run the generic (any scale ratio) backward-combine kernel instead of the token-centric one
 FORCE_GENERIC_COMBINE_BWD = False
@@ -240,14 +241,14 @@ def expert_b2b_fwd(f: torch.Tensor, Wp: torch.Tensor, bias1: torch.Tensor, W1: t
 
 def gemm_rows_rank1(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, plan: DispatchPlan, tile_begin: int,
                     tile_count: int, row_coef: torch.Tensor, row_vec: torch.Tensor, vecs: torch.Tensor, gate: torch.Tensor,
-                    aux: Optional[torch.Tensor] = None, colsum=None, tag: str = ""):
+                    aux: Optional[torch.Tensor] = None, colsum=None, tag: str = "", flags: int = EPI_PAIR_OK):
     """out[row] = (A[row] W_e^T + row_coef[row] * vecs[row_vec[row]] [+ aux[row]]) * [gate[row] > 0]
     (the rank-1 aux is never materialised)."""
     _need_cuda(A, W, out, row_coef, row_vec, vecs, gate, aux)
     E = W.shape[0] // N
     _lib.call("mm_grouped_gemm_rows_rank1", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(W), E, N, W.stride(0),
               _P(plan.tile_info), tile_begin, tile_count, _P(row_coef), _P(row_vec), _P(vecs), vecs.stride(0), _P(aux),
-              aux.stride(0) if aux is not None else 0, _P(gate), gate.stride(0), _P(out), out.stride(0), _P(colsum), _st(),
+              aux.stride(0) if aux is not None else 0, _P(gate), gate.stride(0), _P(out), out.stride(0), _P(colsum), flags, _st(),
               label=f"{tag}:gemm_rows_rank1[K={A.shape[1]},N={N}]")
     return out
 

@@ -216,7 +216,15 @@ def test_grouped_rows_gemm_rank1_aux(K, N, with_aux):
     _lib.call("mm_grouped_gemm_rows_rank1", _lib.ptr(A), rows, K, A.stride(0), _lib.ptr(W), E, N, W.stride(0),
               _lib.ptr(plan.tile_info), 0, layout.total_tiles, _lib.ptr(row_coef), _lib.ptr(row_vec), _lib.ptr(vecs),
               vecs.stride(0), _lib.ptr(aux), N if with_aux else 0, _lib.ptr(gate), gate.stride(0), _lib.ptr(out),
-              out.stride(0), 0, _lib.stream_ptr())
+              out.stride(0), 0, 0, _lib.stream_ptr())
+    if not with_aux and N % 256 == 0:
+        # the same launch on CTA pairs (cta_group::2, flag MM_EPI_PAIR_OK: the plan's segments are 256-row aligned): bit-identical
+        out2 = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        _lib.call("mm_grouped_gemm_rows_rank1", _lib.ptr(A), rows, K, A.stride(0), _lib.ptr(W), E, N, W.stride(0),
+                  _lib.ptr(plan.tile_info), 0, layout.total_tiles, _lib.ptr(row_coef), _lib.ptr(row_vec), _lib.ptr(vecs),
+                  vecs.stride(0), 0, 0, _lib.ptr(gate), gate.stride(0), _lib.ptr(out2), out2.stride(0), 0, 8, _lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(torch.int16), out2.view(torch.int16))
     torch.cuda.synchronize()
     row_e = _row_expert(layout, plan)
     valid = row_e >= 0
@@ -235,11 +243,11 @@ def test_grouped_rows_gemm_rank1_aux(K, N, with_aux):
 
 @pytest.fixture
 def pair_mode():
-    """Route plain row GEMMs with a 192- or 256-wide tile to the CTA-pair kernel (experimental, off by default)."""
+    """CTA-pair kernels on (the default) for launches that pass MM_EPI_PAIR_OK; tests switch them off to get the single-CTA result."""
     lib = _lib.load()
-    lib.mm_debug_gemm_pair(1)
+    lib.mm_debug_gemm_pair(3)
     yield
-    lib.mm_debug_gemm_pair(0)
+    lib.mm_debug_gemm_pair(3)
 
 
 @pytest.mark.parametrize("M,K,N", [(256, 64, 192), (128, 128, 256), (300, 96, 768), (1000, 768, 384), (4096 + 130, 384, 768)])
@@ -248,10 +256,10 @@ def test_pair_rows_gemm_dense_bit_identical_to_single(pair_mode, M, K, N):
     W = _bf16(N, K, scale=K ** -0.5, seed=2)
     bias = torch.randn(N, device="cuda")
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    gemm_rows(A, W, N, M=M, bias=bias, out=out, flags=EPI_RELU)
+    gemm_rows(A, W, N, M=M, bias=bias, out=out, flags=EPI_RELU | 8)
     _lib.load().mm_debug_gemm_pair(0)
     single = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    gemm_rows(A, W, N, M=M, bias=bias, out=single, flags=EPI_RELU)
+    gemm_rows(A, W, N, M=M, bias=bias, out=single, flags=EPI_RELU | 8)
     # same k order, same fp32 accumulation: the two tile shapes must agree bit for bit
     assert torch.equal(out, single)
     ref = torch.relu(A.float() @ W.float().t() + bias)
@@ -268,7 +276,7 @@ def test_pair_rows_gemm_grouped_256_row_segments(pair_mode):
     W = _bf16(E * N, K, scale=K ** -0.5, seed=5)
     bias = torch.randn(E, N, device="cuda")
     out = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
-    gemm_rows(A, W, N, tile_info=tile_info, tile_begin=0, tile_count=len(tiles), bias=bias, out=out, flags=EPI_RELU)
+    gemm_rows(A, W, N, tile_info=tile_info, tile_begin=0, tile_count=len(tiles), bias=bias, out=out, flags=EPI_RELU | 8)
     Wf = W.float().view(E, N, K)
     for t, (e, v) in enumerate(tiles):
         blk = out[t * 128:(t + 1) * 128].float()
