@@ -17,7 +17,9 @@
 //   bwd_z_dlogit_kernel : dlogit[slot, p, 0..3] from beta and the two column-half partial dbeta (+ gate gradient)
 //   bwd_z_prefix_kernel : per (slot, coarse scale, interval) the r+1 exclusive prefix sums, head / tail sums
 //   bwd_z_ident_kernel  : finest scale (r = 1): dZ_0[p] = dl_0(p) w2 [Z_0[p] > 0]  (+ dw2, db1, db2 partials)
-//   bwd_z_rows_kernel   : coarse scales, a warp walks 8 consecutive native rows (+ dw2, db1 partials)
+//   bwd_z_rows_kernel   : coarse scales, a warp walks 16 consecutive native rows (+ dw2, db1 partials); the ratio-4 scale
+//                         (three quarters of the coarse rows) evaluates its four tokens per interval directly instead
+//                         of reading prefix sums (0.26 -> 0.21 ms at cfg2)
 #pragma once
 
 namespace mm {
@@ -81,7 +83,7 @@ bwd_z_prefix_kernel(const CombineArgs a, const ZScratch zs) {
     const int Ps = a.Ps[s], r = a.ratio[s];
     float* base = a.zscr + slot * zs.per_slot;
     const float* dlog = base;
-    if (m < Ps - 1) {
+    if (m < Ps - 1 && r != 4) {      // ratio 4 is evaluated directly by the rows kernel (z_open_sums_r4): no prefix table
         float2* pa = reinterpret_cast<float2*>(base + zs.pa_off[s]) + static_cast<long long>(m) * (r + 1);
         const int p0 = r * m + (r >> 1);
         const float inv_r = 1.0f / static_cast<float>(r);
@@ -221,6 +223,24 @@ MM_DEVINL void z_open_sums(float za, float zb, int r, const float2* __restrict__
     S1 = h.y - l.y;
 }
 
+// The same sums for r = 4 (the scale with three quarters of the coarse rows) evaluated directly: four lerp FMAs and four
+// predicated adds per element instead of the crossing point, two conversions and two gathers — about half the instructions.
+// dl[j] are the interval's four token gradients (warp-uniform), lambda_j = (j + 0.5) / 4.
+MM_DEVINL void z_open_sums_r4(float za, float zb, const float (&dl)[4], float& S0, float& S1) {
+    const float d = zb - za;
+    S0 = 0.f; S1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float lam = (static_cast<float>(j) + 0.5f) * 0.25f;
+        if (fmaf(lam, d, za) > 0.f) { S0 += dl[j]; S1 = fmaf(lam, dl[j], S1); }
+    }
+}
+// token gradients of interval m of a ratio-4 scale s (tokens 4 m + 2 .. 4 m + 5), read from the per-slot dlogit table
+MM_DEVINL void z_load_dl4(const float* __restrict__ dlog, int m, int s, float (&dl)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dl[j] = __ldg(dlog + 4LL * (4 * m + 2 + j) + s);
+}
+
 template <int N>
 MM_DEVINL void z_load_row_raw(const __nv_bfloat16* row, int lane, uint2 (&q)[N]) {
 #pragma unroll
@@ -264,14 +284,26 @@ bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunk
         load_row_bf16x4<NE>(a.Z + (base + i_a) * H, lane, zb);              // zb = Z[i_a]
         if (i_a + 1 < Ps) z_load_row_raw<NE>(a.Z + (base + i_a + 1) * H, lane, n1);
         if (i_a + 2 < Ps && i_a + 1 < i_b) z_load_row_raw<NE>(a.Z + (base + i_a + 2) * H, lane, n2);
+        const bool direct4 = r == 4;
         if (i_a >= 1) {   // B-side of the interval that ends in the first row of this chunk
             load_row_bf16x4<NE>(a.Z + (base + i_a - 1) * H, lane, za);
-            const float2* pa = PA + static_cast<long long>(i_a - 1) * (r + 1);
+            if (direct4) {
+                float dl[4];
+                z_load_dl4(sbase, i_a - 1, s, dl);
 #pragma unroll
-            for (int k = 0; k < E; ++k) {
-                float S0, S1;
-                z_open_sums(za[k], zb[k], r, pa, S0, S1);
-                carry[k] = S1;
+                for (int k = 0; k < E; ++k) {
+                    float S0, S1;
+                    z_open_sums_r4(za[k], zb[k], dl, S0, S1);
+                    carry[k] = S1;
+                }
+            } else {
+                const float2* pa = PA + static_cast<long long>(i_a - 1) * (r + 1);
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    float S0, S1;
+                    z_open_sums(za[k], zb[k], r, pa, S0, S1);
+                    carry[k] = S1;
+                }
             }
         }
         for (int i = i_a; i < i_b; ++i) {
@@ -297,6 +329,17 @@ bwd_z_rows_kernel(const CombineArgs a, const ZScratch zs, int chunks1, int chunk
                 for (int k = 0; k < E; ++k) {
                     if (za[k] > 0.f) { row[k] += ts; dw2[k] = fmaf(ts, za[k], dw2[k]); }
                     carry[k] = 0.f;
+                }
+            } else if (direct4) {
+                float dl[4];
+                z_load_dl4(sbase, i, s, dl);
+#pragma unroll
+                for (int k = 0; k < E; ++k) {
+                    float S0, S1;
+                    z_open_sums_r4(za[k], zb[k], dl, S0, S1);
+                    row[k] += S0 - S1;
+                    carry[k] = S1;
+                    dw2[k] += za[k] * S0 + (zb[k] - za[k]) * S1;
                 }
             } else {
                 const float2* pa = PA + static_cast<long long>(i) * (r + 1);
