@@ -63,8 +63,11 @@ int launch_b2b_pair_fwd(const CUtensorMap& tA1, const CUtensorMap& tB1, const CU
 }  // namespace
 
 // 1 when mm_expert_b2b_fwd covers this shape (otherwise run the two GEMMs separately through mm_grouped_gemm_rows)
+// (K1 in (128, 192] only on CTA pairs — flags & 1 of mm_expert_b2b_fwd —: the halved weight stages leave room for a 48 KB f tile)
 extern "C" int mm_expert_b2b_fwd_supported(int K1, int D, int H) {
-    return (D == B2B_D && H == B2B_H && K1 > 0 && K1 % 16 == 0 && K1 <= 128) ? 1 : 0;
+    if (!(D == B2B_D && H == B2B_H && K1 > 0 && K1 % 16 == 0)) return 0;
+    if (K1 <= 128) return 1;
+    return (K1 <= 192 && !(b2b_debug_flags() & 1)) ? 2 : 0;
 }
 
 // Y = ReLU(f Wp_e^T + bp_e) (bf16, written once) and Z = Y W1_e^T + b1_e (bf16) over the 128-row tiles
@@ -74,8 +77,9 @@ extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long l
                                  const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
                                  long long ld_y, void* Z, long long ld_z, int flags, void* stream) {
     MM_REQUIRE(f && Wp && W1 && bias1 && bias2 && tile_info && Y && Z, MM_ERR_BAD_SHAPE, "mm_expert_b2b_fwd: null operand");
-    MM_REQUIRE(mm_expert_b2b_fwd_supported(K1, D, H), MM_ERR_UNSUPPORTED,
-               "mm_expert_b2b_fwd: needs D = 768, H = 384 and K1 a multiple of 16 up to 128");
+    const int sup = mm_expert_b2b_fwd_supported(K1, D, H);
+    MM_REQUIRE(sup == 1 || (sup == 2 && (flags & 1) && tile_count >= 2), MM_ERR_UNSUPPORTED,
+               "mm_expert_b2b_fwd: needs D = 768, H = 384 and K1 a multiple of 16 up to 128 (up to 192 on CTA pairs, flags & 1)");
     if (tile_count <= 0) return MM_OK;
     const uint64_t io_rows = static_cast<uint64_t>(tile_count) * TILE_M;
     // flags & 1: the caller guarantees that the tiles (2j, 2j + 1) of this launch never belong to two experts (SEG_ALIGN row
@@ -109,6 +113,8 @@ extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long l
     g.z = static_cast<__nv_bfloat16*>(Z);
     g.ld_z = ld_z;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pairs) return K1 <= 64 ? launch_b2b_pair_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st) : launch_b2b_pair_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st);
+    if (pairs) return K1 <= 64    ? launch_b2b_pair_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st)
+                      : K1 <= 128 ? launch_b2b_pair_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st)
+                                  : launch_b2b_pair_fwd<3>(tA1, tB1, tB2, tY, tZ, g, st);
     return K1 <= 64 ? launch_b2b_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st) : launch_b2b_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st);
 }

@@ -444,10 +444,10 @@ b2b_fwd_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 //   a2full[] (8 warps)                 own epilogue -> own store warp;   a2empty[] (2)   multicast commit of GEMM 2 + own store warp
 // A tile no expert owns (second tile of a segment's last pair) runs the protocol with zero valid rows: its epilogue writes zeros.
 // =====================================================================================================================
-constexpr int B2BP_S1 = 6, B2BP_S2 = 6, B2BP_SA2 = 3;
-static_assert(B2B_NCH % B2BP_S1 == 0 && (B2B_NCH / B2BP_S1) % 2 == 0 && (2 * B2B_NCH) % B2BP_S2 == 0 &&
-                  ((2 * B2B_NCH) / B2BP_S2) % 2 == 0 && B2B_NRING % B2BP_SA2 == 0 && (B2B_NRING / B2BP_SA2) % 2 == 0 &&
-                  (B2B_NCH / B2BP_SA2) % 2 == 0,
+constexpr int B2BP_S2 = 6, B2BP_SA2 = 3;
+constexpr int b2bp_s1(int nkb1) { return nkb1 <= 2 ? 6 : 2; }       // Wp ring depth: a 48 KB f tile (K1 up to 192) leaves room for two chunks
+static_assert((2 * B2B_NCH) % B2BP_S2 == 0 && ((2 * B2B_NCH) / B2BP_S2) % 2 == 0 && B2B_NRING % B2BP_SA2 == 0 &&
+                  (B2B_NRING / B2BP_SA2) % 2 == 0 && (B2B_NCH / B2BP_SA2) % 2 == 0 && (B2B_NCH / 6) % 2 == 0 && (B2B_NCH / 2) % 2 == 0,
               "ring stages and phases are compile-time functions of the chunk index: every ring must wrap an even number of times per tile");
 
 template <int NKB1>
@@ -456,11 +456,12 @@ struct B2BPairSmem {
     static constexpr int B1_STAGE = NKB1 * 4096;                   // half of a Wp chunk: 32 rows x 64 k per k block
     static constexpr int B2_STAGE = (B2B_H / 4) * 128;             // half of a W1 half chunk: 96 rows x 64 k = 12 KB
     static constexpr int A2_BYTES = 16384;
+    static constexpr int S1 = b2bp_s1(NKB1);
     static constexpr int OFF_B1 = A1_BYTES;
-    static constexpr int OFF_B2 = OFF_B1 + B2BP_S1 * B1_STAGE;
+    static constexpr int OFF_B2 = OFF_B1 + S1 * B1_STAGE;
     static constexpr int OFF_A2 = OFF_B2 + B2BP_S2 * B2_STAGE;
     static constexpr int OFF_BAR = OFF_A2 + B2BP_SA2 * A2_BYTES;
-    static constexpr int N_BARS = 2 + 2 * B2BP_S1 + 2 * B2BP_S2 + 4 + 3 * B2BP_SA2 + 2;
+    static constexpr int N_BARS = 2 + 2 * S1 + 2 * B2BP_S2 + 4 + 3 * B2BP_SA2 + 2;
     static constexpr int TOTAL = OFF_BAR + N_BARS * 8 + 16 + 1024;
 };
 
@@ -470,6 +471,7 @@ b2b_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
                     const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY,
                     const __grid_constant__ CUtensorMap tmZ, const B2BFwdArgs a) {
     using S = B2BPairSmem<NKB1>;
+    constexpr int B2BP_S1 = S::S1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA1 = smem;

@@ -307,13 +307,13 @@ def _b2b_case(n_items, E, P, K1, seed, idle_expert=False):
     b1 = torch.randn(E, H, device="cuda")
     Y = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     Z = torch.full((rows, H), float("nan"), device="cuda", dtype=torch.bfloat16)
-    assert _lib.call("mm_expert_b2b_fwd_supported", K1, D, H) == 1
+    assert _lib.call("mm_expert_b2b_fwd_supported", K1, D, H) >= 1      # 2: only on CTA pairs (K1 in (128, 192])
     ops.expert_b2b_fwd(f, Wp, bp, W1, b1, Y, Z, plan=plan, tile_begin=0, tile_count=layout.total_tiles)
     torch.cuda.synchronize()
     return layout, plan, row_e, f, Wp, W1, bp, b1, Y, Z
 
 
-@pytest.mark.parametrize("K1", [96, 64, 128, 32])
+@pytest.mark.parametrize("K1", [96, 64, 128, 32, 192, 144])
 @pytest.mark.parametrize("idle", [False, True])
 def test_b2b_forward_bit_identical_to_the_two_gemms(K1, idle):
     """The fused kernel runs the same MMAs in the same k order on the same bf16-rounded Y: Y and Z must be bit-identical
