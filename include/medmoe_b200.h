@@ -218,8 +218,9 @@ int mm_local_cos_lse_fwd(const float* wcU, const float* words, int B, int n_caps
 int mm_local_cos_lse_bwd(const float* dsim, long long ld_dsim, const float* sim, long long ld_sim, const float* cosv,
                          const float* wcU, const float* words, int B, int n_caps, int Wp, int D, const int32_t* cap_len,
                          float temp2, int agg_mean, void* dwcU, void* dwcUT, long long ld_t, float* dwords, void* stream);
-/* experimental: 1 = run eligible row GEMMs (plain bf16 epilogue, BN 192 / 256) on CTA pairs (tcgen05 cta_group::2);
- * also switched on by MEDMOE_GEMM_PAIR=1.  Needs 256-row aligned expert segments when tile_info is given. */
+/* A/B switch of the CTA-pair (tcgen05 cta_group::2) row GEMMs, which run wherever a launch passes MM_EPI_PAIR_OK:
+ * bit 0 = plain bf16 epilogue GEMMs with a 192 / 256 wide tile, bit 1 = the rank-1 (dY) GEMM; default 3, also
+ * MEDMOE_GEMM_PAIR=<bits>.  (The back-to-back kernel has its own switch: MEDMOE_B2B_DEBUG bit 0 = no pairs.) */
 void mm_debug_gemm_pair(int on);
 /* test hook: 1 = compute dUT with the CUDA-core kernel instead of the tcgen05 one (process-wide) */
 void mm_debug_force_cuda_core_dut(int on);

@@ -3,12 +3,14 @@
 // Two CTAs of a cluster (the two SMs of a TPC) compute a 256 x BN tile: CTA r stages its own 128 rows of A and HALF of
 // the W tile (BN / 2 rows), the leader CTA issues one M = 256 MMA per k step that reads both halves, and each CTA keeps
 // the accumulator of its 128 rows in its own TMEM.  Per SM this halves the B bytes TMA writes into and the tensor core
-// reads out of shared memory — the resource that caps the single-CTA kernel (208 B/clk wanted, 128 available).
+// reads out of shared memory, halves the weight bytes that come out of L2 per 128-row tile, and lets the same shared
+// memory hold more stages (the single-CTA kernels re-fetch their weight tile from L2 for every tile).
 //
 // Pairs are (tile 2j, tile 2j + 1) of the launch; both must multiply the same expert's weights, which the 256-row segment
 // alignment of the row layout guarantees (plan.py).  A pair whose second tile is not owned runs with zero valid rows there
 // (it writes zeros, like the single-CTA kernel's zero fill); a pair with no owned tile is zero-filled by warp 3.
-// Plain epilogue only (bias, ReLU, bf16 TMA store): this is the E1 / E4 / dX path.
+// gemm_rows_pair_kernel: plain epilogue (bias, ReLU, bf16 TMA store) — the E1 / E4 / dX path; gemm_rows_pair_r1_kernel
+// (below): rank-1 aux + gate epilogue — the dY GEMM.  Used when the caller passes EPI_PAIR_OK (api_core.cu).
 // Barriers: both CTAs' TMA loads complete on the LEADER's `full` (which expects the bytes of the pair); `empty` and `tfull`
 // are signalled in both CTAs by multicast commits; the peer's epilogue warps arrive remotely on the leader's `tempty`.
 // Remote arrives use the default .release.cta form: a cluster-scope release costs a full memory fence per arrive (measured:
