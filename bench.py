@@ -292,8 +292,10 @@ def load_traffic_table():
 
 # bench tag -> (kernel-name regex of the ncu summary, occurrence of that kernel inside one step)
 TRAFFIC_KEYS = {
-    "dY": (r"gemm_rows_kernel<256,3,0,2,12>", 0), "E4": (r"gemm_rows_kernel<192,4,0,0,16>", 0),
-    "E1.s0": (r"gemm_rows_kernel<256,4,0,0,16>", 0), "E1E4.s0": (r"b2b_fwd_kernel<2>", 0), "dW1": (r"gemm_wgrad_kernel<256,4,0>", 0),
+    "dY": (r"gemm_rows_pair_r1_kernel<256,4,12>|gemm_rows_kernel<256,3,0,2,12>", 0),
+    "E4": (r"gemm_rows_pair_kernel<192,6,16>|gemm_rows_kernel<192,4,0,0,16>", 0),
+    "E1.s0": (r"gemm_rows_kernel<256,4,0,0,16>", 0), "E1E4.s0": (r"b2b_pair_fwd_kernel<2>|b2b_fwd_kernel<2>", 0),
+    "E1E4.s1": (r"b2b_pair_fwd_kernel<3>", 0), "dW1": (r"gemm_wgrad_kernel<256,4,0>", 0),
     "combine_fwd.out": (r"cm_out_kernel<0,0>", 0), "combine_fwd.logits": (r"cm_logits_kernel", 0),
     "combine_bwd.rowdot": (r"rank1_rowdot_kernel<768>", 0), "combine_bwd.dZ.rows": (r"bwd_z_rows_kernel<768>", 0),
     "combine_bwd.dZ.ident": (r"bwd_z_ident_kernel<768>", 0), "combine_bwd.dbeta": (r"cm_dbeta_kernel", 0),
