@@ -55,6 +55,17 @@ class Expert(nn.Module):
         return out
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def _expert_param_list(experts: Sequence[Expert]) -> List[torch.Tensor]:
     ps: List[torch.Tensor] = []
     for ex in experts:
@@ -88,14 +99,21 @@ class _ExpertsFunction(torch.autograd.Function):
         feat_needs_grad = [f.requires_grad for f in feats]
         param_needs_grad = any(p.requires_grad for p in params)
 
-        # ---- bf16 shadows of the fp32 master weights, stacked over experts (+ transposes for dgrad): ONE launch ----
-        pk = ops.pack_expert_params(params, E, S, widths, D, H, need_T=param_needs_grad or any(feat_needs_grad))
+        # ---- bf16 shadows of the fp32 master weights, stacked over experts (+ transposes for dgrad): ONE launch, on a side
+        #      stream: it depends on nothing but the parameters, so it runs under the counting sort and the row permutation
+        #      (fork / join by events: capturable in a CUDA graph) ----
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)
+        pk = ops.pack_expert_params(params, E, S, widths, D, H, need_T=param_needs_grad or any(feat_needs_grad),
+                                    launch_stream=side)
         Wp, W1, bp, b1, w2, b2 = pk["Wp"], pk["W1"], pk["bp"], pk["b1"], pk["w2"], pk["b2"]
 
         layout = make_layout(B, topk, E, P)
         plan = build_plan(item_expert.reshape(-1).contiguous(), layout)
         feats_c = [f.contiguous() for f in feats]
         fs = ops.dispatch_rows(feats_c, plan, widths)
+        cur.wait_stream(side)
 
         Y = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
         Z = torch.empty(layout.total_rows, H, dtype=torch.bfloat16, device=dev)

@@ -145,11 +145,13 @@ def transpose_cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def pack_expert_params(params: Sequence[torch.Tensor], E: int, S: int, widths: Sequence[int], D: int, H: int, need_T: bool):
+def pack_expert_params(params: Sequence[torch.Tensor], E: int, S: int, widths: Sequence[int], D: int, H: int, need_T: bool,
+                       launch_stream=None):
     """The experts' fp32 master parameters -> stacked kernel operands, in one launch (mm_pack_expert_params).
     params: per expert [conv_s.weight, conv_s.bias] * S + [attn0.weight, attn0.bias, attn2.weight, attn2.bias].
     Returns dict: Wp[s] bf16 [E*D, D_s], WpT[s] bf16 [E*D_s, D] | None, W1 bf16 [E*H, D], W1T bf16 [E*D, H] | None,
-    bp[s] fp32 [E, D], b1 [E, H], w2 [E, H], b2 [E]."""
+    bp[s] fp32 [E, D], b1 [E, H], w2 [E, H], b2 [E].
+    `launch_stream`: enqueue the kernel there (the caller forks / joins); the buffers are allocated under the current stream."""
     per = 2 * S + 4
     dev = params[0].device
     keep = []                                     # fp32 / contiguous temporaries stay alive until the launch is enqueued
@@ -195,8 +197,11 @@ def pack_expert_params(params: Sequence[torch.Tensor], E: int, S: int, widths: S
         job(params[base + 2 * S + 2], out["w2"][e], None, 1, H, 1)
         job(params[base + 2 * S + 3], out["b2"][e:e + 1], None, 1, 1, 1)
     n = len(src)
+    # (temporaries of non-fp32 parameters are freed right after the call, and the per-call event profiler records on the current
+    # stream: both cases keep the launch there)
+    st = launch_stream.cuda_stream if (launch_stream is not None and not keep and _lib.PROFILER is None) else _st()
     _lib.call("mm_pack_expert_params", (_lib.C.c_void_p * n)(*src), (_lib.C.c_void_p * n)(*dst), (_lib.C.c_void_p * n)(*dstT),
-              _lib.host_i32(rows), _lib.host_i32(cols), _lib.host_i32(kind), n, _st())
+              _lib.host_i32(rows), _lib.host_i32(cols), _lib.host_i32(kind), n, st)
     del keep
     return out
 
