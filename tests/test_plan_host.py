@@ -30,6 +30,14 @@ def _check(n_items, K, P, seed, topk=1):
             for r in (r0, r0 + P[s] - 1):
                 e, valid = ref["tile_info"][r // 128]
                 assert e == ref["slot_expert"][slot] and r % 128 < valid
+    # CTA pairs (tcgen05 cta_group::2 kernels): segments start on 256-row boundaries and regions hold an even number of tiles,
+    # so the tiles (2j, 2j + 1) of a region never belong to two experts
+    for s in range(lay.S):
+        assert lay.tile_base[s] % 2 == 0 and lay.region_tiles[s] % 2 == 0
+        assert all(ref["seg_start"][s][e] % mmplan.SEG_ALIGN == 0 for e in range(K))
+        for t in range(lay.tile_base[s], lay.tile_base[s] + lay.region_tiles[s], 2):
+            e0, e1 = ref["tile_info"][t][0], ref["tile_info"][t + 1][0]
+            assert e0 == e1 or e0 < 0 or e1 < 0, (s, t, e0, e1)
     # wgrad chunks: disjoint, cover every owned tile once, never mix experts
     covered = {}
     for (e, first, cnt, s) in ref["chunks"]:
