@@ -203,6 +203,14 @@ undispatch_rows_kernel(UndispatchRowsArgs a, const int* __restrict__ inv_perm, c
     if (e0 >= per_item) return;
     const long long e1 = min(per_item, e0 + DISPATCH_ELEMS_PER_BLOCK);
     const int n_items = a.n_images * a.topk;
+    if (sizeof(DstT) == 2 && a.topk == 1) {
+        // one choice per image, bf16 in and out: a plain permuted copy (no unpack / accumulate / repack, source row looked up once)
+        const int slot = inv_perm[img];
+        const __nv_bfloat16* src = a.src[s] + static_cast<long long>(slot_row[s * n_items + slot] - a.region_base[s]) * a.D[s];
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(a.dst[s]) + img * per_item;
+        for (long long i = e0 + threadIdx.x * 8; i < e1; i += 256 * 8) stg_v4(d + i, ldg_nc_v4(src + i));
+        return;
+    }
     for (long long i = e0 + threadIdx.x * 8; i < e1; i += 256 * 8) {
         float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = 0; j < a.topk; ++j) {

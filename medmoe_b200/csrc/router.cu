@@ -137,36 +137,56 @@ router_bwd_sample_kernel(const float* __restrict__ dprobs, const float* __restri
 // dW2[e, o] = sum_b dlogit[b, e] hidden[b, o], db2[e] = sum_b dlogit[b, e]   (blocks 0 .. K-1, thread = hidden unit o)
 // db1[o]    = sum_b dhidden[b, o]                                            (block K)
 // coalesced over o, batch reduction in a fixed order (deterministic); replaces two latency-bound launches of batch_outer_kernel.
-__global__ void __launch_bounds__(ROUTER_HID)
+constexpr int ROUTER_SMALL_SLICES = 8;      // batch slices per block: 8 x 128 threads, eight loads in flight per thread
+__global__ void __launch_bounds__(ROUTER_HID * ROUTER_SMALL_SLICES)
 router_bwd_small_kernel(const float* __restrict__ dlogit, const float* __restrict__ hidden, const float* __restrict__ dhidden,
                         int B, int K, float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ db1) {
-    const int o = threadIdx.x, e = blockIdx.x;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+    __shared__ float s_acc[ROUTER_SMALL_SLICES][ROUTER_HID];
+    __shared__ float s_accb[ROUTER_SMALL_SLICES];
+    const int o = threadIdx.x, sl = threadIdx.y, e = blockIdx.x;
+    // slice sl takes the rows b = sl, sl + SLICES, ...; partial sums are combined in slice order (deterministic)
+    float acc = 0.f, accb = 0.f;
     if (e < K) {
-        int b = 0;
-        for (; b + 4 <= B; b += 4) {
+        int b = sl;
+        for (; b + 7 * ROUTER_SMALL_SLICES < B; b += 8 * ROUTER_SMALL_SLICES) {
+            float l[8], h[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float l = __ldg(dlogit + static_cast<size_t>(b + u) * K + e);
-                acc[u] = fmaf(l, __ldg(hidden + static_cast<size_t>(b + u) * ROUTER_HID + o), acc[u]);
-                accb[u] += l;
+            for (int u = 0; u < 8; ++u) {
+                l[u] = __ldg(dlogit + static_cast<size_t>(b + u * ROUTER_SMALL_SLICES) * K + e);
+                h[u] = __ldg(hidden + static_cast<size_t>(b + u * ROUTER_SMALL_SLICES) * ROUTER_HID + o);
             }
-        }
-        for (; b < B; ++b) {
-            const float l = __ldg(dlogit + static_cast<size_t>(b) * K + e);
-            acc[0] = fmaf(l, __ldg(hidden + static_cast<size_t>(b) * ROUTER_HID + o), acc[0]);
-            accb[0] += l;
-        }
-        dW2[e * ROUTER_HID + o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        if (o == 0) db2[e] = (accb[0] + accb[1]) + (accb[2] + accb[3]);
-    } else {
-        int b = 0;
-        for (; b + 4 <= B; b += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] += __ldg(dhidden + static_cast<size_t>(b + u) * ROUTER_HID + o);
+            for (int u = 0; u < 8; ++u) { acc = fmaf(l[u], h[u], acc); accb += l[u]; }
         }
-        for (; b < B; ++b) acc[0] += __ldg(dhidden + static_cast<size_t>(b) * ROUTER_HID + o);
-        db1[o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        for (; b < B; b += ROUTER_SMALL_SLICES) {
+            const float l = __ldg(dlogit + static_cast<size_t>(b) * K + e);
+            acc = fmaf(l, __ldg(hidden + static_cast<size_t>(b) * ROUTER_HID + o), acc);
+            accb += l;
+        }
+    } else {
+        int b = sl;
+        for (; b + 7 * ROUTER_SMALL_SLICES < B; b += 8 * ROUTER_SMALL_SLICES) {
+            float h[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) h[u] = __ldg(dhidden + static_cast<size_t>(b + u * ROUTER_SMALL_SLICES) * ROUTER_HID + o);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += h[u];
+        }
+        for (; b < B; b += ROUTER_SMALL_SLICES) acc += __ldg(dhidden + static_cast<size_t>(b) * ROUTER_HID + o);
+    }
+    s_acc[sl][o] = acc;
+    if (o == 0) s_accb[sl] = accb;
+    __syncthreads();
+    if (sl == 0) {
+        float t = 0.f, tb = 0.f;
+#pragma unroll
+        for (int k = 0; k < ROUTER_SMALL_SLICES; ++k) { t += s_acc[k][o]; tb += s_accb[k]; }
+        if (e < K) {
+            dW2[e * ROUTER_HID + o] = t;
+            if (o == 0) db2[e] = tb;
+        } else {
+            db1[o] = t;
+        }
     }
 }
 
@@ -207,7 +227,7 @@ extern "C" int mm_router_bwd(const float* dprobs, const float* probs, const floa
         if (int rc = run_sgemm(g, st, "mm_router_bwd(dW1)")) return rc;
     }
     // dW2[K, 128] = dlogit^T h, db2 = sum_b dlogit, db1 = sum_b dh: one launch
-    router_bwd_small_kernel<<<K + 1, ROUTER_HID, 0, st>>>(dlogit, hidden, dhidden, B, K, dW2, db2, db1);
+    router_bwd_small_kernel<<<K + 1, dim3(ROUTER_HID, ROUTER_SMALL_SLICES), 0, st>>>(dlogit, hidden, dhidden, B, K, dW2, db2, db1);
     mm::note_launches(1);
     return mm_check_launch("mm_router_bwd");
 }
