@@ -1009,10 +1009,12 @@ combine_bwd_finalize_kernel(const CombineArgs a, int s) {
 }
 
 // out[e, c] = sum over the slots of expert e and their nrb blocks of part[slot, blk, c].
-// grid = (ceil(C / 32), K); block = 32 columns x 8 row groups, fixed summation order (deterministic).
-__global__ void __launch_bounds__(256)
+// grid = (ceil(C / 32), K); block = 32 columns x 32 row groups (the 100 blocks of cfg2 are latency-bound: the more row groups,
+// the shorter each thread's serial chain of loads), fixed summation order (deterministic).
+constexpr int ER_GROUPS = 32;
+__global__ void __launch_bounds__(32 * ER_GROUPS)
 expert_reduce_kernel(const float* __restrict__ part, const int* __restrict__ offsets, int nrb, int C, float* __restrict__ out) {
-    __shared__ float sm[8][33];
+    __shared__ float sm[ER_GROUPS][33];
     const int e = blockIdx.y;
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -1020,14 +1022,14 @@ expert_reduce_kernel(const float* __restrict__ part, const int* __restrict__ off
     float acc = 0.f;
     if (c < C) {
 #pragma unroll 8
-        for (long long r = lo + grp; r < hi; r += 8) acc += part[r * C + c];
+        for (long long r = lo + grp; r < hi; r += ER_GROUPS) acc += part[r * C + c];
     }
     sm[grp][cl] = acc;
     __syncthreads();
     if (grp == 0 && c < C) {
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) t += sm[g][cl];
+        for (int g = 0; g < ER_GROUPS; ++g) t += sm[g][cl];
         out[static_cast<size_t>(e) * C + c] = t;
     }
 }
@@ -1357,7 +1359,7 @@ extern "C" int mm_interp_softmax_combine_bwd(const void* Y, const void* Z, const
         if (rc) return rc;
     }
     const int C = 2 * (D / 2) + 1;
-    expert_reduce_kernel<<<dim3((C + 31) / 32, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
+    expert_reduce_kernel<<<dim3((C + 31) / 32, K), 32 * ER_GROUPS, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
     mm::note_launches(1);
     mm::trace_mark("combine_bwd.expert_reduce", st);
     return mm_check_launch("mm_interp_softmax_combine_bwd(reduce)");
@@ -1472,7 +1474,7 @@ extern "C" int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, co
         }
         mm::note_launches(1);
         mm::trace_mark("combine_bwd.rowdot", st);
-        rank1_coef_kernel<<<dim3((total + 255) / 256, a.n_items), 256, 0, st>>>(a, row_coef);
+        rank1_coef_kernel<<<dim3((rank1_coef_units(a) + 255) / 256, a.n_items), 256, 0, st>>>(a, row_coef);
         mm::note_launches(1);
         mm::trace_mark("combine_bwd.coef", st);
         rc = mm_check_launch("mm_interp_softmax_combine_bwd_tc(rank-1)");
@@ -1554,7 +1556,7 @@ extern "C" int mm_interp_softmax_combine_bwd_tc(const void* Y, const void* Z, co
     }
     if (rc) return rc;
     const int C = 2 * (D / 2) + 1;
-    expert_reduce_kernel<<<dim3((C + 31) / 32, K), 256, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
+    expert_reduce_kernel<<<dim3((C + 31) / 32, K), 32 * ER_GROUPS, 0, st>>>(part, offsets, a.nrb, C, dw2_db1_db2);
     mm::note_launches(1);
     mm::trace_mark("combine_bwd.expert_reduce", st);
     return mm_check_launch("mm_interp_softmax_combine_bwd_tc(reduce)");

@@ -77,13 +77,26 @@ rank1_rowdot_kernel(const CombineArgs a, float* __restrict__ row_dot, int* __res
     }
 }
 
-// grid = (ceil(sum Ps / 256), n_items); thread = native row: c[row] = g / P * sum over the row's token window of w_i(p) beta_s(p)
+// c[row] = g / P * sum over the row's token window of w_i(p) beta_s(p).
+// grid = (ceil(units / 256), n_items).  The two finest scales take one thread per native row (windows of 3 and ~10 tokens at
+// 224^2); the rows of the two coarsest scales have windows of ~34 and ~130 tokens, which one thread walks in 130 dependent
+// steps while the rest of the grid has long finished — they take a whole warp each (lanes stride the window, shuffle reduction).
 __global__ void __launch_bounds__(256)
 rank1_coef_kernel(const CombineArgs a, float* __restrict__ row_coef) {
     const int slot = blockIdx.y;
-    const int u = blockIdx.x * 256 + threadIdx.x;
-    const int total = a.Ps[0] + a.Ps[1] + a.Ps[2] + a.Ps[3];
-    if (u >= total) return;
+    const int fine = a.Ps[0] + a.Ps[1], coarse = a.Ps[2] + a.Ps[3];
+    const int fine_pad = (fine + 31) & ~31;                     // warps never mix the two kinds of units
+    const int unit = blockIdx.x * 256 + threadIdx.x;            // unit < fine: one thread per row; from fine_pad on 32 threads per coarse row
+    const int lane = threadIdx.x & 31;
+    const bool wide = unit >= fine_pad;
+    int u = unit, p_step = 1, p_off = 0;
+    if (wide) {
+        u = fine + (unit - fine_pad) / 32;
+        p_step = 32; p_off = lane;
+    } else if (unit >= fine) {
+        return;
+    }
+    if (u >= fine + coarse) return;
     int s, i;
     r1_split(a, u, s, i);
     const int item = a.perm[slot];
@@ -100,14 +113,20 @@ rank1_coef_kernel(const CombineArgs a, float* __restrict__ row_coef) {
     p_hi = min(p_hi, a.P);
     const float* bt = a.beta + static_cast<size_t>(slot) * a.P * 4 + s;
     float acc = 0.f;
-    for (int p = p_lo; p < p_hi; ++p) {
+    for (int p = p_lo + p_off; p < p_hi; p += p_step) {
         const LerpSrc L = lerp_src(p, scale, Ps);
         float w = 0.f;
         if (L.i0 == i) w += 1.0f - L.lam;
         if (L.i1 == i) w += L.lam;
         if (w != 0.f) acc = fmaf(w, bt[4LL * p], acc);
     }
+    if (wide) {
+        acc = warp_sum(acc);
+        if (lane != 0) return;
+    }
     row_coef[static_cast<long long>(a.slot_row[s * a.n_items + slot]) + i] = acc * g / static_cast<float>(a.P);
 }
+// number of thread units of rank1_coef_kernel per item
+static inline int rank1_coef_units(const CombineArgs& a) { return ((a.Ps[0] + a.Ps[1] + 31) & ~31) + 32 * (a.Ps[2] + a.Ps[3]); }
 
 }  // namespace mm
