@@ -222,8 +222,14 @@ static int launch_rows_pair(const RowsMaps& m, const RowsGemmArgs& args, cudaStr
 // rank-1 aux + gate epilogue on CTA pairs (the dY GEMM)
 template <int BN>
 static int launch_rows_pair_r1(const RowsMaps& m, const RowsGemmArgs& args, cudaStream_t st) {
-    constexpr int EW = MM_EPI_WARPS_RANK1;
-    constexpr int STAGES = 4;
+#ifndef MM_PAIR_R1_EW            // tuning experiments: MEDMOE_NVCC_EXTRA="-DMM_PAIR_R1_EW=8 -DMM_PAIR_R1_STAGES=5"
+#define MM_PAIR_R1_EW MM_EPI_WARPS_RANK1
+#endif
+#ifndef MM_PAIR_R1_STAGES
+#define MM_PAIR_R1_STAGES 4
+#endif
+    constexpr int EW = MM_PAIR_R1_EW;
+    constexpr int STAGES = MM_PAIR_R1_STAGES;
     using S = PairR1Smem<BN, STAGES, EW>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_rows_pair_r1_kernel<BN, STAGES, EW>;
