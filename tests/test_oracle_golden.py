@@ -150,3 +150,28 @@ def test_flava_label_smoothing_oracle_matches_reference_golden():
         assert abs(loss.item() - g[tag + "loss"].item()) < 1e-6 and abs(la.item() - g[tag + "loss_a"].item()) < 1e-6
         assert torch.allclose(a.grad, g[tag + "da"], atol=1e-7) and torch.allclose(b.grad, g[tag + "db"], atol=1e-7)
         assert abs(s.grad.item() - g[tag + "dscale"].item()) < 1e-5
+
+
+def test_storage_aware_expert_reduces_to_the_closed_form():
+    """`expert_forward_storage_aware` (the oracle variant that rounds Y and Z at the CUDA path's two storage points, used to pin
+    the attn_proj.0 gradient) is the closed form exactly when nothing is rounded, stays within bf16 rounding of it otherwise,
+    and its rounding is invisible to autograd (straight-through): gradients exist and are finite for every parameter."""
+    import torch
+    from oracle import moe_oracle as mo
+    params = mo.init_params(2, [8, 16, 32, 64], 64, 64, seed=3)
+    torch.manual_seed(4)
+    feats = [torch.randn(3, n, d) for n, d in zip([64, 16, 4, 1], [8, 16, 32, 64])]
+    ref = mo.expert_forward_closed_form(params, 1, feats)
+    same = mo.expert_forward_storage_aware(params, 1, feats, storage=None)
+    assert (ref - same).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    pr = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    stored = mo.expert_forward_storage_aware(pr, 1, feats, storage=torch.bfloat16)
+    rel = ((stored.detach() - ref).norm() / ref.norm()).item()
+    assert 0.0 < rel < 1e-2, rel
+    stored.square().sum().backward()
+    for k, v in pr.items():
+        if k.startswith("experts.1.") and not k.endswith("attn_proj.2.bias"):
+            assert v.grad is not None and torch.isfinite(v.grad).all() and v.grad.abs().max() > 0, k
+    # and through the routed block
+    (gf, lf, probs), idx = mo.moe_forward_sparse(params, feats, torch.randn(3, 64), storage=torch.bfloat16)
+    assert gf.shape == (3, 64) and torch.isfinite(lf).all()
