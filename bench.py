@@ -687,6 +687,7 @@ def main():
             nbytes[f"E1E4.s{s}"] = Bi * Ps[s] * (HIDDEN[s] + D + H) * 2
         nbytes["dY"] = R * (H + 2 * D) * 2 + (R * D * 2 if args.local_grad else R * 8)
         rows_c = sum(Ps) - P0
+        direct0 = bool(getattr(moe, "last_direct_finest", False))
         for k, v in {
             "combine_fwd.logits": sum(Ps) * H * 2 + P0 * 16,
             "combine_fwd.out": sum(Ps) * D * 2 + P0 * D * 2 / args.topk + P0 * 16,      # out is per image, Y rows per item
@@ -696,8 +697,9 @@ def main():
             "combine_bwd.rowdot": sum(Ps) * D * 2 + sum(Ps) * 8,
             "combine_bwd.dZ.rows": rows_c * H * 2 * 2,
             "combine_bwd.dZ.ident": P0 * H * 2 * 2 + P0 * 16,
-            "mm_dispatch_rows": 2 * sum(p * d for p, d in zip(Ps, HIDDEN)) * 2,
-            "mm_undispatch_rows": 2 * sum(p * d for p, d in zip(Ps, HIDDEN)) * 2,
+            # (the finest scale is not permuted when its consumers address the image-order tensor through the group map)
+            "mm_dispatch_rows": 2 * sum(p * d for p, d in list(zip(Ps, HIDDEN))[1 if direct0 else 0:]) * 2,
+            "mm_undispatch_rows": 2 * sum(p * d for p, d in list(zip(Ps, HIDDEN))[1 if direct0 else 0:]) * 2,
         }.items():
             nbytes[k] = v * Bi
         kernels = {}

@@ -144,6 +144,27 @@ int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long long ldf, co
                       const int32_t* tile_info, int tile_begin, int tile_count, void* Y, long long ld_y, void* Z,
                       long long ld_z, int flags, void* stream);
 
+/* ---- finest scale without a sorted copy ---------------------------------------------------
+ * P_0 = 3136 / 9216 rows per image are multiples of 64 and expert segments start on 256-row boundaries, so every 64-row
+ * group of the finest region's expert-sorted row space lies inside ONE image.  mm_dispatch_group_map writes
+ * g64[group] = first row of that group in IMAGE order (img * P0 + 64 j), -1 for padding; the three entry points below
+ * address the reference's own [B, P0, D_0] tensors through it with 64-row (32-row) TMA boxes, which replaces the permute
+ * of the finest stage feature (input of swin.py:41), its read by the conv weight gradient, and the un-permute of its
+ * gradient.  top-k == 1, bf16 features. */
+int mm_dispatch_group_map(const int32_t* perm, const int32_t* slot_row0, int n_items, int topk, int P0, int region_base0,
+                          int n_groups, int32_t* g64, void* stream);
+int mm_expert_b2b_fwd_gather(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
+                             long long ldwp, const float* bias1, const void* W1, int H, long long ldw1, const float* bias2,
+                             const int32_t* tile_info, int tile_begin, int tile_count, void* Y, long long ld_y, void* Z,
+                             long long ld_z, int flags, const int32_t* f_g64, void* stream);
+int mm_grouped_gemm_wgrad_colsum_gather(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows,
+                                        int N2, long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count,
+                                        int tile_base, float* out, float* colsum, const int32_t* b_g64, void* stream);
+int mm_grouped_gemm_rows_scatter(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                                 long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, const float* bias,
+                                 void* out, long long out_rows, long long ld_out, const int32_t* out_g64, int flags,
+                                 void* stream);
+
 /* ---- (4) interpolate + scale-softmax + weighted combine / scatter-back ------------------
  * replaces swin.py:42-80 (F.interpolate, stack/permute, attn_proj[1:], softmax over scales,
  * weighted sum) and swin.py:108-113 (gather, mean, local_feat layout).

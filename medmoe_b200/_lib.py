@@ -88,6 +88,13 @@ SIGNATURES = {
     "mm_l2_normalize_fwd": (c_int, [c_vp, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
     "mm_l2_normalize_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_f, c_vp, c_vp]),
     "mm_zeroshot_argmax": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp]),
+    "mm_dispatch_group_map": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "mm_expert_b2b_fwd_gather": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_vp, c_int, c_ll, c_vp, c_vp, c_int,
+                                         c_int, c_vp, c_ll, c_vp, c_ll, c_int, c_vp, c_vp]),
+    "mm_grouped_gemm_wgrad_colsum_gather": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_int,
+                                                    c_vp, c_vp, c_vp, c_vp]),
+    "mm_grouped_gemm_rows_scatter": (c_int, [c_vp, c_ll, c_int, c_ll, c_vp, c_int, c_int, c_ll, c_vp, c_int, c_int, c_vp, c_vp,
+                                             c_ll, c_ll, c_vp, c_int, c_vp]),
     "mm_p2p_workspace_bytes": (c_ll, [c_int, c_ll]),
     "mm_p2p_alloc": (c_int, [c_ll, c_vp, c_vp]),
     "mm_p2p_open": (c_int, [c_vp, c_vp]),

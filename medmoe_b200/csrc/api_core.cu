@@ -320,7 +320,8 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
                           long long ldw, const int32_t* tile_info, int tile_begin, int tile_count, int M,
                           const float* bias, const void* aux, long long ld_aux, const Rank1Aux* r1, const void* gate,
                           long long ld_gate, void* out, long long ld_out, int out_f32, float* colsum,
-                          float out_scale, int flags, void* stream, const int32_t* cap_len = nullptr, float cap_temp = 0.f) {
+                          float out_scale, int flags, void* stream, const int32_t* cap_len = nullptr, float cap_temp = 0.f,
+                          const int32_t* out_g64 = nullptr, long long out_rows = 0) {
     MM_REQUIRE(A && W && out, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows: null operand");
     MM_REQUIRE(!(flags & EPI_CAP_SOFTMAX) || (cap_len && !aux && !r1 && !gate && !out_f32 && !colsum), MM_ERR_UNSUPPORTED,
                "mm_grouped_gemm_rows: the caption-softmax epilogue is a plain bf16 epilogue and needs cap_len");
@@ -352,9 +353,11 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
                           "mm_grouped_gemm_rows(W)");
     if (rc) return rc;
     m.out = m.a; m.aux = m.a; m.gate = m.a;   // placeholders when unused
+    MM_REQUIRE(!out_g64 || (!out_f32 && !aux && !r1 && !gate && !colsum && tile_info && out_rows > 0), MM_ERR_UNSUPPORTED,
+               "mm_grouped_gemm_rows_scatter: plain bf16 epilogue with tile_info only");
     if (!out_f32) {
-        rc = encode_tmap(&m.out, out, static_cast<uint64_t>(N), io_rows, static_cast<uint64_t>(ld_out), 32, 32,
-                         CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(out)");
+        rc = encode_tmap(&m.out, out, static_cast<uint64_t>(N), out_g64 ? static_cast<uint64_t>(out_rows) : io_rows,
+                         static_cast<uint64_t>(ld_out), 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "mm_grouped_gemm_rows(out)");
         if (rc) return rc;
     }
     if (aux) {
@@ -387,8 +390,9 @@ static int gemm_rows_impl(const void* A, long long a_rows, int K, long long lda,
     g.ld_vecs = r1 ? r1->ld_vecs : 0;
     g.cap_len = cap_len;
     g.cap_temp = cap_temp;
+    g.out_g64 = out_g64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool pair_ok = (flags & EPI_PAIR_OK) && (tile_info ? (tile_begin % 2 == 0 && tile_count >= 2) : M > TILE_M);
+    const bool pair_ok = !out_g64 && (flags & EPI_PAIR_OK) && (tile_info ? (tile_begin % 2 == 0 && tile_count >= 2) : M > TILE_M);
     if (pair_ok && (pair_mode() & 2) && tile_info && r1 && !aux && gate && !colsum && out_scale == 1.0f && !bias && BN == 256) {
         rc = encode_tmap_bf16(&m.b, W, static_cast<uint64_t>(K), static_cast<uint64_t>(E) * N, static_cast<uint64_t>(ldw), 64,
                               BN / 2, "mm_grouped_gemm_rows_rank1(W, pair)");
@@ -430,6 +434,18 @@ extern "C" int mm_grouped_gemm_rows(const void* A, long long a_rows, int K, long
                           gate, ld_gate, out, ld_out, out_f32, colsum, out_scale, flags, stream);
 }
 
+// same plain bf16 GEMM whose output is in IMAGE order: 64-row group g of the launch's row space is stored at rows
+// out_g64[g] .. + 64 of out [out_rows, N] (mm_dispatch_group_map), padding groups are dropped — the un-permute of the result
+// (reference: the gradient of swin.py:105-108's gather) happens in the store.
+extern "C" int mm_grouped_gemm_rows_scatter(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
+                                            long long ldw, const int32_t* tile_info, int tile_begin, int tile_count,
+                                            const float* bias, void* out, long long out_rows, long long ld_out,
+                                            const int32_t* out_g64, int flags, void* stream) {
+    MM_REQUIRE(out_g64 && tile_info, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_rows_scatter: out_g64 and tile_info required");
+    return gemm_rows_impl(A, a_rows, K, lda, W, E, N, ldw, tile_info, tile_begin, tile_count, 0, bias, nullptr, 0, nullptr, nullptr, 0,
+                          out, ld_out, 0, nullptr, 1.0f, flags & ~EPI_PAIR_OK, stream, nullptr, 0.f, out_g64, out_rows);
+}
+
 // out = (A W_e^T + row_coef[row] * vecs[row_vec[row], :]) * [gate > 0]: the dY GEMM when only global_feat has a
 // cotangent, so that the combine's gradient w.r.t. Y is rank-1 per image and never materialised.
 extern "C" int mm_grouped_gemm_rows_rank1(const void* A, long long a_rows, int K, long long lda, const void* W, int E, int N,
@@ -458,7 +474,7 @@ extern "C" int mm_local_scores_softmax_exp(const void* A, long long rows, int K,
 // dW[e][N1, N2] += sum_rows A[row, N1]^T B[row, N2] over the chunks of expert e (+ optional column sums of A).
 static int gemm_wgrad_impl(const void* A, long long a_rows, int N1, long long lda, const void* B, long long b_rows, int N2,
                            long long ldb, const int32_t* chunks, int chunk_begin, int chunk_count, int tile_base,
-                           float* out, float* colsum, void* stream) {
+                           float* out, float* colsum, void* stream, const int32_t* b_g64 = nullptr) {
     MM_REQUIRE(A && B && out && chunks, MM_ERR_BAD_SHAPE, "mm_grouped_gemm_wgrad: null operand");
     MM_REQUIRE(N1 > 0 && N1 % 8 == 0 && N2 > 0 && N2 % 8 == 0, MM_ERR_BAD_SHAPE,
                "mm_grouped_gemm_wgrad: N1, N2 must be positive multiples of 8");
@@ -488,6 +504,7 @@ static int gemm_wgrad_impl(const void* A, long long a_rows, int N1, long long ld
     g.n_j = (N2 + BN - 1) / BN;
     g.out = out;
     g.colsum = colsum;
+    g.b_g64 = b_g64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (colsum) {
         switch (BN) {
@@ -523,3 +540,16 @@ extern "C" int mm_grouped_gemm_wgrad_colsum(const void* A, long long a_rows, int
     return gemm_wgrad_impl(A, a_rows, N1, lda, B, b_rows, N2, ldb, chunks, chunk_begin, chunk_count, tile_base, out, colsum,
                            stream);
 }
+
+// mm_grouped_gemm_wgrad_colsum with B in IMAGE order: 64-row group g of the launch's row space = rows b_g64[g] .. + 64 of B
+// (mm_dispatch_group_map; the rows of A that belong to padding groups are zero).
+extern "C" int mm_grouped_gemm_wgrad_colsum_gather(const void* A, long long a_rows, int N1, long long lda, const void* B,
+                                                   long long b_rows, int N2, long long ldb, const int32_t* chunks,
+                                                   int chunk_begin, int chunk_count, int tile_base, float* out, float* colsum,
+                                                   const int32_t* b_g64, void* stream) {
+    MM_REQUIRE(colsum && b_g64 && tile_base == 0, MM_ERR_BAD_SHAPE,
+               "mm_grouped_gemm_wgrad_colsum_gather: colsum / b_g64 required, tile_base must be 0 (groups are launch-relative)");
+    return gemm_wgrad_impl(A, a_rows, N1, lda, B, b_rows, N2, ldb, chunks, chunk_begin, chunk_count, tile_base, out, colsum,
+                           stream, b_g64);
+}
+

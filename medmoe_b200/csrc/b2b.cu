@@ -72,10 +72,10 @@ extern "C" int mm_expert_b2b_fwd_supported(int K1, int D, int H) {
 
 // Y = ReLU(f Wp_e^T + bp_e) (bf16, written once) and Z = Y W1_e^T + b1_e (bf16) over the 128-row tiles
 // [tile_begin, tile_begin + tile_count) of one scale region; f / Y / Z point at the region's first row.
-extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
-                                 long long ldwp, const float* bias1, const void* W1, int H, long long ldw1,
-                                 const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
-                                 long long ld_y, void* Z, long long ld_z, int flags, void* stream) {
+static int b2b_fwd_impl(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
+                        long long ldwp, const float* bias1, const void* W1, int H, long long ldw1,
+                        const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
+                        long long ld_y, void* Z, long long ld_z, int flags, const int32_t* f_g64, void* stream) {
     MM_REQUIRE(f && Wp && W1 && bias1 && bias2 && tile_info && Y && Z, MM_ERR_BAD_SHAPE, "mm_expert_b2b_fwd: null operand");
     const int sup = mm_expert_b2b_fwd_supported(K1, D, H);
     MM_REQUIRE(sup == 1 || (sup == 2 && (flags & 1) && tile_count >= 2), MM_ERR_UNSUPPORTED,
@@ -85,9 +85,10 @@ extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long l
     // flags & 1: the caller guarantees that the tiles (2j, 2j + 1) of this launch never belong to two experts (SEG_ALIGN row
     // layout) -> CTA pairs (cta_group::2) share every weight tile: each CTA stages half of its rows
     const bool pairs = (flags & 1) && !(b2b_debug_flags() & 1) && tile_count >= 2;
+    MM_REQUIRE(!f_g64 || pairs, MM_ERR_UNSUPPORTED, "mm_expert_b2b_fwd_gather: the group-map addressing of f needs the CTA-pair kernel (flags & 1)");
     CUtensorMap tA1, tB1, tB2, tY, tZ;
     int rc = encode_tmap_bf16(&tA1, f, static_cast<uint64_t>(K1), static_cast<uint64_t>(f_rows), static_cast<uint64_t>(ldf), 64,
-                              TILE_M, "mm_expert_b2b_fwd(f)");
+                              f_g64 ? 64 : TILE_M, "mm_expert_b2b_fwd(f)");
     if (rc) return rc;
     rc = encode_tmap_bf16(&tB1, Wp, static_cast<uint64_t>(K1), static_cast<uint64_t>(E) * D, static_cast<uint64_t>(ldwp), 64,
                           pairs ? B2B_NC / 2 : B2B_NC, "mm_expert_b2b_fwd(Wp)");
@@ -112,9 +113,29 @@ extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long l
     g.ld_y = ld_y;
     g.z = static_cast<__nv_bfloat16*>(Z);
     g.ld_z = ld_z;
+    g.f_g64 = f_g64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (pairs) return K1 <= 64    ? launch_b2b_pair_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st)
                       : K1 <= 128 ? launch_b2b_pair_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st)
                                   : launch_b2b_pair_fwd<3>(tA1, tB1, tB2, tY, tZ, g, st);
     return K1 <= 64 ? launch_b2b_fwd<1>(tA1, tB1, tB2, tY, tZ, g, st) : launch_b2b_fwd<2>(tA1, tB1, tB2, tY, tZ, g, st);
+}
+
+extern "C" int mm_expert_b2b_fwd(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
+                                 long long ldwp, const float* bias1, const void* W1, int H, long long ldw1,
+                                 const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
+                                 long long ld_y, void* Z, long long ld_z, int flags, void* stream) {
+    return b2b_fwd_impl(f, f_rows, K1, ldf, Wp, E, D, ldwp, bias1, W1, H, ldw1, bias2, tile_info, tile_begin, tile_count, Y, ld_y, Z,
+                        ld_z, flags, nullptr, stream);
+}
+
+// same with f in IMAGE order ([f_rows, K1] = the reference's [B, P, K1] stage feature itself): the 64-row groups of the launch's
+// expert-sorted row space are addressed through f_g64 (mm_dispatch_group_map), so no sorted copy of f is made.  Needs flags & 1.
+extern "C" int mm_expert_b2b_fwd_gather(const void* f, long long f_rows, int K1, long long ldf, const void* Wp, int E, int D,
+                                        long long ldwp, const float* bias1, const void* W1, int H, long long ldw1,
+                                        const float* bias2, const int32_t* tile_info, int tile_begin, int tile_count, void* Y,
+                                        long long ld_y, void* Z, long long ld_z, int flags, const int32_t* f_g64, void* stream) {
+    MM_REQUIRE(f_g64, MM_ERR_BAD_SHAPE, "mm_expert_b2b_fwd_gather: f_g64 is NULL");
+    return b2b_fwd_impl(f, f_rows, K1, ldf, Wp, E, D, ldwp, bias1, W1, H, ldw1, bias2, tile_info, tile_begin, tile_count, Y, ld_y, Z,
+                        ld_z, flags, f_g64, stream);
 }

@@ -42,6 +42,8 @@ struct B2BFwdArgs {
     long long ld_y;
     __nv_bfloat16* z;
     long long ld_z;
+    const int* f_g64;        // pair kernel only, or nullptr: f is in IMAGE order and 64-row group g of the launch's (expert-sorted) row
+                             // space lives at rows f_g64[g] .. + 64 of it (mm_dispatch_group_map; -1 = padding): no sorted copy of f
 };
 
 constexpr int B2B_D = 768, B2B_H = 384, B2B_NC = 64, B2B_NCH = B2B_D / B2B_NC;   // 12 chunks
@@ -556,8 +558,17 @@ b2b_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
                             a1ph ^= 1;
                             if (rank == 0) mbar_expect_tx(a1full, 2 * NKB1 * 16384);
                             const int lt = min(2 * p1 + static_cast<int>(rank), a.tile_count - 1);
+                            if (a.f_g64) {      // two 64-row boxes per k block, addressed through the group map (padding groups read group 0)
+                                const int r0 = max(a.f_g64[2 * lt], 0), r1 = max(a.f_g64[2 * lt + 1], 0);
 #pragma unroll
-                            for (int kb = 0; kb < NKB1; ++kb) tma_load_2d_pair(sA1 + kb * 16384, &tmA1, bar_a1, kb * 64, lt * TILE_M);
+                                for (int kb = 0; kb < NKB1; ++kb) {
+                                    tma_load_2d_pair(sA1 + kb * 16384, &tmA1, bar_a1, kb * 64, r0);
+                                    tma_load_2d_pair(sA1 + kb * 16384 + 8192, &tmA1, bar_a1, kb * 64, r1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int kb = 0; kb < NKB1; ++kb) tma_load_2d_pair(sA1 + kb * 16384, &tmA1, bar_a1, kb * 64, lt * TILE_M);
+                            }
                             c1 = 0; progressed = true;
                         }
                     } else {

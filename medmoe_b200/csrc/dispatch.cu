@@ -261,9 +261,42 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
     }
 }
 
+// g64[group] = first row, in image order, of the 64 consecutive rows that make up 64-row group `group` of the finest region's
+// expert-sorted row space (or -1 for padding / slack).  P0 % 64 == 0 and segments start on 256-row boundaries, so a group never
+// straddles two items.  With this map the finest scale needs no sorted copy: TMA boxes of 64 rows are addressed through it.
+// grid = (ceil(P0 / 64 / 256) | ceil(n_groups / 256), n_items + 1); block y == n_items clears, the others fill their item's groups.
+__global__ void __launch_bounds__(256)
+group_map_fill_kernel(const int* __restrict__ perm, const int* __restrict__ slot_row0, int n_items, int topk, int P0, int region_base0,
+                      int* __restrict__ g64) {
+    const int slot = blockIdx.y;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= P0 / 64) return;
+    const int img = perm[slot] / topk;
+    g64[(slot_row0[slot] - region_base0) / 64 + j] = img * P0 + 64 * j;
+}
+__global__ void __launch_bounds__(256) group_map_clear_kernel(int* __restrict__ g64, int n_groups) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g < n_groups) g64[g] = -1;
+}
+
 }  // namespace mm
 
 using namespace mm;
+
+// see include/medmoe_b200.h
+extern "C" int mm_dispatch_group_map(const int32_t* perm, const int32_t* slot_row0, int n_items, int topk, int P0,
+                                     int region_base0, int n_groups, int32_t* g64, void* stream) {
+    MM_REQUIRE(perm && slot_row0 && g64 && n_items >= 0 && topk >= 1 && P0 > 0 && P0 % 64 == 0 && region_base0 % 64 == 0 &&
+                   n_groups >= 0,
+               MM_ERR_BAD_SHAPE, "mm_dispatch_group_map: P0 and region_base0 must be multiples of 64");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_groups == 0) return MM_OK;
+    group_map_clear_kernel<<<(n_groups + 255) / 256, 256, 0, st>>>(g64, n_groups);
+    if (n_items > 0) group_map_fill_kernel<<<dim3((P0 / 64 + 255) / 256, n_items), 256, 0, st>>>(perm, slot_row0, n_items, topk, P0,
+                                                                                                region_base0, g64);
+    mm::note_launches(2);
+    return mm_check_launch("mm_dispatch_group_map");
+}
 
 extern "C" int mm_dispatch_build(const int32_t* item_expert, int n_items, int K, int S, const int32_t* P,
                                  const int32_t* region_base, const int32_t* region_tiles, const int32_t* chunk_base,

@@ -61,6 +61,9 @@ struct RowsGemmArgs {
     // EPI_CAP_SOFTMAX (word-patch attention scores, local_loss.cu): words per caption of each 32-column chunk, temperature
     const int* cap_len;
     float cap_temp;
+    // single-CTA bf16 epilogue only, or nullptr: the output is in IMAGE order; the 32 x 32 boxes of 64-row group g of the launch's
+    // row space go to rows out_g64[g] .. + 64 of it (mm_dispatch_group_map), padding groups (-1) and unowned tiles are not stored
+    const int* out_g64;
 };
 
 struct WgradArgs {
@@ -71,6 +74,8 @@ struct WgradArgs {
     int n_i, n_j;            // tiles along N1 (128 each) and N2 (BN each)
     float* out;              // [E, N1, N2] fp32, accumulated with red.add
     float* colsum;           // COLSUM only: [E, N1] fp32, += sum over rows of A[row, i] (column sums of A on the tensor cores)
+    const int* b_g64;        // or nullptr: B is in IMAGE order; 64-row group g of the launch's row space = rows b_g64[g] .. + 64 of B
+                             // (mm_dispatch_group_map; -1 = padding, whose rows of A are zero)
 };
 
 constexpr int EPI_SLOT_BYTES = 32 * 64;   // 32 rows x 32 bf16 columns
@@ -210,7 +215,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===================== tiles no expert owns =====================
         // The capacity slack behind a region's last segment gets defined contents (zeros), so that consumers which
         // stage whole row ranges with TMA (combine_mma.cuh) never multiply uninitialised memory by a zero coefficient.
-        if (!OUT_F32 && a.tile_info) {
+        if (!OUT_F32 && a.tile_info && !a.out_g64) {
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int lt = w / a.n_tiles, nt = w - lt * a.n_tiles;
                 if (a.tile_info[a.tile_begin + lt].x >= 0) continue;
@@ -382,7 +387,12 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmOut, so, col0, lt * TILE_M + q * 32);
+                        int orow = lt * TILE_M + q * 32;
+                        if (a.out_g64) {
+                            const int g = a.out_g64[2 * lt + (q >> 1)];
+                            orow = g < 0 ? -1 : g + (q & 1) * 32;
+                        }
+                        if (orow >= 0) tma_store_2d(&tmOut, so, col0, orow);
                         tma_store_commit();
                     }
                     if (S::OUT_SLOTS == 2) oslot ^= 1;
@@ -481,11 +491,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     uint8_t* dA = sA + stage * S::A_BYTES;
                     uint8_t* dB = sB + stage * B_STAGE;
                     const int r = row0 + kb * 64;
+                    const int rb = a.b_g64 ? max(a.b_g64[r >> 6], 0) : r;
                     tma_load_2d(dA, &tmA, &full[stage], it * 128, r);
                     tma_load_2d(dA + 8192, &tmA, &full[stage], it * 128 + 64, r);
 #pragma unroll
                     for (int j = 0; j < NB_CHUNKS; ++j)
-                        tma_load_2d(dB + j * 8192, &tmB, &full[stage], jt * BN + j * 64, r);
+                        tma_load_2d(dB + j * 8192, &tmB, &full[stage], jt * BN + j * 64, rb);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }

@@ -112,7 +112,14 @@ class _ExpertsFunction(torch.autograd.Function):
         layout = make_layout(B, topk, E, P)
         plan = build_plan(item_expert.reshape(-1).contiguous(), layout)
         feats_c = [f.contiguous() for f in feats]
-        fs = ops.dispatch_rows(feats_c, plan, widths)
+        # The finest scale (53 % of the permuted bytes) needs no sorted copy: P_0 is a multiple of 64 and segments start on 256-row
+        # boundaries, so its consumers address the image-order tensor through a 64-row group map (top-1, bf16 features, CTA-pair
+        # back-to-back kernel).  fs[0] / the sorted d f_0 then do not exist.
+        direct0 = (ops.USE_DIRECT_FINEST and topk == 1 and in_dtype == torch.bfloat16 and P[0] % 64 == 0 and
+                   ops.expert_b2b_supported(widths[0], D, H) and ops.b2b_pairs_available() and layout.region_tiles[0] >= 2)
+        g64 = ops.group_map(plan) if direct0 else None
+        feat0_2d = feats_c[0].view(B * P[0], widths[0]) if direct0 else None
+        fs = ops.dispatch_rows(feats_c, plan, widths, first_scale=1 if direct0 else 0)
         cur.wait_stream(side)
 
         Y = torch.empty(layout.total_rows, D, dtype=torch.bfloat16, device=dev)
@@ -126,8 +133,9 @@ class _ExpertsFunction(torch.autograd.Function):
             n_fused += 1
         for s in range(n_fused):
             r0, nr = layout.region_base[s], layout.region_rows[s]
-            ops.expert_b2b_fwd(fs[s], Wp[s], bp[s], W1, b1, Y[r0:r0 + nr], Z[r0:r0 + nr], plan=plan,
-                               tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"E1E4.s{s}")
+            ops.expert_b2b_fwd(feat0_2d if (direct0 and s == 0) else fs[s], Wp[s], bp[s], W1, b1, Y[r0:r0 + nr], Z[r0:r0 + nr],
+                               plan=plan, tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"E1E4.s{s}",
+                               f_g64=g64 if s == 0 else None)
 
         def e1(s):
             r0 = layout.region_base[s]
@@ -146,6 +154,9 @@ class _ExpertsFunction(torch.autograd.Function):
         ctx.plan, ctx.layout = plan, layout
         ctx.dims = (B, E, S, D, H, widths, topk, per, in_dtype)
         ctx.saved = (fs, Y, Z, beta, w2, pk["W1T"], pk["WpT"], gate_flat)
+        ctx.direct0 = (g64, feat0_2d)
+        if owner is not None:
+            owner.last_direct_finest = direct0
         ctx.feat_needs_grad = feat_needs_grad
         ctx.param_needs_grad = param_needs_grad
         ctx.gate_needs_grad = gate is not None and gate.requires_grad
@@ -158,6 +169,7 @@ class _ExpertsFunction(torch.autograd.Function):
         plan, layout = ctx.plan, ctx.layout
         B, E, S, D, H, widths, topk, per, in_dtype = ctx.dims
         fs, Y, Z, beta, w2, W1T, WsT, gate_flat = ctx.saved
+        g64, feat0_2d = ctx.direct0
         dev = Y.device
         n_in = 6 + S + E * per
         if dfused is None and dglobal is None:
@@ -219,6 +231,9 @@ class _ExpertsFunction(torch.autograd.Function):
 
             def dwp(s):
                 r0, nr = layout.region_base[s], layout.region_rows[s]
+                if s == 0 and g64 is not None:      # B operand = the image-order stage feature, through the group map
+                    return lambda: ops.gemm_wgrad(dPre[r0:r0 + nr], feat0_2d, dWp[s], plan, layout.chunk_base[s], layout.chunk_cap[s],
+                                                  layout.tile_base[s], tag=f"dWp.s{s}", colsum=dbp[s], b_g64=g64)
                 return lambda: ops.gemm_wgrad(dPre[r0:r0 + nr], fs[s], dWp[s], plan, layout.chunk_base[s], layout.chunk_cap[s],
                                               layout.tile_base[s], tag=f"dWp.s{s}", colsum=dbp[s])
             ops.run_scales([dwp(s) for s in range(S)])
@@ -238,14 +253,22 @@ class _ExpertsFunction(torch.autograd.Function):
 
         grads_feats: List = [None] * S
         if any(ctx.feat_needs_grad):
-            dfs = [torch.empty(layout.region_rows[s], widths[s], dtype=torch.bfloat16, device=dev) for s in range(S)]
+            d0 = g64 is not None          # the finest scale's gradient is stored in image order by its GEMM (no sorted copy, no un-permute)
+            dfs = [None if (d0 and s == 0) else torch.empty(layout.region_rows[s], widths[s], dtype=torch.bfloat16, device=dev)
+                   for s in range(S)]
+            dfeat0 = torch.empty(B * layout.P[0], widths[0], dtype=torch.bfloat16, device=dev) if d0 else None
 
             def dx(s):   # df_s = dPre_s W_s
                 r0, nr = layout.region_base[s], layout.region_rows[s]
+                if d0 and s == 0:
+                    return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfeat0, plan=plan, tile_begin=layout.tile_base[s],
+                                                 tile_count=layout.region_tiles[s], tag=f"dX.s{s}", out_g64=g64)
                 return lambda: ops.gemm_rows(dPre[r0:r0 + nr], WsT[s], widths[s], dfs[s], plan=plan, flags=ops.EPI_PAIR_OK,
                                              tile_begin=layout.tile_base[s], tile_count=layout.region_tiles[s], tag=f"dX.s{s}")
             ops.run_scales([dx(s) for s in range(S)])
-            outs = ops.undispatch_rows(dfs, plan, widths, in_dtype)
+            outs = ops.undispatch_rows(dfs, plan, widths, in_dtype, first_scale=1 if d0 else 0)
+            if d0:
+                outs[0] = dfeat0.view(B, layout.P[0], widths[0])
             grads_feats = [o if need else None for o, need in zip(outs, ctx.feat_needs_grad)]
         dgate_out = dgate.view(B, topk) if dgate is not None else None
         return (None, dgate_out, None, None, None, None, *grads_feats, *grads_params)
@@ -300,6 +323,7 @@ class MoE(nn.Module):
         # early (medmoe_b200.distributed.OverlappedGradSync).
         self.last_flat_grad = None
         self.grad_ready_hook = None
+        self.last_direct_finest = False   # the most recent forward addressed the finest stage feature in image order (no sorted copy)
 
     def near_tie_count(self) -> int:
         """Images of the most recent forward whose expert choice hangs on a probability gap < 1e-6 (synchronises).

@@ -102,29 +102,49 @@ def router_bwd(dprobs, probs, hidden, x, W1, W2, need_dx: bool):
 
 
 # ---- dispatch -------------------------------------------------------------------------
-def dispatch_rows(feats: Sequence[torch.Tensor], plan: DispatchPlan, widths: Sequence[int]) -> List[torch.Tensor]:
-    """[B, P_s, D_s] (fp32|bf16, image order) -> bf16 [region_rows_s, D_s] (expert-sorted, padded)."""
+def dispatch_rows(feats: Sequence[torch.Tensor], plan: DispatchPlan, widths: Sequence[int], first_scale: int = 0) -> List:
+    """[B, P_s, D_s] (fp32|bf16, image order) -> bf16 [region_rows_s, D_s] (expert-sorted, padded).
+    `first_scale` = 1 leaves the finest scale out (its consumers address the image-order tensor through the group map):
+    the returned list then has None in its place."""
     lay = plan.layout
     _need_cuda(*feats)
     src_f32 = feats[0].dtype == torch.float32
     for f in feats:
         if f.dtype != feats[0].dtype or f.dtype not in (torch.float32, torch.bfloat16) or not f.is_contiguous():
             raise RuntimeError("stage features must be contiguous and all fp32 or all bf16")
-    dst = [torch.empty(lay.region_rows[s], widths[s], dtype=torch.bfloat16, device=feats[0].device) for s in range(lay.S)]
-    _lib.call("mm_dispatch_rows", _lib.host_ptrs(feats), int(src_f32), _lib.host_ptrs(dst), lay.n_items, lay.topk,
-              lay.num_experts, lay.S, _lib.host_i32(lay.P), _lib.host_i32(widths), _lib.host_i32(lay.region_base),
-              _P(plan.perm), _P(plan.slot_row), _P(plan.counts), _P(plan.seg_start), _st())
-    return dst
+    fs = first_scale
+    dst = [torch.empty(lay.region_rows[s], widths[s], dtype=torch.bfloat16, device=feats[0].device) for s in range(fs, lay.S)]
+    _lib.call("mm_dispatch_rows", _lib.host_ptrs(feats[fs:]), int(src_f32), _lib.host_ptrs(dst), lay.n_items, lay.topk,
+              lay.num_experts, lay.S - fs, _lib.host_i32(lay.P[fs:]), _lib.host_i32(widths[fs:]), _lib.host_i32(lay.region_base[fs:]),
+              _P(plan.perm), _P(plan.slot_row[fs:]), _P(plan.counts), _P(plan.seg_start[fs:]), _st())
+    return [None] * fs + dst
 
 
-def undispatch_rows(srcs: Sequence[torch.Tensor], plan: DispatchPlan, widths: Sequence[int], out_dtype) -> List[torch.Tensor]:
+def undispatch_rows(srcs: Sequence[torch.Tensor], plan: DispatchPlan, widths: Sequence[int], out_dtype, first_scale: int = 0) -> List:
+    """`first_scale` = 1: srcs[0] is ignored (the finest scale's gradient was stored in image order by its GEMM); None in its place."""
     lay = plan.layout
-    _need_cuda(*srcs)
-    dst = [torch.empty(lay.n_images, lay.P[s], widths[s], dtype=out_dtype, device=srcs[0].device) for s in range(lay.S)]
-    _lib.call("mm_undispatch_rows", _lib.host_ptrs(srcs), _lib.host_ptrs(dst), int(out_dtype == torch.float32),
-              lay.n_images, lay.topk, lay.S, _lib.host_i32(lay.P), _lib.host_i32(widths),
-              _lib.host_i32(lay.region_base), _P(plan.inv_perm), _P(plan.slot_row), _st())
-    return dst
+    fs = first_scale
+    _need_cuda(*srcs[fs:])
+    dst = [torch.empty(lay.n_images, lay.P[s], widths[s], dtype=out_dtype, device=srcs[fs].device) for s in range(fs, lay.S)]
+    _lib.call("mm_undispatch_rows", _lib.host_ptrs(srcs[fs:]), _lib.host_ptrs(dst), int(out_dtype == torch.float32),
+              lay.n_images, lay.topk, lay.S - fs, _lib.host_i32(lay.P[fs:]), _lib.host_i32(widths[fs:]),
+              _lib.host_i32(lay.region_base[fs:]), _P(plan.inv_perm), _P(plan.slot_row[fs:]), _st())
+    return [None] * fs + dst
+
+
+# The finest scale without a sorted copy (csrc: mm_dispatch_group_map and the *_gather / *_scatter entry points): top-1, bf16
+# features, P_0 a multiple of 64, CTA-pair back-to-back kernel available.  Switch kept for A/B measurements and tests.
+USE_DIRECT_FINEST = True
+
+
+def group_map(plan: DispatchPlan) -> torch.Tensor:
+    """int32 [region_rows_0 / 64]: first image-order row of every 64-row group of the finest region's sorted row space (-1: padding)."""
+    lay = plan.layout
+    n_groups = lay.region_rows[0] // 64
+    g64 = torch.empty(n_groups, dtype=torch.int32, device=plan.perm.device)
+    _lib.call("mm_dispatch_group_map", _P(plan.perm), _P(plan.slot_row), lay.n_items, lay.topk, lay.P[0], lay.region_base[0],
+              n_groups, _P(g64), _st())
+    return g64
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:
@@ -209,10 +229,17 @@ def pack_expert_params(params: Sequence[torch.Tensor], E: int, S: int, widths: S
 # ---- grouped GEMMs --------------------------------------------------------------------
 def gemm_rows(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, plan: Optional[DispatchPlan] = None,
               tile_begin: int = 0, tile_count: int = 0, M: int = 0, bias=None, aux=None, gate=None, colsum=None,
-              flags: int = 0, out_scale: float = 1.0, tag: str = ""):
-    """out[rows, N] = epi(A[rows, K] W_e[N, K]^T); W is the stacked [E * N, K] bf16 weight."""
+              flags: int = 0, out_scale: float = 1.0, tag: str = "", out_g64=None):
+    """out[rows, N] = epi(A[rows, K] W_e[N, K]^T); W is the stacked [E * N, K] bf16 weight.
+    `out_g64` (group map): `out` is in image order, the store un-permutes (plain bf16 epilogue, plan required)."""
     _need_cuda(A, W, out)
     E = W.shape[0] // N
+    if out_g64 is not None:
+        assert plan is not None and aux is None and gate is None and colsum is None and out.dtype == torch.bfloat16 and out_scale == 1.0
+        _lib.call("mm_grouped_gemm_rows_scatter", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(W), E, N, W.stride(0),
+                  _P(plan.tile_info), tile_begin, tile_count, _P(bias), _P(out), out.shape[0], out.stride(0), _P(out_g64), flags,
+                  _st(), label=f"{tag}:gemm_rows[K={A.shape[1]},N={N}]")
+        return out
     _lib.call("mm_grouped_gemm_rows", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(W), E, N, W.stride(0),
               _P(plan.tile_info) if plan is not None else 0, tile_begin, tile_count, M, _P(bias),
               _P(aux), aux.stride(0) if aux is not None else 0, _P(gate), gate.stride(0) if gate is not None else 0,
@@ -225,19 +252,30 @@ def gemm_rows(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor, *, pl
 USE_B2B_FWD = True
 
 
+def b2b_pairs_available() -> bool:
+    """CTA-pair back-to-back kernel not switched off (MEDMOE_B2B_DEBUG bit 0)."""
+    import os
+    return not (int(os.environ.get("MEDMOE_B2B_DEBUG", "0") or 0) & 1)
+
+
 def expert_b2b_supported(K1: int, D: int, H: int) -> bool:
     return USE_B2B_FWD and bool(_lib.call("mm_expert_b2b_fwd_supported", K1, D, H))
 
 
 def expert_b2b_fwd(f: torch.Tensor, Wp: torch.Tensor, bias1: torch.Tensor, W1: torch.Tensor, bias2: torch.Tensor,
                    Y: torch.Tensor, Z: torch.Tensor, *, plan: DispatchPlan, tile_begin: int, tile_count: int, tag: str = "",
-                   pairs: bool = True):
+                   pairs: bool = True, f_g64=None):
     """Y = ReLU(f Wp_e^T + bias1_e), Z = Y W1_e^T + bias2_e over the tiles of one scale region, in one kernel (Y is not
     re-read).  Wp: stacked [E * D, K1] bf16, W1: stacked [E * H, D] bf16; f / Y / Z start at the region's first row.
     `pairs`: the plan's 256-row segment alignment (plan.SEG_ALIGN) lets CTA pairs share the weight tiles (same results)."""
     _need_cuda(f, Wp, bias1, W1, bias2, Y, Z)
     D, H = Y.shape[1], Z.shape[1]
     E = Wp.shape[0] // D
+    if f_g64 is not None:      # f is the image-order [B * P, K1] tensor, addressed through the group map
+        _lib.call("mm_expert_b2b_fwd_gather", _P(f), f.shape[0], f.shape[1], f.stride(0), _P(Wp), E, D, Wp.stride(0), _P(bias1),
+                  _P(W1), H, W1.stride(0), _P(bias2), _P(plan.tile_info), tile_begin, tile_count, _P(Y), Y.stride(0), _P(Z),
+                  Z.stride(0), 1, _P(f_g64), _st(), label=f"{tag}:expert_b2b[K1={f.shape[1]}]")
+        return Y, Z
     _lib.call("mm_expert_b2b_fwd", _P(f), f.shape[0], f.shape[1], f.stride(0), _P(Wp), E, D, Wp.stride(0), _P(bias1), _P(W1),
               H, W1.stride(0), _P(bias2), _P(plan.tile_info), tile_begin, tile_count, _P(Y), Y.stride(0), _P(Z), Z.stride(0),
               int(pairs and tile_begin % 2 == 0), _st(), label=f"{tag}:expert_b2b[K1={f.shape[1]}]")
@@ -259,10 +297,16 @@ def gemm_rows_rank1(A: torch.Tensor, W: torch.Tensor, N: int, out: torch.Tensor,
 
 
 def gemm_wgrad(A: torch.Tensor, Bm: torch.Tensor, out: torch.Tensor, plan: DispatchPlan, chunk_begin: int,
-               chunk_count: int, tile_base: int, tag: str = "", colsum: Optional[torch.Tensor] = None):
+               chunk_count: int, tile_base: int, tag: str = "", colsum: Optional[torch.Tensor] = None, b_g64=None):
     """out[e] (+)= A_e^T B_e over the rows of expert e; out fp32 [E, N1, N2] must be pre-zeroed.
-    colsum (fp32 [E, N1], pre-zeroed): also accumulate the column sums of A per expert (bias gradient)."""
+    colsum (fp32 [E, N1], pre-zeroed): also accumulate the column sums of A per expert (bias gradient).
+    `b_g64` (group map): Bm is in image order and is addressed through the map (needs colsum, tile_base 0)."""
     _need_cuda(A, Bm, out, colsum)
+    if b_g64 is not None:
+        _lib.call("mm_grouped_gemm_wgrad_colsum_gather", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(Bm), Bm.shape[0],
+                  Bm.shape[1], Bm.stride(0), _P(plan.chunks), chunk_begin, chunk_count, tile_base, _P(out), _P(colsum), _P(b_g64),
+                  _st(), label=f"{tag}:gemm_wgrad[N1={A.shape[1]},N2={Bm.shape[1]}]")
+        return out
     if colsum is None:
         _lib.call("mm_grouped_gemm_wgrad", _P(A), A.shape[0], A.shape[1], A.stride(0), _P(Bm), Bm.shape[0], Bm.shape[1],
                   Bm.stride(0), _P(plan.chunks), chunk_begin, chunk_count, tile_base, _P(out), _st(),

@@ -217,3 +217,36 @@ def test_attn_proj0_gradient_against_storage_aware_oracle():
           f"vs storage-aware oracle {worst['stored']:.4f}")
     assert worst["fp32"] < TIGHT["attn0"]
     assert worst["stored"] < 1e-2      # measured 1.5e-3 (vs 1.9e-2 against the fp32 oracle)
+
+
+def test_finest_scale_addressed_in_image_order_is_bit_identical_to_the_sorted_copy():
+    """Round 2: with top-1 routing and bf16 features the finest stage feature is not permuted — the back-to-back kernel, the conv
+    weight-gradient GEMM and the input-gradient GEMM address the image-order tensors through a 64-row group map
+    (mm_dispatch_group_map, *_gather / *_scatter entry points).  Same operands, same order of accumulation: outputs and every
+    gradient must equal the sorted-copy path bit for bit."""
+    K, Ps, B = 4, [3136, 784, 196, 49], 7
+    params = _bf16_params(K, seed=141)
+    torch.manual_seed(142)
+    feats = [torch.randn(B, p, d).to(torch.bfloat16) for p, d in zip(Ps, HID)]
+    sw, cg = torch.randn(B, D), torch.randn(B, D)
+    cl = (torch.randn(B, D, 56, 56) / 3136).to(torch.bfloat16)
+    results = []
+    for direct in (True, False):
+        ops.USE_DIRECT_FINEST = direct
+        try:
+            moe = _module_from(params, K, HID, D)
+            fg = [f.cuda().requires_grad_(True) for f in feats]
+            gf, lf, probs = moe(fg, sw.cuda())
+            assert moe.last_direct_finest == direct
+            ((gf * cg.cuda()).sum() + (lf.float() * cl.cuda().float()).sum()).backward()
+            results.append((gf.detach().clone(), lf.detach().clone(), [f.grad.clone() for f in fg],
+                            {k: p.grad.clone() for k, p in moe.named_parameters()}))
+        finally:
+            ops.USE_DIRECT_FINEST = True
+    (gf_a, lf_a, df_a, dp_a), (gf_b, lf_b, df_b, dp_b) = results
+    assert torch.equal(gf_a, gf_b) and torch.equal(lf_a, lf_b)
+    for s in range(4):
+        assert torch.equal(df_a[s], df_b[s]), f"d_feat{s}"
+    for k in dp_a:
+        # weight gradients are fp32 red.add reductions over row chunks: the order of the atomic adds is not fixed
+        assert rel_err(dp_a[k].cpu(), dp_b[k].cpu()) < 1e-5 or float(dp_b[k].abs().max()) == 0.0, k
