@@ -55,3 +55,17 @@ def test_compute_call_fails_loudly_without_a_gpu():
         moe([torch.randn(1, 64, 96), torch.randn(1, 16, 192), torch.randn(1, 4, 384), torch.randn(1, 1, 768)], torch.randn(1, 768))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         medmoe_b200.GLORIAGlobalContrastiveLoss()(torch.randn(4, 768), torch.randn(4, 768))
+
+
+def test_epilogue_flag_values_match_the_header():
+    """The Python host layer passes the epilogue flags as plain ints: they must be the header's enum values."""
+    from medmoe_b200 import ops
+    h = open(os.path.join(ROOT, "include", "medmoe_b200.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"(MM_EPI_\w+)\s*=\s*(\d+)", h))
+    assert enum["MM_EPI_RELU"] == ops.EPI_RELU and enum["MM_EPI_ZERO_PAD"] == ops.EPI_ZERO_PAD
+    assert enum["MM_EPI_PAIR_OK"] == ops.EPI_PAIR_OK
+    # and the kernels' own enum (csrc/gemm.cuh)
+    g = open(os.path.join(ROOT, "medmoe_b200", "csrc", "gemm.cuh")).read()
+    kern = dict((k, int(v)) for k, v in re.findall(r"\b(EPI_\w+)\s*=\s*(\d+)", g))
+    for name, val in enum.items():
+        assert kern[name[3:]] == val, name
